@@ -305,6 +305,23 @@ static int findRoot(int id, std::vector<int>& parents) {
   }
 }
 
+// Islands.init/connect/fold (Islands.elm:23-119) over groups given as (id, kind) pairs in CSR order.
+// `connect` is applied in REVERSE group order, as buildAndWarmStart does (Solver.elm:201-206).
+// Returns per-group root and the visiting order: islands by ascending root, groups inside in CSR order.
+static void islandsOrder(int nGroups, const int* id1, const int* kind1, const int* id2, const int* kind2, int maxId,
+                         std::vector<int>& root, std::vector<int>& gorder) {
+  std::vector<int> parents(maxId + 1);
+  for (int i = 0; i <= maxId; i++) parents[i] = i;
+  for (int g = nGroups - 1; g >= 0; g--)
+    if (kind1[g] == 2 && kind2[g] == 2) {   // Islands.connect, Islands.elm:30-46
+      int ra = findRoot(id1[g], parents), rb = findRoot(id2[g], parents);
+      if (ra - rb < 0) parents[rb] = ra; else if (ra - rb > 0) parents[ra] = rb;
+    }
+  root.resize(nGroups); gorder.resize(nGroups);
+  for (int g = 0; g < nGroups; g++) { root[g] = findRoot(kind1[g] == 2 ? id1[g] : id2[g], parents); gorder[g] = g; }
+  std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return root[a] - root[b] < 0; });
+}
+
 // SolverBody.elm:97-225
 static void integrateBody(OBody& b, const SB& s, double dt, V3 gravity) {
   if (b.kind == 1) return;
@@ -391,8 +408,6 @@ static void stepWorld(const ep_shapes* S, const ep_bodies* B, WorldIn& W, const 
   int maxId = -1;
   for (OBody& b : W.bodies) maxId = b.id > maxId ? b.id : maxId;
   std::vector<SB> sb(maxId + 1, SB{0, 0, 0, 0, 0, 0});
-  std::vector<int> parents(maxId + 1);
-  for (int i = 0; i <= maxId; i++) parents[i] = i;
   // buildAndWarmStart walks pairGroups (reverse enumeration order), Solver.elm:122-208
   for (int gi = (int)groups.size() - 1; gi >= 0; gi--) {
     Group& g = groups[gi];
@@ -413,16 +428,15 @@ static void stepWorld(const ep_shapes* S, const ep_bodies* B, WorldIn& W, const 
       applyEquationWarmStart(c.friction1Lambda, c.friction1, *g.b1, *g.b2, s1, s2);
       applyEquationWarmStart(c.friction2Lambda, c.friction2, *g.b1, *g.b2, s1, s2);
     }
-    if (g.b1->kind == 2 && g.b2->kind == 2) {   // Islands.connect, Islands.elm:30-46
-      int ra = findRoot(g.b1->id, parents), rb = findRoot(g.b2->id, parents);
-      if (ra - rb < 0) parents[rb] = ra; else if (ra - rb > 0) parents[ra] = rb;
-    }
   }
-  // Islands.fold, Islands.elm:51-119
-  for (Group& g : groups) g.root = findRoot(g.b1->kind == 2 ? g.b1->id : g.b2->id, parents);
-  std::vector<int> gorder(groups.size());
-  for (size_t i = 0; i < groups.size(); i++) gorder[i] = (int)i;
-  std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return groups[a].root - groups[b].root < 0; });
+  // Islands.connect (inside buildAndWarmStart) + Islands.fold, Islands.elm:30-119
+  std::vector<int> gorder, groot;
+  {
+    std::vector<int> i1, k1, i2, k2;
+    for (Group& g : groups) { i1.push_back(g.b1->id); k1.push_back(g.b1->kind); i2.push_back(g.b2->id); k2.push_back(g.b2->kind); }
+    islandsOrder((int)groups.size(), i1.data(), k1.data(), i2.data(), k2.data(), maxId, groot, gorder);
+    for (size_t i = 0; i < groups.size(); i++) groups[i].root = groot[i];
+  }
   int minRem = W.iterations;
   size_t pos = 0;
   while (pos < gorder.size()) {
@@ -607,4 +621,13 @@ extern "C" int ep_oracle_support_feature(const ep_shapes* S, int shape, const do
   std::vector<V3> v = supportFeature(rd3(axis), a.convex);
   for (size_t i = 0; i < v.size(); i++) wr3(out6 + 3 * i, v[i]);
   return (int)v.size();
+}
+
+// Islands.fold visiting order for the known-answer test tests/SolverIslandsTest.elm:136-163.
+extern "C" int ep_oracle_islands(int32_t n_groups, const int32_t* id1, const int32_t* kind1, const int32_t* id2, const int32_t* kind2,
+                                 int32_t max_id, int32_t* out_root, int32_t* out_order) {
+  std::vector<int> root, order;
+  islandsOrder(n_groups, id1, kind1, id2, kind2, max_id, root, order);
+  for (int g = 0; g < n_groups; g++) { out_root[g] = root[g]; out_order[g] = order[g]; }
+  return EP_OK;
 }
