@@ -1,0 +1,513 @@
+// C ABI of the stepping engine (include/elm_physics_b200.h): context, uploads, the per-step launch
+// sequence, downloads.  Host code here is marshalling + launch plumbing only; all physics is in
+// ep_kernels.cu.  There is no CPU fallback: without a usable CUDA device ep_create fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/elm_physics_b200.h"
+#include "ep_device.cuh"
+
+#include "ep_kernels.cuh"
+
+namespace ep {
+__global__ void k_export_lambda(const RowRec* rows, int n, double* lam, double* t1) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    lam[c] = rows[c].lamN; t1[3 * c] = rows[c].f1J[3]; t1[3 * c + 1] = rows[c].f1J[4]; t1[3 * c + 2] = rows[c].f1J[5];
+  }
+}
+}  // namespace ep
+
+using namespace ep;
+
+struct ep_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<void*> shape_allocs, world_allocs;
+  Dev d{};
+  bool have_shapes = false, have_worlds = false;
+  // host mirrors needed for marshalling
+  std::vector<int32_t> h_sh_kind, h_sh_f64_off, h_sh_i32_off, h_sh_i32;
+  std::vector<double> h_sh_f64;
+  std::vector<int32_t> h_world_body_off, h_body_id, h_iterations;
+  int sm_count = 148;
+  int64_t launches = 0;
+  int64_t stats[EP_STAT_COUNT] = {0};
+};
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                     \
+      return EP_ECUDA;                                                                                   \
+    }                                                                                                    \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(ep_ctx* ctx, std::vector<void*>& pool, T** out, size_t n) {
+  void* p = nullptr;
+  CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  pool.push_back(p);
+  *out = (T*)p;
+  return EP_OK;
+}
+template <typename T>
+static int dev_upload(ep_ctx* ctx, std::vector<void*>& pool, const T** out, const T* src, size_t n) {
+  T* p = nullptr;
+  int rc = dev_alloc(ctx, pool, &p, n);
+  if (rc) return rc;
+  if (n) CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = p;
+  return EP_OK;
+}
+template <typename T>
+static int dev_upload_rw(ep_ctx* ctx, std::vector<void*>& pool, T** out, const T* src, size_t n) {
+  const T* p = nullptr;
+  int rc = dev_upload(ctx, pool, &p, src, n);
+  *out = (T*)p;
+  return rc;
+}
+static void free_pool(std::vector<void*>& pool) {
+  for (void* p : pool) cudaFree(p);
+  pool.clear();
+}
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+extern "C" int ep_create(ep_ctx** out, int device) {
+  if (!out) return EP_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return EP_ENODEVICE;
+  ep_ctx* ctx = new ep_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return EP_ENODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return EP_OK;
+}
+
+extern "C" void ep_destroy(ep_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_pool(ctx->world_allocs);
+  free_pool(ctx->shape_allocs);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* ep_last_error(const ep_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* ep_stream(ep_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int ep_upload_shapes(ep_ctx* ctx, const ep_shapes* S) {
+  if (!ctx || !S || S->n_shapes < 0) return EP_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_pool(ctx->shape_allocs);
+  int ns = S->n_shapes;
+  ctx->h_sh_kind.assign(S->kind, S->kind + ns);
+  ctx->h_sh_f64_off.assign(S->f64_off, S->f64_off + ns + 1);
+  ctx->h_sh_i32_off.assign(S->i32_off, S->i32_off + ns + 1);
+  ctx->h_sh_f64.assign(S->f64, S->f64 + S->f64_off[ns]);
+  ctx->h_sh_i32.assign(S->i32, S->i32 + S->i32_off[ns]);
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_kind, ctx->h_sh_kind.data(), ns));
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_f64_off, ctx->h_sh_f64_off.data(), ns + 1));
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_i32_off, ctx->h_sh_i32_off.data(), ns + 1));
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_f64, ctx->h_sh_f64.data(), ctx->h_sh_f64.size()));
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_i32, ctx->h_sh_i32.data(), ctx->h_sh_i32.size()));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_shapes = true;
+  return EP_OK;
+}
+
+static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
+  auto& pool = ctx->world_allocs;
+  TRY(dev_alloc(ctx, pool, &f.contacts, d.contact_cap));
+  TRY(dev_alloc(ctx, pool, &f.rows, d.contact_cap));
+  TRY(dev_alloc(ctx, pool, &f.slot_row1, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_row2, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &f.slot_cstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_ccount, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &f.slot_jstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_jcount, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &f.slot_ncon, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_root, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &f.hkeys, (size_t)d.hash_mask + 1)); TRY(dev_alloc(ctx, pool, &f.hvals, (size_t)d.hash_mask + 1));
+  TRY(dev_alloc(ctx, pool, &f.cand_base, d.n_worlds)); TRY(dev_alloc(ctx, pool, &f.cand_n, d.n_worlds));
+  TRY(dev_alloc(ctx, pool, &f.counters, CNT_COUNT));
+  CK(cudaMemsetAsync(f.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), ctx->stream));
+  CK(cudaMemsetAsync(f.counters, 0, CNT_COUNT * sizeof(int32_t), ctx->stream));
+  CK(cudaMemsetAsync(f.cand_base, 0, std::max(d.n_worlds, 1) * sizeof(int32_t), ctx->stream));
+  CK(cudaMemsetAsync(f.cand_n, 0, std::max(d.n_worlds, 1) * sizeof(int32_t), ctx->stream));
+  return EP_OK;
+}
+
+static int grid_for(const ep_ctx* ctx, int64_t n, int block, int per_sm) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params* P, const ep_contacts* warm) {
+  if (!ctx || !B || !P) return EP_EINVAL;
+  if (!ctx->have_shapes) { ctx->err = "ep_upload_shapes must be called first"; return EP_ESTATE; }
+  if (B->n_worlds != P->n_worlds) { ctx->err = "bodies/params world count mismatch"; return EP_EINVAL; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_pool(ctx->world_allocs);
+  ctx->have_worlds = false;
+  auto& pool = ctx->world_allocs;
+  Dev& d = ctx->d;
+  const int nw = B->n_worlds, nb = B->n_bodies, ni = B->n_insts;
+  d.n_worlds = nw; d.n_bodies = nb; d.n_insts = ni;
+  for (int w = 0; w < nw; w++)
+    if (P->iterations[w] < 1) { ctx->err = "solverIterations must be >= 1"; return EP_EINVAL; }
+  ctx->h_world_body_off.assign(B->world_body_off, B->world_body_off + nw + 1);
+  ctx->h_body_id.assign(B->body_id, B->body_id + nb);
+  ctx->h_iterations.assign(P->iterations, P->iterations + nw);
+  // bodies
+  TRY(dev_upload(ctx, pool, &d.world_body_off, B->world_body_off, nw + 1));
+  TRY(dev_upload(ctx, pool, &d.body_id, B->body_id, nb));
+  TRY(dev_upload(ctx, pool, &d.kind, B->kind, nb));
+  std::vector<int32_t> body_world(nb), inst_body(ni);
+  int64_t slot_cap = 0;
+  for (int w = 0; w < nw; w++) {
+    int64_t n = B->world_body_off[w + 1] - B->world_body_off[w];
+    slot_cap += n * (n - 1) / 2;
+    for (int r = B->world_body_off[w]; r < B->world_body_off[w + 1]; r++) body_world[r] = w;
+  }
+  if (slot_cap >= (int64_t)1 << 31) { ctx->err = "too many body pairs for 32-bit pair slots"; return EP_ECAPACITY; }
+  for (int r = 0; r < nb; r++) {
+    if (B->body_id[r] < 0 || B->body_id[r] >= 262144) { ctx->err = "body id out of range [0, 2^18)"; return EP_EINVAL; }
+    for (int k = B->inst_off[r]; k < B->inst_off[r + 1]; k++) inst_body[k] = r;
+    if (B->inst_off[r + 1] - B->inst_off[r] > 255) { ctx->err = "more than 255 shapes on a body"; return EP_EINVAL; }
+  }
+  TRY(dev_upload(ctx, pool, &d.body_world, body_world.data(), nb));
+  TRY(dev_upload_rw(ctx, pool, &d.pos, B->pos, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.quat, B->quat, 4 * (size_t)nb));
+  TRY(dev_upload_rw(ctx, pool, &d.vel, B->vel, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.angvel, B->angvel, 3 * (size_t)nb));
+  TRY(dev_upload_rw(ctx, pool, &d.force, B->force, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.torque, B->torque, 3 * (size_t)nb));
+  TRY(dev_upload_rw(ctx, pool, &d.iiw, B->inv_inertia_world, 9 * (size_t)nb));
+  TRY(dev_upload(ctx, pool, &d.inv_mass, B->inv_mass, nb)); TRY(dev_upload(ctx, pool, &d.inv_inertia, B->inv_inertia, 3 * (size_t)nb));
+  TRY(dev_upload(ctx, pool, &d.ldp, B->lin_damp_pow, nb)); TRY(dev_upload(ctx, pool, &d.adp, B->ang_damp_pow, nb));
+  TRY(dev_upload(ctx, pool, &d.lin_lock, B->lin_lock, 3 * (size_t)nb)); TRY(dev_upload(ctx, pool, &d.ang_lock, B->ang_lock, 3 * (size_t)nb));
+  TRY(dev_upload(ctx, pool, &d.radius, B->bounding_radius, nb));
+  TRY(dev_upload(ctx, pool, &d.inst_off, B->inst_off, nb + 1));
+  TRY(dev_upload(ctx, pool, &d.inst_shape, B->inst_shape, ni));
+  TRY(dev_upload(ctx, pool, &d.inst_body, inst_body.data(), ni));
+  TRY(dev_upload(ctx, pool, &d.inst_friction, B->inst_friction, ni));
+  TRY(dev_upload(ctx, pool, &d.inst_bounciness, B->inst_bounciness, ni));
+  TRY(dev_alloc(ctx, pool, &d.pre_pos, 3 * (size_t)nb)); TRY(dev_alloc(ctx, pool, &d.pre_quat, 4 * (size_t)nb));
+  CK(cudaMemcpyAsync(d.pre_pos, d.pos, 3 * (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.pre_quat, d.quat, 4 * (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  // world-placed shape blocks + placement work items (moving bodies first)
+  const int ns = (int)ctx->h_sh_kind.size();
+  std::vector<int64_t> woff(ni);
+  int64_t wtotal = 0;
+  for (int k = 0; k < ni; k++) {
+    int s = B->inst_shape[k];
+    if (s < 0 || s >= ns) { ctx->err = "shape index out of range"; return EP_EINVAL; }
+    woff[k] = wtotal;
+    wtotal += ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s];
+  }
+  std::vector<double> wf(std::max<int64_t>(wtotal, 1));
+  std::vector<int32_t> pl_inst, pl_code;
+  int n_moving = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = 0; k < ni; k++) {
+      bool moving = B->kind[inst_body[k]] != EP_STATIC;
+      if (moving != (pass == 0)) continue;
+      int s = B->inst_shape[k];
+      const double* f = ctx->h_sh_f64.data() + ctx->h_sh_f64_off[s];
+      const int32_t* ib = ctx->h_sh_i32.data() + ctx->h_sh_i32_off[s];
+      if (pass == 0 || true) std::copy(f, f + (ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s]), wf.begin() + woff[k]);
+      auto item = [&](int rel, int dir) { pl_inst.push_back(k); pl_code.push_back(rel * 2 + dir); };
+      switch (ctx->h_sh_kind[s]) {
+        case EP_SPHERE: case EP_PARTICLE: item(0, 0); break;
+        case EP_CAPSULE: case EP_PLANE: item(0, 0); item(3, 1); break;
+        case EP_CONVEX: {
+          int nv = ib[1], ng = ib[2];
+          item(0, 0);
+          if (ib[0]) { item(3, 1); item(6, 1); item(9, 1); }
+          for (int v = 0; v < nv; v++) item(EP_CONVEX_F64_HEADER + 3 * v, 0);
+          for (int g = 0; g < ng; g++) {
+            int base = EP_CONVEX_F64_HEADER + 3 * nv + EP_GROUP_F64 * g;
+            item(base, 1);
+            if (ib[EP_CONVEX_I32_HEADER + EP_GROUP_I32 * g]) item(base + 4, 1);
+          }
+          break;
+        }
+        default: ctx->err = "unknown shape kind"; return EP_EINVAL;
+      }
+    }
+    if (pass == 0) n_moving = (int)pl_inst.size();
+  }
+  d.n_pl_moving = n_moving; d.n_pl_all = (int)pl_inst.size();
+  TRY(dev_upload(ctx, pool, &d.inst_woff, woff.data(), ni));
+  TRY(dev_upload_rw(ctx, pool, &d.wf64, wf.data(), wf.size()));
+  TRY(dev_upload(ctx, pool, &d.pl_inst, pl_inst.data(), pl_inst.size()));
+  TRY(dev_upload(ctx, pool, &d.pl_code, pl_code.data(), pl_code.size()));
+  // params
+  TRY(dev_upload(ctx, pool, &d.gravity, P->gravity, 3 * (size_t)nw));
+  TRY(dev_upload(ctx, pool, &d.dt, P->dt, nw));
+  TRY(dev_upload(ctx, pool, &d.iterations, P->iterations, nw));
+  d.collide = nullptr; d.collide_off = nullptr;
+  if (P->collide) {
+    std::vector<int64_t> off(P->collide_off, P->collide_off + nw);
+    int64_t n_last = B->world_body_off[nw] - B->world_body_off[nw - 1];
+    size_t total = (size_t)(off[nw - 1] + n_last * n_last);
+    TRY(dev_upload(ctx, pool, &d.collide, P->collide, total));
+    TRY(dev_upload(ctx, pool, &d.collide_off, off.data(), nw));
+  }
+  // constraint registrations -> CSR over the registering body row, stable in list order
+  const int ncn = P->n_constraints;
+  d.n_constraints = ncn;
+  {
+    std::vector<int> order(ncn);
+    for (int c = 0; c < ncn; c++) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P->con_body_a[x] < P->con_body_a[y]; });
+    std::vector<int32_t> a_off(nb + 1, 0), cb(ncn), ck(ncn);
+    std::vector<double> cd(24 * (size_t)ncn);
+    for (int c = 0; c < ncn; c++) {
+      int a = P->con_body_a[order[c]], b = P->con_body_b[order[c]];
+      if (a < 0 || a >= nb || b < 0 || b >= nb || body_world[a] != body_world[b]) { ctx->err = "constraint between bodies of different worlds"; return EP_EINVAL; }
+      a_off[a + 1]++;
+      cb[c] = b; ck[c] = P->con_kind[order[c]];
+      std::copy(P->con_data + 24 * (size_t)order[c], P->con_data + 24 * (size_t)order[c] + 24, cd.begin() + 24 * (size_t)c);
+    }
+    for (int r = 0; r < nb; r++) a_off[r + 1] += a_off[r];
+    TRY(dev_upload(ctx, pool, &d.con_a_off, a_off.data(), nb + 1));
+    TRY(dev_upload(ctx, pool, &d.con_b, cb.data(), ncn));
+    TRY(dev_upload(ctx, pool, &d.con_kind, ck.data(), ncn));
+    TRY(dev_upload(ctx, pool, &d.con_data, cd.data(), cd.size()));
+  }
+  // capacities
+  d.slot_cap = std::max<int64_t>(slot_cap, 1);
+  int64_t ccap = std::max<int64_t>(1 << 14, 16 * (int64_t)nb);
+  if (const char* e = getenv("EP_CONTACT_CAP")) ccap = std::max<int64_t>(atoll(e), 64);
+  if (warm && warm->world_group_off) ccap = std::max<int64_t>(ccap, warm->group_contact_off[warm->world_group_off[nw]]);
+  d.contact_cap = (int32_t)std::min<int64_t>(ccap, (1ll << 31) - 64);
+  int64_t h = 1; while (h < 2 * (int64_t)d.contact_cap) h <<= 1;
+  d.hash_mask = (int32_t)(h - 1);
+  d.jrow_cap = 6 * ncn + 8;
+  // scratch
+  TRY(dev_alloc(ctx, pool, &d.sorted, nb)); TRY(dev_alloc(ctx, pool, &d.sort_key, nb));
+  TRY(dev_alloc(ctx, pool, &d.sbv, 6 * (size_t)nb));
+  CK(cudaMemsetAsync(d.sbv, 0, 6 * (size_t)std::max(nb, 1) * sizeof(double), ctx->stream));
+  TRY(dev_alloc(ctx, pool, &d.uf_parent, nb)); TRY(dev_alloc(ctx, pool, &d.uf_count, nb)); TRY(dev_alloc(ctx, pool, &d.uf_fill, nb));
+  TRY(dev_alloc(ctx, pool, &d.isl_off, nb)); TRY(dev_alloc(ctx, pool, &d.isl_cnt, nb)); TRY(dev_alloc(ctx, pool, &d.isl_world, nb));
+  TRY(dev_alloc(ctx, pool, &d.isl_groups, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));
+  CK(cudaMemcpyAsync(d.world_min_rem, P->iterations, nw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d.world_n_islands, 0, std::max(nw, 1) * sizeof(int32_t), ctx->stream));
+  TRY(dev_alloc(ctx, pool, &d.jrows, d.jrow_cap));
+  TRY(dev_alloc(ctx, pool, &d.flags, FLAG_COUNT));
+  CK(cudaMemsetAsync(d.flags, 0, FLAG_COUNT * sizeof(int32_t), ctx->stream));
+  TRY(alloc_frame(ctx, d.cur, d));
+  TRY(alloc_frame(ctx, d.prev, d));
+  // previous frame's contacts = warm-start cache (Physics.elm:528-529, Equation.elm:50-58)
+  if (warm && warm->world_group_off && warm->world_group_off[nw] > 0) {
+    int ng = warm->world_group_off[nw];
+    int nc = warm->group_contact_off[ng];
+    if (ng > d.slot_cap) { ctx->err = "warm-start groups exceed pair capacity"; return EP_ECAPACITY; }
+    std::vector<int32_t> row1(ng), row2(ng), cstart(ng), ccount(ng), zero(ng, 0), neg(ng, -1);
+    std::vector<ContactRec> crec(std::max(nc, 1));
+    std::vector<RowRec> rrec(std::max(nc, 1));
+    memset(crec.data(), 0, crec.size() * sizeof(ContactRec));
+    memset(rrec.data(), 0, rrec.size() * sizeof(RowRec));
+    for (int w = 0; w < nw; w++) {
+      std::unordered_map<int, int> id2row;
+      for (int r = B->world_body_off[w]; r < B->world_body_off[w + 1]; r++) id2row[B->body_id[r]] = r;
+      for (int g = warm->world_group_off[w]; g < warm->world_group_off[w + 1]; g++) {
+        auto a = id2row.find(warm->group_id1[g]), b = id2row.find(warm->group_id2[g]);
+        cstart[g] = warm->group_contact_off[g];
+        ccount[g] = warm->group_contact_off[g + 1] - warm->group_contact_off[g];
+        if (a == id2row.end() || b == id2row.end()) { row1[g] = 0; row2[g] = 0; ccount[g] = 0; continue; }   // body gone: entries never match
+        row1[g] = a->second; row2[g] = b->second;
+        for (int c = cstart[g]; c < cstart[g] + ccount[g]; c++) {
+          crec[c].fk = warm->feature_key[c]; crec[c].sk = warm->shape_key[c]; crec[c].slot = g;
+          rrec[c].lamN = warm->lambda[c];
+          rrec[c].f1J[3] = warm->t1[3 * c]; rrec[c].f1J[4] = warm->t1[3 * c + 1]; rrec[c].f1J[5] = warm->t1[3 * c + 2];
+        }
+      }
+    }
+    FrameBuf& f = d.prev;
+    CK(cudaMemcpyAsync(f.slot_row1, row1.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.slot_row2, row2.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.slot_cstart, cstart.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.slot_ccount, ccount.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.contacts, crec.data(), nc * sizeof(ContactRec), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.rows, rrec.data(), nc * sizeof(RowRec), cudaMemcpyHostToDevice, ctx->stream));
+    k_hash_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+  }
+  // place every shape once (static bodies are never re-placed)
+  if (d.n_pl_all > 0) {
+    k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, ctx->stream>>>(d, d.n_pl_all);
+    CK(cudaGetLastError());
+    // static items sit after the moving ones, so the per-step launch covers [0, n_pl_moving)
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_worlds = true;
+  return EP_OK;
+}
+
+extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
+  if (!ctx || n_steps < 0) return EP_EINVAL;
+  if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
+  CK(cudaSetDevice(ctx->device));
+  Dev& d = ctx->d;
+  cudaStream_t st = ctx->stream;
+  if (d.n_bodies == 0) return EP_OK;
+  const int gw = std::max(1, std::min(d.n_worlds, ctx->sm_count * 16));
+  const int gwide = ctx->sm_count * 8;
+  for (int s = 0; s < n_steps; s++) {
+    CK(cudaMemsetAsync(d.cur.counters, 0, CNT_COUNT * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(d.cur.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), st));
+    if (d.n_pl_moving > 0) k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving);
+    k_sort<<<gw, 128, 0, st>>>(d);
+    k_broadphase<<<gw, 128, 0, st>>>(d);
+    k_narrowphase<<<gwide, 128, 0, st>>>(d);
+    k_equations<<<gwide, 128, 0, st>>>(d);
+    k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d);
+    k_solve<<<gwide, 128, 0, st>>>(d);
+    k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d);
+    CK(cudaGetLastError());
+    ctx->launches += (d.n_pl_moving > 0 ? 8 : 7);
+    std::swap(d.cur, d.prev);     // the frame just computed becomes the warm-start cache
+  }
+  return EP_OK;
+}
+
+static int check_flags(ep_ctx* ctx) {
+  int32_t fl[FLAG_COUNT];
+  CK(cudaMemcpyAsync(fl, ctx->d.flags, sizeof fl, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (fl[FLAG_POOL_OVERFLOW]) { ctx->err = "contact pool overflow (raise EP_CONTACT_CAP)"; return EP_ECAPACITY; }
+  if (fl[FLAG_PAIR_OVERFLOW]) { ctx->err = "pair slot / per-pair contact buffer overflow"; return EP_ECAPACITY; }
+  if (fl[FLAG_POLY_OVERFLOW]) { ctx->err = "clip polygon buffer overflow (face with too many vertices)"; return EP_ECAPACITY; }
+  if (fl[FLAG_JOINT_OVERFLOW]) { ctx->err = "joint row pool overflow"; return EP_ECAPACITY; }
+  return EP_OK;
+}
+
+extern "C" int ep_sync(ep_ctx* ctx) {
+  if (!ctx) return EP_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->have_worlds) return EP_OK;
+  return check_flags(ctx);
+}
+
+extern "C" int ep_download_bodies(ep_ctx* ctx, ep_bodies* B) {
+  if (!ctx || !B) return EP_EINVAL;
+  if (!ctx->have_worlds || B->n_bodies != ctx->d.n_bodies) { ctx->err = "body count mismatch"; return EP_ESTATE; }
+  CK(cudaSetDevice(ctx->device));
+  const Dev& d = ctx->d;
+  size_t nb = d.n_bodies;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(B->pos, d.pos, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->quat, d.quat, 4 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->vel, d.vel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->angvel, d.angvel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->force, d.force, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->torque, d.torque, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->inv_inertia_world, d.iiw, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return check_flags(ctx);
+}
+
+extern "C" int ep_download_contacts(ep_ctx* ctx, ep_contacts* out) {
+  if (!ctx || !out) return EP_EINVAL;
+  if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
+  CK(cudaSetDevice(ctx->device));
+  TRY(check_flags(ctx));
+  const Dev& d = ctx->d;
+  const FrameBuf& f = d.prev;     // last computed frame
+  cudaStream_t st = ctx->stream;
+  const int nw = d.n_worlds;
+  int32_t cnt[CNT_COUNT];
+  CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int ns = cnt[CNT_CAND], nc = cnt[CNT_CONTACTS];
+  std::vector<int32_t> base(nw), num(nw), row1(ns), row2(ns), cstart(ns), ccount(ns), jcount(ns), ncon(ns), root(ns), minrem(nw), nisl(nw);
+  std::vector<ContactRec> crec(std::max(nc, 1));
+  std::vector<double> lam(std::max(nc, 1)), t1(3 * (size_t)std::max(nc, 1)), prepos(3 * (size_t)d.n_bodies), prequat(4 * (size_t)d.n_bodies);
+  double *d_lam = nullptr, *d_t1 = nullptr;
+  CK(cudaMalloc(&d_lam, std::max(nc, 1) * sizeof(double)));
+  CK(cudaMalloc(&d_t1, 3 * (size_t)std::max(nc, 1) * sizeof(double)));
+  if (nc > 0) k_export_lambda<<<grid_for(ctx, nc, 256, 16), 256, 0, st>>>(f.rows, nc, d_lam, d_t1);
+  auto D2H = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  acc(D2H(base.data(), f.cand_base, nw * 4)); acc(D2H(num.data(), f.cand_n, nw * 4));
+  acc(D2H(row1.data(), f.slot_row1, ns * 4)); acc(D2H(row2.data(), f.slot_row2, ns * 4));
+  acc(D2H(cstart.data(), f.slot_cstart, ns * 4)); acc(D2H(ccount.data(), f.slot_ccount, ns * 4));
+  acc(D2H(jcount.data(), f.slot_jcount, ns * 4)); acc(D2H(ncon.data(), f.slot_ncon, ns * 4)); acc(D2H(root.data(), f.slot_root, ns * 4));
+  acc(D2H(minrem.data(), d.world_min_rem, nw * 4)); acc(D2H(nisl.data(), d.world_n_islands, nw * 4));
+  acc(D2H(crec.data(), f.contacts, (size_t)nc * sizeof(ContactRec)));
+  acc(D2H(lam.data(), d_lam, (size_t)nc * 8)); acc(D2H(t1.data(), d_t1, 3 * (size_t)nc * 8));
+  acc(D2H(prepos.data(), d.pre_pos, prepos.size() * 8)); acc(D2H(prequat.data(), d.pre_quat, prequat.size() * 8));
+  acc(cudaStreamSynchronize(st));
+  cudaFree(d_lam); cudaFree(d_t1);
+  if (e != cudaSuccess) { ctx->err = std::string("download: ") + cudaGetErrorString(e); return EP_ECUDA; }
+  // compact the valid pair slots world by world, enumeration order; contacts stay in solver order
+  int64_t ng = 0, nco = 0;
+  for (int w = 0; w < nw; w++)
+    for (int s = base[w]; s < base[w] + num[w]; s++)
+      if (ccount[s] > 0 || jcount[s] > 0) { ng++; nco += std::max(ccount[s], 0); }
+  if (ng > out->group_cap || nco > out->contact_cap) { ctx->err = "ep_contacts capacity too small"; return EP_ECAPACITY; }
+  int g = 0, c = 0;
+  out->n_worlds = nw;
+  for (int w = 0; w < nw; w++) {
+    out->world_group_off[w] = g;
+    int nbw = ctx->h_world_body_off[w + 1] - ctx->h_world_body_off[w];
+    int used = ctx->h_iterations[w] - minrem[w];
+    out->iterations[w] = nbw == 0 ? 0 : (1 - used > 0 ? 1 : used);      // Solver.elm:225-231, 275-276
+    if (out->world_n_islands) out->world_n_islands[w] = nisl[w];
+    for (int s = base[w]; s < base[w] + num[w]; s++) {
+      if (!(ccount[s] > 0 || jcount[s] > 0)) continue;
+      out->group_id1[g] = ctx->h_body_id[row1[s]]; out->group_id2[g] = ctx->h_body_id[row2[s]];
+      if (out->group_n_constraints) out->group_n_constraints[g] = ncon[s] < 0 ? -ncon[s] : ncon[s];
+      if (out->group_island) out->group_island[g] = root[s] >= 0 ? ctx->h_body_id[root[s]] : -1;
+      if (out->group_pre_pos1) {
+        memcpy(out->group_pre_pos1 + 3 * g, prepos.data() + 3 * (size_t)row1[s], 24);
+        memcpy(out->group_pre_quat1 + 4 * g, prequat.data() + 4 * (size_t)row1[s], 32);
+      }
+      out->group_contact_off[g] = c;
+      for (int k = 0; k < std::max(ccount[s], 0); k++, c++) {
+        const ContactRec& r = crec[cstart[s] + k];
+        out->shape_key[c] = r.sk; out->feature_key[c] = r.fk;
+        memcpy(out->ni + 3 * c, r.ni, 24); memcpy(out->pi + 3 * c, r.pi, 24); memcpy(out->pj + 3 * c, r.pj, 24);
+        out->friction[c] = r.friction; out->bounciness[c] = r.bounciness;
+        out->lambda[c] = lam[cstart[s] + k];
+        memcpy(out->t1 + 3 * c, t1.data() + 3 * (size_t)(cstart[s] + k), 24);
+      }
+      g++;
+    }
+  }
+  out->world_group_off[nw] = g;
+  out->group_contact_off[g] = c;
+  ctx->stats[EP_STAT_CANDIDATE_PAIRS] = ns; ctx->stats[EP_STAT_GROUPS] = g; ctx->stats[EP_STAT_CONTACTS] = c;
+  ctx->stats[EP_STAT_ISLANDS] = cnt[CNT_ISLANDS];
+  return EP_OK;
+}
+
+extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_contacts* warm_in, ep_contacts* out, int32_t n_steps) {
+  TRY(ep_upload_worlds(ctx, bodies, params, warm_in));
+  TRY(ep_step_resident(ctx, n_steps));
+  TRY(ep_download_bodies(ctx, bodies));
+  if (out) TRY(ep_download_contacts(ctx, out));
+  return EP_OK;
+}
+
+extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
+  if (!ctx || !out) return EP_EINVAL;
+  ctx->stats[EP_STAT_KERNEL_LAUNCHES] = ctx->launches;
+  for (int i = 0; i < n && i < EP_STAT_COUNT; i++) out[i] = ctx->stats[i];
+  return EP_OK;
+}

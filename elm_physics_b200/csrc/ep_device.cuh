@@ -1,0 +1,85 @@
+// Device-resident data of one context (all worlds concatenated) — see DESIGN.md "Data layout in HBM".
+#pragma once
+#include <stdint.h>
+
+namespace ep {
+
+// One solved contact's geometry + identity: `Contact`/`SolverContact` (src/Internal/Contact.elm:16-33).
+struct ContactRec {
+  int64_t fk;            // featureKey < 2^48 (ContactId.elm:94-96)
+  int32_t sk;            // shapeKey = s1*256+s2 (ContactId.elm:75-77)
+  int32_t slot;          // owning pair slot
+  double ni[3], pi[3], pj[3];
+  double friction, bounciness;
+};
+
+// `ContactEquations` + `ContactData` (src/Internal/Equation.elm:63-93): three Jacobian rows (wA, vB, wB;
+// vA = -vB) and their Spook scalars; min/max normal impulse are the constants 0 / 1e6.
+struct RowRec {
+  double nJ[9], f1J[9], f2J[9];
+  double nB, nInvC, f1B, f1InvC, f2B, f2InvC, eps, mu;
+  double lamN, lamF1, lamF2;
+  double pad;            // 40 doubles = 320 B: rows stay 64 B aligned
+};
+
+// `ConstraintEquation` (src/Internal/Equation.elm:503-511); bounds are the constants -1e6 / 1e6.
+struct JointRow { double J[9]; double B, invC, eps, lam; double pad[3]; };   // 16 doubles
+
+enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_COUNT = 8 };
+enum { FLAG_POOL_OVERFLOW = 0, FLAG_PAIR_OVERFLOW = 1, FLAG_POLY_OVERFLOW = 2, FLAG_JOINT_OVERFLOW = 3, FLAG_COUNT = 4 };
+
+struct FrameBuf {        // double-buffered: the previous frame is the warm-start cache
+  ContactRec* contacts;
+  RowRec* rows;
+  int32_t* slot_row1;    // pair slots: body rows (body1 = lower gravity-sort position)
+  int32_t* slot_row2;
+  int32_t* slot_cstart;  // contacts of the slot, solver order
+  int32_t* slot_ccount;
+  int32_t* slot_jstart;  // joint rows of the slot, solver order
+  int32_t* slot_jcount;
+  int32_t* slot_ncon;    // user constraints carried by the pair
+  int32_t* slot_root;    // island root body row (-1 when the slot is not a pair group)
+  int64_t* hkeys;        // open-addressing table (world << 36 | bodyKey) -> slot
+  int32_t* hvals;
+  int32_t* cand_base;    // [n_worlds] first slot of the world (enumeration order inside)
+  int32_t* cand_n;       // [n_worlds]
+  int32_t* counters;     // [CNT_COUNT]
+};
+
+struct Dev {
+  // shape templates (ep_shapes)
+  const int32_t* sh_kind; const int32_t* sh_f64_off; const int32_t* sh_i32_off; const double* sh_f64; const int32_t* sh_i32;
+  // bodies (ep_bodies)
+  int32_t n_worlds, n_bodies, n_insts;
+  const int32_t* world_body_off; const int32_t* body_id; const int32_t* kind; const int32_t* body_world;
+  double *pos, *quat, *vel, *angvel, *force, *torque, *iiw;
+  const double *inv_mass, *inv_inertia, *ldp, *adp, *lin_lock, *ang_lock, *radius;
+  const int32_t* inst_off; const int32_t* inst_shape; const int32_t* inst_body;
+  const double* inst_friction; const double* inst_bounciness;
+  const int64_t* inst_woff;   // world-placed f64 block of each instance (same layout as its template)
+  double* wf64;
+  double *pre_pos, *pre_quat; // transform3d before the last integration (contactPoints, Physics.elm:1180-1186)
+  // placement work items: (instance, rel offset*2 + isDirection)
+  const int32_t* pl_inst; const int32_t* pl_code; int32_t n_pl_moving; int32_t n_pl_all;
+  // params (ep_params)
+  const double* gravity; const double* dt; const int32_t* iterations;
+  const uint8_t* collide; const int64_t* collide_off;
+  // constraint registrations sorted by (a row, b row): CSR over a
+  int32_t n_constraints; const int32_t* con_a_off; const int32_t* con_b; const int32_t* con_kind; const double* con_data;
+  // scratch
+  int32_t* sorted;            // [n_bodies] world base + gravity-sort position -> body row
+  double* sort_key;           // [n_bodies]
+  double* sbv;                // [n_bodies][6] solver-body delta velocities (SolverBody.elm:16-25)
+  int32_t* uf_parent;         // [n_bodies] union-find over world-local body indices
+  int32_t* uf_count;          // [n_bodies]
+  int32_t* uf_fill;           // [n_bodies]
+  int32_t* isl_off; int32_t* isl_cnt; int32_t* isl_world; int32_t* isl_groups;
+  int32_t* world_min_rem;     // [n_worlds] min over islands of remaining iterations
+  int32_t* world_n_islands;   // [n_worlds]
+  JointRow* jrows;
+  int32_t* flags;             // [FLAG_COUNT]
+  int64_t slot_cap; int32_t contact_cap; int32_t hash_mask; int32_t jrow_cap;
+  FrameBuf cur, prev;
+};
+
+}  // namespace ep

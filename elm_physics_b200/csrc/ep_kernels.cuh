@@ -1,0 +1,681 @@
+// Step kernels for sm_100a (compiled with -fmad=false; see ep_math.cuh).  One launch of each per
+// simulate call, over ALL resident worlds:
+//   k_place       Shape.placeIn of every moving body's shapes            (src/Internal/Shape.elm:94-110)
+//   k_sort        stable gravity sort per world                          (src/Physics.elm:548-573)
+//   k_broadphase  i<j bounding-sphere test, ordered ballot compaction    (src/Internal/BroadPhase.elm:54-215)
+//   k_narrowphase shape matrix per candidate pair                        (src/Internal/NarrowPhase.elm, src/Collision/*)
+//   k_equations   Jacobian rows + Spook scalars + warm-start lookup      (src/Internal/Equation.elm:116-450)
+//   k_islands     union-find (min id root), per-island group lists       (src/Internal/Islands.elm)
+//   k_solve       warm start + PGS per island, reference row order       (src/Internal/Solver.elm:39-880)
+//   k_integrate   SolverBody.solved                                      (src/Internal/SolverBody.elm:97-225)
+#pragma once
+#include "ep_device.cuh"
+#include "ep_narrowphase.cuh"
+
+namespace ep {
+
+constexpr int64_t kHashEmpty = -1;
+constexpr double kMaxImpulse = 1000000.0;      // Equation.elm:459-461
+constexpr double kWarmStartFactor = 0.85;      // Equation.elm:467-469
+
+__device__ __forceinline__ uint32_t hash_mix(int64_t k) {
+  uint64_t x = (uint64_t)k;
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+// ContactId.elm:62-68 with the world index on top (ids < 2^18, worlds < 2^27)
+__device__ __forceinline__ int64_t pair_key(int world, int ida, int idb) {
+  int64_t a = ida, b = idb;
+  int64_t bk = (a - b <= 0) ? a * 262144 + b : b * 262144 + a;
+  return ((int64_t)world << 36) | bk;
+}
+__device__ void hash_insert(const FrameBuf& fb, int mask, int64_t key, int val) {
+  uint32_t h = hash_mix(key) & mask;
+  for (;;) {
+    unsigned long long old = atomicCAS((unsigned long long*)&fb.hkeys[h], (unsigned long long)kHashEmpty, (unsigned long long)key);
+    if (old == (unsigned long long)kHashEmpty || old == (unsigned long long)key) { fb.hvals[h] = val; return; }
+    h = (h + 1) & mask;
+  }
+}
+__device__ int hash_find(const FrameBuf& fb, int mask, int64_t key) {
+  uint32_t h = hash_mix(key) & mask;
+  for (;;) {
+    int64_t k = fb.hkeys[h];
+    if (k == key) return fb.hvals[h];
+    if (k == kHashEmpty) return -1;
+    h = (h + 1) & mask;
+  }
+}
+
+// ---- k_place ------------------------------------------------------------------------------------------
+__global__ void k_place(Dev d, int n_items) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += gridDim.x * blockDim.x) {
+    int inst = d.pl_inst[t], code = d.pl_code[t];
+    int rel = code >> 1;
+    int body = d.inst_body[inst];
+    const double* src = d.sh_f64 + d.sh_f64_off[d.inst_shape[inst]] + rel;
+    double* dst = d.wf64 + d.inst_woff[inst] + rel;
+    Q4 q; q.x = d.quat[4 * body]; q.y = d.quat[4 * body + 1]; q.z = d.quat[4 * body + 2]; q.w = d.quat[4 * body + 3];
+    V3 v = ld3(src);
+    st3(dst, (code & 1) ? rotate(q, v) : point_place(ld3(d.pos + 3 * body), q, v));
+  }
+}
+
+// ---- k_sort : one CTA per world, rank sort == stable sort under the reference comparator ---------------
+__global__ void k_sort(Dev d) {
+  for (int w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
+    int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    V3 g = ld3(d.gravity + 3 * w);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      V3 p = ld3(d.pos + 3 * (r0 + i));
+      d.sort_key[r0 + i] = -(p.x * g.x + p.y * g.y + p.z * g.z);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      double a = d.sort_key[r0 + i];
+      int rank = 0;
+      for (int j = 0; j < n; j++) {
+        double b = d.sort_key[r0 + j];
+        bool lt = b - a < 0, gt = b - a > 0;          // Physics.elm:563-571
+        rank += (lt || (!gt && j < i)) ? 1 : 0;
+      }
+      d.sorted[r0 + rank] = r0 + i;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- k_broadphase -------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_from_index(int64_t p, int n, int& i, int& j) {
+  double t = 2.0 * n - 1.0;
+  int ii = (int)((t - sqrt(t * t - 8.0 * (double)p)) * 0.5);
+  if (ii < 0) ii = 0;
+  while ((int64_t)ii * n - (int64_t)ii * (ii + 1) / 2 > p) ii--;
+  while ((int64_t)(ii + 1) * n - (int64_t)(ii + 1) * (ii + 2) / 2 <= p) ii++;
+  i = ii;
+  j = (int)(p - ((int64_t)ii * n - (int64_t)ii * (ii + 1) / 2)) + ii + 1;
+}
+// constraintsBetween (BroadPhase.elm:144-186): +n forward registrations, -n flipped ones, 0 none
+__device__ int constraints_between(const Dev& d, int r1, int r2) {
+  if (d.n_constraints == 0) return 0;
+  if (d.kind[r1] != 2 && d.kind[r2] != 2) return 0;
+  int n = 0;
+  for (int c = d.con_a_off[r1]; c < d.con_a_off[r1 + 1]; c++) n += d.con_b[c] == r2;
+  if (n > 0) return n;
+  for (int c = d.con_a_off[r2]; c < d.con_a_off[r2 + 1]; c++) n += d.con_b[c] == r1;
+  return -n;
+}
+// bodiesMayContact (BroadPhase.elm:189-215)
+__device__ __forceinline__ bool may_contact(const Dev& d, int w, int r0, int n, int r1, int r2) {
+  double rr = d.radius[r1] + d.radius[r2];
+  double dx = d.pos[3 * r2] - d.pos[3 * r1], dy = d.pos[3 * r2 + 1] - d.pos[3 * r1 + 1], dz = d.pos[3 * r2 + 2] - d.pos[3 * r1 + 2];
+  double dist2 = dx * dx + dy * dy + dz * dz;
+  if (!(rr * rr - dist2 > 0)) return false;
+  if (!(d.kind[r1] == 2 || d.kind[r2] == 2)) return false;
+  if (d.collide) return d.collide[d.collide_off[w] + (int64_t)(r1 - r0) * n + (r2 - r0)] != 0;
+  return true;
+}
+
+__global__ void k_broadphase(Dev d) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
+    int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    int64_t P = (int64_t)n * (n - 1) / 2;
+    // pass A: count candidate pairs
+    int cnt = 0;
+    for (int64_t p = threadIdx.x; p < P; p += blockDim.x) {
+      int i, j; pair_from_index(p, n, i, j);
+      int r1 = d.sorted[r0 + i], r2 = d.sorted[r0 + j];
+      cnt += (may_contact(d, w, r0, n, r1, r2) || constraints_between(d, r1, r2) != 0) ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_warp[wid] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < nwarps; k++) tot += s_warp[k];
+      int base = atomicAdd(&d.cur.counters[CNT_CAND], tot);
+      if ((int64_t)base + tot > d.slot_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 1; tot = 0; base = 0; }
+      d.cur.cand_base[w] = base; d.cur.cand_n[w] = tot;
+      s_base = base;
+      d.world_min_rem[w] = d.iterations[w];
+    }
+    __syncthreads();
+    bool dead = d.cur.cand_n[w] == 0;
+    // pass B: ordered (enumeration order) ballot compaction
+    int running = s_base;
+    for (int64_t p0 = 0; p0 < P && !dead; p0 += blockDim.x) {
+      int64_t p = p0 + threadIdx.x;
+      bool flag = false; int r1 = 0, r2 = 0, ncon = 0; bool may = false;
+      if (p < P) {
+        int i, j; pair_from_index(p, n, i, j);
+        r1 = d.sorted[r0 + i]; r2 = d.sorted[r0 + j];
+        may = may_contact(d, w, r0, n, r1, r2);
+        ncon = constraints_between(d, r1, r2);
+        flag = may || ncon != 0;
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, flag);
+      __syncthreads();
+      if (lane == 0) s_warp[wid] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int k = 0; k < nwarps; k++) { int c = s_warp[k]; if (k < wid) before += c; total += c; }
+      if (flag) {
+        int s = running + before + __popc(bal & ((1u << lane) - 1u));
+        d.cur.slot_row1[s] = r1; d.cur.slot_row2[s] = r2;
+        d.cur.slot_ccount[s] = may ? -1 : 0;      // -1: narrowphase pending
+        d.cur.slot_cstart[s] = 0; d.cur.slot_jcount[s] = 0; d.cur.slot_jstart[s] = 0;
+        d.cur.slot_ncon[s] = ncon; d.cur.slot_root[s] = -1;
+      }
+      running += total;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- k_narrowphase : one thread per candidate pair ------------------------------------------------------
+__device__ __forceinline__ ShapeRef shape_ref(const Dev& d, int inst) {
+  ShapeRef s; int sh = d.inst_shape[inst];
+  s.kind = d.sh_kind[sh]; s.f = d.wf64 + d.inst_woff[inst]; s.ib = d.sh_i32 + d.sh_i32_off[sh];
+  return s;
+}
+
+__global__ void __launch_bounds__(128) k_narrowphase(Dev d) {
+  const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
+  RawContact buf[kMaxPairContacts];
+  TagPt pa[kMaxPoly], pb[kMaxPoly];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    if (d.cur.slot_ccount[s] != -1) continue;
+    int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+    ContactSink sink; sink.buf = buf; sink.n = 0; sink.cap = kMaxPairContacts; sink.overflow = false;
+    bool polyOvf = false;
+    unsigned short sks[kMaxPairContacts];
+    int i1b = d.inst_off[r1], i1e = d.inst_off[r1 + 1], i2b = d.inst_off[r2], i2e = d.inst_off[r2 + 1];
+    for (int a = i1b; a < i1e; a++) {
+      ShapeRef sa = shape_ref(d, a);
+      for (int b = i2b; b < i2e; b++) {
+        int n0 = sink.n;
+        shape_pair_contacts(sa, shape_ref(d, b), sink, pa, pb, polyOvf);
+        // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
+        for (int x = n0, y = sink.n - 1; x < y; x++, y--) { RawContact t = buf[x]; buf[x] = buf[y]; buf[y] = t; }
+        unsigned short sk = (unsigned short)((a - i1b + 1) * 256 + (b - i2b + 1));
+        for (int x = n0; x < sink.n; x++) sks[x] = sk;
+      }
+    }
+    if (sink.overflow) d.flags[FLAG_PAIR_OVERFLOW] = 2;
+    if (polyOvf) d.flags[FLAG_POLY_OVERFLOW] = 1;
+    int n = sink.n, base = 0;
+    if (n > 0) {
+      base = atomicAdd(&d.cur.counters[CNT_CONTACTS], n);
+      if (base + n > d.contact_cap) { d.flags[FLAG_POOL_OVERFLOW] = 1; n = 0; base = 0; }
+    }
+    for (int k = 0; k < n; k++) {
+      ContactRec c;
+      int sk = sks[k];
+      int a = i1b + (sk >> 8) - 1, b = i2b + (sk & 255) - 1;
+      double f1 = d.inst_friction[a], f2 = d.inst_friction[b], b1 = d.inst_bounciness[a], b2 = d.inst_bounciness[b];
+      c.fk = buf[k].fk; c.sk = sk; c.slot = s;
+      c.ni[0] = buf[k].ni.x; c.ni[1] = buf[k].ni.y; c.ni[2] = buf[k].ni.z;
+      c.pi[0] = buf[k].pi.x; c.pi[1] = buf[k].pi.y; c.pi[2] = buf[k].pi.z;
+      c.pj[0] = buf[k].pj.x; c.pj[1] = buf[k].pj.y; c.pj[2] = buf[k].pj.z;
+      c.friction = sqrt(f1 * f2);                         // Material.elm:23-25
+      c.bounciness = (b1 + b2 + eabs(b1 - b2)) * 0.5;     // Material.elm:31-33
+      d.cur.contacts[base + k] = c;
+    }
+    d.cur.slot_cstart[s] = base; d.cur.slot_ccount[s] = n;
+    if (n > 0) hash_insert(d.cur, d.hash_mask, pair_key(d.body_world[r1], d.body_id[r1], d.body_id[r2]), s);
+  }
+}
+
+// ---- k_equations : one thread per pair group --------------------------------------------------------------
+struct BodyK { int kind; double invMass; M33 I; };
+__device__ __forceinline__ BodyK load_bodyk(const Dev& d, int r) {
+  BodyK b; b.kind = d.kind[r]; b.invMass = d.inv_mass[r];
+  const double* m = d.iiw + 9 * r;
+  b.I.m11 = m[0]; b.I.m21 = m[1]; b.I.m31 = m[2]; b.I.m12 = m[3]; b.I.m22 = m[4]; b.I.m32 = m[5]; b.I.m13 = m[6]; b.I.m23 = m[7]; b.I.m33 = m[8];
+  return b;
+}
+struct BodyE { BodyK k; V3 x, v, w, f, tq; Q4 q; };
+__device__ __forceinline__ BodyE load_bodye(const Dev& d, int r) {
+  BodyE b; b.k = load_bodyk(d, r);
+  b.x = ld3(d.pos + 3 * r); b.v = ld3(d.vel + 3 * r); b.w = ld3(d.angvel + 3 * r); b.f = ld3(d.force + 3 * r); b.tq = ld3(d.torque + 3 * r);
+  b.q.x = d.quat[4 * r]; b.q.y = d.quat[4 * r + 1]; b.q.z = d.quat[4 * r + 2]; b.q.w = d.quat[4 * r + 3];
+  return b;
+}
+// J = (wA, vB, wB), Equation.elm:26-36 ; wA = n x ri, vB = n, wB = rj x n (389-400)
+__device__ __forceinline__ void contact_jac(V3 n, V3 ri, V3 rj, double* J) {
+  J[0] = n.y * ri.z - n.z * ri.y; J[1] = n.z * ri.x - n.x * ri.z; J[2] = n.x * ri.y - n.y * ri.x;
+  J[3] = n.x; J[4] = n.y; J[5] = n.z;
+  J[6] = rj.y * n.z - rj.z * n.y; J[7] = rj.z * n.x - rj.x * n.z; J[8] = rj.x * n.y - rj.y * n.x;
+}
+// computeGW, Equation.elm:626-631
+__device__ __forceinline__ double compute_gw(const BodyE& bi, const BodyE& bj, const double* J) {
+  return -(J[3] * bi.v.x + J[4] * bi.v.y + J[5] * bi.v.z)
+         + (J[0] * bi.w.x + J[1] * bi.w.y + J[2] * bi.w.z)
+         + (J[3] * bj.v.x + J[4] * bj.v.y + J[5] * bj.v.z)
+         + (J[6] * bj.w.x + J[7] * bj.w.y + J[8] * bj.w.z);
+}
+// computeGimgt, Equation.elm:612-621
+__device__ __forceinline__ double compute_gimgt(const BodyE& bi, const BodyE& bj, const double* J) {
+  const M33 &I = bi.k.I, &K = bj.k.I;
+  return bi.k.invMass + bj.k.invMass
+         + (J[0] * (I.m11 * J[0] + I.m12 * J[1] + I.m13 * J[2]))
+         + (J[1] * (I.m21 * J[0] + I.m22 * J[1] + I.m23 * J[2]))
+         + (J[2] * (I.m31 * J[0] + I.m32 * J[1] + I.m33 * J[2]))
+         + (J[6] * (K.m11 * J[6] + K.m12 * J[7] + K.m13 * J[8]))
+         + (J[7] * (K.m21 * J[6] + K.m22 * J[7] + K.m23 * J[8]))
+         + (J[8] * (K.m31 * J[6] + K.m32 * J[7] + K.m33 * J[8]));
+}
+// computeGiMf, Equation.elm:583-607
+__device__ __forceinline__ double compute_gimf(V3 gravity, const BodyE& bi, const BodyE& bj, const double* J) {
+  V3 gi = bi.k.kind == 2 ? gravity : mk(0, 0, 0), gj = bj.k.kind == 2 ? gravity : mk(0, 0, 0);
+  const M33 &I = bi.k.I, &K = bj.k.I;
+  return -(J[3] * (bi.k.invMass * bi.f.x + gi.x) + J[4] * (bi.k.invMass * bi.f.y + gi.y) + J[5] * (bi.k.invMass * bi.f.z + gi.z))
+         + (J[3] * (bj.k.invMass * bj.f.x + gj.x) + J[4] * (bj.k.invMass * bj.f.y + gj.y) + J[5] * (bj.k.invMass * bj.f.z + gj.z))
+         + (J[0] * (I.m11 * bi.tq.x + I.m12 * bi.tq.y + I.m13 * bi.tq.z))
+         + (J[1] * (I.m21 * bi.tq.x + I.m22 * bi.tq.y + I.m23 * bi.tq.z))
+         + (J[2] * (I.m31 * bi.tq.x + I.m32 * bi.tq.y + I.m33 * bi.tq.z))
+         + (J[6] * (K.m11 * bj.tq.x + K.m12 * bj.tq.y + K.m13 * bj.tq.z))
+         + (J[7] * (K.m21 * bj.tq.x + K.m22 * bj.tq.y + K.m23 * bj.tq.z))
+         + (J[8] * (K.m31 * bj.tq.x + K.m32 * bj.tq.y + K.m33 * bj.tq.z));
+}
+// computeContactB, Equation.elm:532-546
+__device__ __forceinline__ double compute_contact_b(double spookA, double spookB, double e, V3 pi, V3 pj, V3 ni, const BodyE& bi, const BodyE& bj, const double* J) {
+  double g = ((pj.x - pi.x) * ni.x) + ((pj.y - pi.y) * ni.y) + ((pj.z - pi.z) * ni.z);
+  double gW = (e + 1) * (vdot(bj.v, ni) - vdot(bi.v, ni))
+              + (bj.w.x * J[6] + bj.w.y * J[7] + bj.w.z * J[8])
+              + (bi.w.x * J[0] + bi.w.y * J[1] + bi.w.z * J[2]);
+  return -g * spookA - gW * spookB;
+}
+struct Spook { double a, b, eps; };
+__device__ __forceinline__ Spook spook(double dt) {      // Equation.elm:369-376, 494-501
+  Spook s;
+  s.a = 4.0 / (dt * (1 + 4 * 3.0));
+  s.b = (4.0 * 3.0) / (1 + 4 * 3.0);
+  s.eps = 4.0 / (dt * dt * 10000000.0 * (1 + 4 * 3.0));
+  return s;
+}
+__device__ __forceinline__ void joint_row(JointRow& r, double dt, V3 gravity, const BodyE& b1, const BodyE& b2, double velocityB, double eps) {
+  r.B = velocityB - (dt * compute_gimf(gravity, b1, b2, r.J));     // computeSolverB 520-522
+  r.invC = 1 / (compute_gimgt(b1, b2, r.J) + eps);                 // computeSolverInvC 527-529
+  r.eps = eps; r.lam = 0;
+}
+// point-to-point rows for basis x,y,z (Equation.elm:308-361); writes 3 rows in EMISSION order
+__device__ void p2p_rows(JointRow* out, double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2, V3 pivot1, V3 pivot2) {
+  V3 ri = rotate(b1.q, pivot1), rj = rotate(b2.q, pivot2);
+  for (int a = 0; a < 3; a++) {
+    V3 ni = mk(a == 0 ? 1.0 : 0.0, a == 1 ? 1.0 : 0.0, a == 2 ? 1.0 : 0.0);
+    V3 pi = vadd(b1.x, ri), pj = vadd(b2.x, rj);
+    contact_jac(ni, ri, rj, out[a].J);
+    joint_row(out[a], dt, gravity, b1, b2, compute_contact_b(sp.a, sp.b, 0, pi, pj, ni, b1, b2, out[a].J), sp.eps);
+  }
+}
+// rotational row (Equation.elm:272-305, 549-565)
+__device__ void rot_row(JointRow& r, double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2, V3 ni, V3 nj) {
+  r.J[0] = nj.y * ni.z - nj.z * ni.y; r.J[1] = nj.z * ni.x - nj.x * ni.z; r.J[2] = nj.x * ni.y - nj.y * ni.x;
+  r.J[3] = 0; r.J[4] = 0; r.J[5] = 0;
+  r.J[6] = ni.y * nj.z - ni.z * nj.y; r.J[7] = ni.z * nj.x - ni.x * nj.z; r.J[8] = ni.x * nj.y - ni.y * nj.x;
+  double g = 0 - vdot(ni, nj);
+  double gW = compute_gw(b1, b2, r.J);
+  joint_row(r, dt, gravity, b1, b2, -g * sp.a - gW * sp.b, sp.eps);
+}
+__device__ __forceinline__ int constraint_rows(int kind) { return kind == 0 ? 3 : (kind == 1 ? 5 : (kind == 2 ? 6 : 1)); }
+
+__global__ void __launch_bounds__(128) k_equations(Dev d) {
+  const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    int nc = d.cur.slot_ccount[s], ncon = d.cur.slot_ncon[s];
+    if (nc <= 0 && ncon == 0) continue;
+    int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+    int w = d.body_world[r1];
+    double dt = d.dt[w]; V3 gravity = ld3(d.gravity + 3 * w);
+    Spook sp = spook(dt);
+    BodyE b1 = load_bodye(d, r1), b2 = load_bodye(d, r2);
+    if (nc > 0) {
+      // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128
+      int ps = hash_find(d.prev, d.hash_mask, pair_key(w, d.body_id[r1], d.body_id[r2]));
+      int pc0 = 0, pcn = 0;
+      if (ps >= 0) { pc0 = d.prev.slot_cstart[ps]; pcn = d.prev.slot_ccount[ps]; }
+      int c0 = d.cur.slot_cstart[s];
+      for (int k = 0; k < nc; k++) {
+        const ContactRec& c = d.cur.contacts[c0 + k];
+        // Cache.lookup: first match in pairGroup.contacts order == LAST match in solver order (ContactCache.elm:76-87)
+        double lam = 0; V3 ct1 = mk(0, 0, 0);
+        for (int m = pcn - 1; m >= 0; m--) {
+          const ContactRec& p = d.prev.contacts[pc0 + m];
+          if ((p.fk - c.fk == 0) && (p.sk - c.sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
+        }
+        // contactEquations, Equation.elm:364-450
+        V3 ni = ld3(c.ni), pi = ld3(c.pi), pj = ld3(c.pj);
+        V3 ri = vsub(pi, b1.x), rj = vsub(pj, b2.x);
+        V3 t1, t2; stable_tangents(ct1, ni, t1, t2);
+        RowRec r;
+        contact_jac(ni, ri, rj, r.nJ); contact_jac(t1, ri, rj, r.f1J); contact_jac(t2, ri, rj, r.f2J);
+        r.nB = compute_contact_b(sp.a, sp.b, c.bounciness, pi, pj, ni, b1, b2, r.nJ) - (dt * compute_gimf(gravity, b1, b2, r.nJ));
+        r.nInvC = 1 / (compute_gimgt(b1, b2, r.nJ) + sp.eps);
+        r.f1B = (-compute_gw(b1, b2, r.f1J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f1J));
+        r.f1InvC = 1 / (compute_gimgt(b1, b2, r.f1J) + sp.eps);
+        r.f2B = (-compute_gw(b1, b2, r.f2J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f2J));
+        r.f2InvC = 1 / (compute_gimgt(b1, b2, r.f2J) + sp.eps);
+        r.eps = sp.eps; r.mu = c.friction;
+        r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.pad = 0;
+        d.cur.rows[c0 + k] = r;
+      }
+    }
+    if (ncon != 0) {
+      // addConstraintEquations (Equation.elm:157-361): rows are emitted per constraint in list order and consed,
+      // so the solver order is the reverse of emission: row e of E lands at jstart + E-1-e.
+      bool flipped = ncon < 0;
+      int ra = flipped ? r2 : r1, rb = flipped ? r1 : r2;
+      int E = 0;
+      for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1]; c++) if (d.con_b[c] == rb) E += constraint_rows(d.con_kind[c]);
+      int j0 = atomicAdd(&d.cur.counters[CNT_JROWS], E);
+      if (j0 + E > d.jrow_cap) { d.flags[FLAG_JOINT_OVERFLOW] = 1; E = 0; j0 = 0; }
+      int e = 0;
+      for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1] && E > 0; c++) {
+        if (d.con_b[c] != rb) continue;
+        const double* A = d.con_data + 24 * c;      // registering body's side
+        const double* Bd = A + 12;                   // partner's side
+        const double* s1 = flipped ? Bd : A;         // relativeToCenterOfMassFlipped, Constraint.elm:64-95
+        const double* s2 = flipped ? A : Bd;
+        int kind = d.con_kind[c];
+        JointRow tmp[6];
+        int nr = constraint_rows(kind);
+        if (kind == 3) {                              // Distance, Equation.elm:175-228
+          double half = A[0] / 2;
+          V3 ni = vdirection(b2.x, b1.x);
+          V3 ri = vscale(half, ni), rj = vscale(-half, ni);
+          V3 pi = vadd(ri, b1.x), pj = vadd(rj, b2.x);
+          contact_jac(ni, ri, rj, tmp[0].J);
+          joint_row(tmp[0], dt, gravity, b1, b2, compute_contact_b(sp.a, sp.b, 0, pi, pj, ni, b1, b2, tmp[0].J), sp.eps);
+        } else {
+          p2p_rows(tmp, dt, gravity, sp, b1, b2, ld3(s1), ld3(s2));
+          if (kind == 1) {                            // Hinge, Equation.elm:231-242
+            V3 worldAxis2 = rotate(b2.q, ld3(s2 + 3));
+            V3 n1, n2; tangents(rotate(b1.q, ld3(s1 + 3)), n1, n2);
+            rot_row(tmp[3], dt, gravity, sp, b1, b2, n1, worldAxis2);
+            rot_row(tmp[4], dt, gravity, sp, b1, b2, n2, worldAxis2);
+          } else if (kind == 2) {                     // Lock, Equation.elm:245-269
+            V3 x1 = rotate(b1.q, ld3(s1 + 3)), y1 = rotate(b1.q, ld3(s1 + 6)), z1 = rotate(b1.q, ld3(s1 + 9));
+            V3 x2 = rotate(b2.q, ld3(s2 + 3)), y2 = rotate(b2.q, ld3(s2 + 6)), z2 = rotate(b2.q, ld3(s2 + 9));
+            rot_row(tmp[3], dt, gravity, sp, b1, b2, x1, y2);
+            rot_row(tmp[4], dt, gravity, sp, b1, b2, y1, z2);
+            rot_row(tmp[5], dt, gravity, sp, b1, b2, z1, x2);
+          }
+        }
+        for (int k = 0; k < nr; k++, e++) { tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
+      }
+      d.cur.slot_jstart[s] = j0; d.cur.slot_jcount[s] = E;
+    }
+  }
+}
+
+// ---- k_islands : one thread per world -----------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* parent, int x) {       // Islands.elm:125-145 (path halving)
+  for (;;) {
+    int p = parent[x];
+    if (p == x) return x;
+    int g = parent[p];
+    if (g == p) return p;
+    parent[x] = g;
+    x = g;
+  }
+}
+__global__ void k_islands(Dev d) {
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < d.n_worlds; w += gridDim.x * blockDim.x) {
+    int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    int* parent = d.uf_parent + r0; int* count = d.uf_count + r0; int* fill = d.uf_fill + r0;
+    for (int l = 0; l < n; l++) { parent[l] = l; count[l] = 0; }
+    int s0 = d.cur.cand_base[w], sn = d.cur.cand_n[w];
+    int valid = 0;
+    for (int s = s0 + sn - 1; s >= s0; s--) {           // Islands.connect inside buildAndWarmStart (Solver.elm:201-206)
+      if (d.cur.slot_ccount[s] <= 0 && d.cur.slot_jcount[s] <= 0) continue;
+      valid++;
+      int ra = d.cur.slot_row1[s], rb = d.cur.slot_row2[s];
+      if (d.kind[ra] == 2 && d.kind[rb] == 2) {
+        int a = uf_find(parent, ra - r0), b = uf_find(parent, rb - r0);
+        int ia = d.body_id[r0 + a], ib = d.body_id[r0 + b];   // lower id becomes root (Islands.elm:39-46)
+        if (ia - ib < 0) parent[b] = a; else if (ia - ib > 0) parent[a] = b;
+      }
+    }
+    for (int s = s0; s < s0 + sn; s++) {                // annotate (Islands.elm:68-89)
+      if (d.cur.slot_ccount[s] <= 0 && d.cur.slot_jcount[s] <= 0) { d.cur.slot_root[s] = -1; continue; }
+      int ra = d.cur.slot_row1[s], rb = d.cur.slot_row2[s];
+      int root = uf_find(parent, (d.kind[ra] == 2 ? ra : rb) - r0);
+      d.cur.slot_root[s] = r0 + root;
+      count[root]++;
+    }
+    int nisl = 0;
+    for (int l = 0; l < n; l++) nisl += count[l] > 0;
+    d.world_n_islands[w] = nisl;
+    if (nisl == 0) continue;
+    int ibase = atomicAdd(&d.cur.counters[CNT_ISLANDS], nisl);
+    int gbase = atomicAdd(&d.cur.counters[CNT_ISL_GROUPS], valid);
+    int k = 0, goff = gbase;
+    for (int l = 0; l < n; l++) if (count[l] > 0) {
+      d.isl_off[ibase + k] = goff; d.isl_cnt[ibase + k] = count[l]; d.isl_world[ibase + k] = w;
+      fill[l] = goff; goff += count[l]; k++;
+    }
+    for (int s = s0; s < s0 + sn; s++) {                // groups of an island stay in enumeration order
+      int root = d.cur.slot_root[s];
+      if (root >= 0) d.isl_groups[fill[root - r0]++] = s;
+    }
+  }
+}
+
+// ---- k_solve : one thread per island --------------------------------------------------------------------
+struct SB { double vX, vY, vZ, wX, wY, wZ; };
+__device__ __forceinline__ SB load_sb(const double* p) { SB s; s.vX = p[0]; s.vY = p[1]; s.vZ = p[2]; s.wX = p[3]; s.wY = p[4]; s.wZ = p[5]; return s; }
+__device__ __forceinline__ void store_sb(double* p, const SB& s) { p[0] = s.vX; p[1] = s.vY; p[2] = s.vZ; p[3] = s.wX; p[4] = s.wY; p[5] = s.wZ; }
+// applyVelocityBody1/2 (Solver.elm:505-550) == applyEquationWarmStart (39-85)
+__device__ __forceinline__ void apply_row(double dl, const double* J, const BodyK& k1, const BodyK& k2, SB& s1, SB& s2) {
+  if (k1.kind == 2) {
+    const M33& I = k1.I; double k = dl * k1.invMass;
+    double vX = s1.vX - k * J[3], vY = s1.vY - k * J[4], vZ = s1.vZ - k * J[5];
+    double wX = s1.wX + (I.m11 * J[0] + I.m12 * J[1] + I.m13 * J[2]) * dl;
+    double wY = s1.wY + (I.m21 * J[0] + I.m22 * J[1] + I.m23 * J[2]) * dl;
+    double wZ = s1.wZ + (I.m31 * J[0] + I.m32 * J[1] + I.m33 * J[2]) * dl;
+    s1.vX = vX; s1.vY = vY; s1.vZ = vZ; s1.wX = wX; s1.wY = wY; s1.wZ = wZ;
+  }
+  if (k2.kind == 2) {
+    const M33& I = k2.I; double k = dl * k2.invMass;
+    double vX = s2.vX + k * J[3], vY = s2.vY + k * J[4], vZ = s2.vZ + k * J[5];
+    double wX = s2.wX + (I.m11 * J[6] + I.m12 * J[7] + I.m13 * J[8]) * dl;
+    double wY = s2.wY + (I.m21 * J[6] + I.m22 * J[7] + I.m23 * J[8]) * dl;
+    double wZ = s2.wZ + (I.m31 * J[6] + I.m32 * J[7] + I.m33 * J[8]) * dl;
+    s2.vX = vX; s2.vY = vY; s2.vZ = vZ; s2.wX = wX; s2.wY = wY; s2.wZ = wZ;
+  }
+}
+__device__ __forceinline__ double gw_lambda(const double* J, const SB& b1, const SB& b2) {
+  return -(J[3] * b1.vX + J[4] * b1.vY + J[5] * b1.vZ)
+         + (J[0] * b1.wX + J[1] * b1.wY + J[2] * b1.wZ)
+         + (J[3] * b2.vX + J[4] * b2.vY + J[5] * b2.vZ)
+         + (J[6] * b2.wX + J[7] * b2.wY + J[8] * b2.wZ);
+}
+// velocityNonFrictionGroup (Solver.elm:850-864): joints (572-619) then contact normals (625-672)
+__device__ double sweep_nonfriction(const Dev& d, int s, double tot) {
+  int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+  BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
+  SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
+  int j0 = d.cur.slot_jstart[s], jn = d.cur.slot_jcount[s];
+  for (int k = 0; k < jn; k++) {
+    JointRow& r = d.jrows[j0 + k];
+    double lam = r.lam;
+    double prev = r.invC * (r.B - gw_lambda(r.J, s1, s2) - r.eps * lam);
+    double dl = (lam + prev - (-kMaxImpulse) < 0) ? (-kMaxImpulse) - lam : ((lam + prev - kMaxImpulse > 0) ? kMaxImpulse - lam : prev);
+    apply_row(dl, r.J, k1, k2, s1, s2);
+    r.lam = lam + dl;
+    tot = tot + eabs(dl);
+  }
+  int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
+  for (int k = 0; k < cn; k++) {
+    RowRec& r = d.cur.rows[c0 + k];
+    double lam = r.lamN;
+    double prev = r.nInvC * (r.nB - gw_lambda(r.nJ, s1, s2) - r.eps * lam);
+    double dl = (lam + prev - 0.0 < 0) ? 0.0 - lam : ((lam + prev - kMaxImpulse > 0) ? kMaxImpulse - lam : prev);
+    apply_row(dl, r.nJ, k1, k2, s1, s2);
+    r.lamN = lam + dl;
+    tot = tot + eabs(dl);
+  }
+  if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
+  if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
+  return tot;
+}
+// velocityFrictionGroup / solveVelocityFrictions (Solver.elm:678-844)
+__device__ double sweep_friction(const Dev& d, int s, double tot) {
+  int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
+  if (cn <= 0) return tot;
+  int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+  BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
+  SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
+  const M33 &I1 = k1.I, &I2 = k2.I;
+  for (int k = 0; k < cn; k++) {
+    RowRec& r = d.cur.rows[c0 + k];
+    double nl = r.lamN;
+    const double* e1 = r.f1J;
+    double cap1 = r.mu * nl;
+    double gW1 = gw_lambda(e1, s1, s2);
+    double dPrev1 = r.f1InvC * (r.f1B - gW1 - r.eps * r.lamF1);
+    double d1 = (r.lamF1 + dPrev1 + cap1 < 0) ? -cap1 - r.lamF1 : ((r.lamF1 + dPrev1 - cap1 > 0) ? cap1 - r.lamF1 : dPrev1);
+    double k1a = d1 * k1.invMass;
+    double b1vX = s1.vX - k1a * e1[3], b1vY = s1.vY - k1a * e1[4], b1vZ = s1.vZ - k1a * e1[5];
+    double b1wX = s1.wX + (I1.m11 * e1[0] + I1.m12 * e1[1] + I1.m13 * e1[2]) * d1;
+    double b1wY = s1.wY + (I1.m21 * e1[0] + I1.m22 * e1[1] + I1.m23 * e1[2]) * d1;
+    double b1wZ = s1.wZ + (I1.m31 * e1[0] + I1.m32 * e1[1] + I1.m33 * e1[2]) * d1;
+    double k1b = d1 * k2.invMass;
+    double b2vX = s2.vX + k1b * e1[3], b2vY = s2.vY + k1b * e1[4], b2vZ = s2.vZ + k1b * e1[5];
+    double b2wX = s2.wX + (I2.m11 * e1[6] + I2.m12 * e1[7] + I2.m13 * e1[8]) * d1;
+    double b2wY = s2.wY + (I2.m21 * e1[6] + I2.m22 * e1[7] + I2.m23 * e1[8]) * d1;
+    double b2wZ = s2.wZ + (I2.m31 * e1[6] + I2.m32 * e1[7] + I2.m33 * e1[8]) * d1;
+    const double* e2 = r.f2J;
+    double cap2 = r.mu * nl;
+    double gW2 = -(e2[3] * b1vX + e2[4] * b1vY + e2[5] * b1vZ)
+                 + (e2[0] * b1wX + e2[1] * b1wY + e2[2] * b1wZ)
+                 + (e2[3] * b2vX + e2[4] * b2vY + e2[5] * b2vZ)
+                 + (e2[6] * b2wX + e2[7] * b2wY + e2[8] * b2wZ);
+    double dPrev2 = r.f2InvC * (r.f2B - gW2 - r.eps * r.lamF2);
+    double d2 = (r.lamF2 + dPrev2 + cap2 < 0) ? -cap2 - r.lamF2 : ((r.lamF2 + dPrev2 - cap2 > 0) ? cap2 - r.lamF2 : dPrev2);
+    if (k1.kind == 2) {
+      double k2a = d2 * k1.invMass;
+      s1.vX = b1vX - k2a * e2[3]; s1.vY = b1vY - k2a * e2[4]; s1.vZ = b1vZ - k2a * e2[5];
+      s1.wX = b1wX + (I1.m11 * e2[0] + I1.m12 * e2[1] + I1.m13 * e2[2]) * d2;
+      s1.wY = b1wY + (I1.m21 * e2[0] + I1.m22 * e2[1] + I1.m23 * e2[2]) * d2;
+      s1.wZ = b1wZ + (I1.m31 * e2[0] + I1.m32 * e2[1] + I1.m33 * e2[2]) * d2;
+    }
+    if (k2.kind == 2) {
+      double k2b = d2 * k2.invMass;
+      s2.vX = b2vX + k2b * e2[3]; s2.vY = b2vY + k2b * e2[4]; s2.vZ = b2vZ + k2b * e2[5];
+      s2.wX = b2wX + (I2.m11 * e2[6] + I2.m12 * e2[7] + I2.m13 * e2[8]) * d2;
+      s2.wY = b2wY + (I2.m21 * e2[6] + I2.m22 * e2[7] + I2.m23 * e2[8]) * d2;
+      s2.wZ = b2wZ + (I2.m31 * e2[6] + I2.m32 * e2[7] + I2.m33 * e2[8]) * d2;
+    }
+    r.lamF1 = r.lamF1 + d1;
+    r.lamF2 = r.lamF2 + d2;
+    tot = tot + eabs(d1) + eabs(d2);
+  }
+  if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
+  if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
+  return tot;
+}
+
+__global__ void __launch_bounds__(128) k_solve(Dev d) {
+  const int total = d.cur.counters[CNT_ISLANDS];
+  for (int isl = blockIdx.x * blockDim.x + threadIdx.x; isl < total; isl += gridDim.x * blockDim.x) {
+    int g0 = d.isl_off[isl], gn = d.isl_cnt[isl], w = d.isl_world[isl];
+    // warm start in reverse enumeration order (buildAndWarmStart walks pairGroups, Solver.elm:122-208)
+    for (int gi = gn - 1; gi >= 0; gi--) {
+      int s = d.isl_groups[g0 + gi];
+      int cn = d.cur.slot_ccount[s];
+      if (cn <= 0) continue;
+      int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+      BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
+      SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
+      int c0 = d.cur.slot_cstart[s];
+      for (int k = 0; k < cn; k++) {
+        const RowRec& r = d.cur.rows[c0 + k];
+        if (r.lamN == 0) continue;                      // Solver.elm:41
+        apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
+      }
+      if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
+      if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
+    }
+    int remaining = d.iterations[w], rem;
+    for (;;) {
+      double p1 = 0, p2;
+      for (int gi = 0; gi < gn; gi++) p1 = sweep_nonfriction(d, d.isl_groups[g0 + gi], p1);
+      // solve2Body keeps ONE running sum through both phases (Solver.elm:473-489); step adds two sums (345-358)
+      p2 = (gn == 1) ? p1 : 0;
+      for (int gi = 0; gi < gn; gi++) p2 = sweep_friction(d, d.isl_groups[g0 + gi], p2);
+      double deltaTot = (gn == 1) ? p2 : p1 + p2;
+      if (remaining == 1) { rem = 0; break; }
+      if (deltaTot - kSolverTolerance < 0) { rem = remaining - 1; break; }
+      remaining--;
+    }
+    atomicMin(&d.world_min_rem[w], rem);
+  }
+}
+
+// ---- k_integrate : one thread per body (SolverBody.elm:97-225) ---------------------------------------------
+__global__ void k_integrate(Dev d) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < d.n_bodies; r += gridDim.x * blockDim.x) {
+    int kind = d.kind[r];
+    double* sb = d.sbv + 6 * r;
+    SB s = load_sb(sb);
+    sb[0] = 0; sb[1] = 0; sb[2] = 0; sb[3] = 0; sb[4] = 0; sb[5] = 0;
+    V3 x = ld3(d.pos + 3 * r);
+    Q4 q; q.x = d.quat[4 * r]; q.y = d.quat[4 * r + 1]; q.z = d.quat[4 * r + 2]; q.w = d.quat[4 * r + 3];
+    st3(d.pre_pos + 3 * r, x);
+    d.pre_quat[4 * r] = q.x; d.pre_quat[4 * r + 1] = q.y; d.pre_quat[4 * r + 2] = q.z; d.pre_quat[4 * r + 3] = q.w;
+    if (kind == 1) continue;
+    int w = d.body_world[r];
+    double dt = d.dt[w];
+    V3 v = ld3(d.vel + 3 * r), om = ld3(d.angvel + 3 * r);
+    V3 step_v, step_w;
+    if (kind == 3) { step_v = v; step_w = om; }
+    else {
+      V3 g = ld3(d.gravity + 3 * w), f = ld3(d.force + 3 * r), tq = ld3(d.torque + 3 * r);
+      double im = d.inv_mass[r], ld = d.ldp[r], ad = d.adp[r];
+      V3 ll = ld3(d.lin_lock + 3 * r), al = ld3(d.ang_lock + 3 * r);
+      const double* m = d.iiw + 9 * r;   // m11,m21,m31,m12,m22,m32,m13,m23,m33
+      V3 nv = mk(((g.x + f.x * im) * dt + v.x * ld + s.vX) * ll.x, ((g.y + f.y * im) * dt + v.y * ld + s.vY) * ll.y, ((g.z + f.z * im) * dt + v.z * ld + s.vZ) * ll.z);
+      double vl = vlen(nv), br = d.radius[r];
+      step_v = ((vl == 0) || (br == 0) || (vl * dt - br < 0)) ? nv : vscale(br / (vl * dt), nv);
+      V3 nw = mk(((m[0] * tq.x + m[3] * tq.y + m[6] * tq.z) * dt + om.x * ad + s.wX) * al.x,
+                 ((m[1] * tq.x + m[4] * tq.y + m[7] * tq.z) * dt + om.y * ad + s.wY) * al.y,
+                 ((m[2] * tq.x + m[5] * tq.y + m[8] * tq.z) * dt + om.z * ad + s.wZ) * al.z);
+      step_w = nw;
+      st3(d.vel + 3 * r, nv); st3(d.angvel + 3 * r, nw);
+    }
+    // rotateBy (Transform3d.elm:368-376), translateBy, normalize (256-262)
+    V3 a = mk(step_w.x * dt, step_w.y * dt, step_w.z * dt);
+    double nqx = q.x + (a.x * q.w + a.y * q.z - a.z * q.y) * 0.5;
+    double nqy = q.y + (a.y * q.w + a.z * q.x - a.x * q.z) * 0.5;
+    double nqz = q.z + (a.z * q.w + a.x * q.y - a.y * q.x) * 0.5;
+    double nqw = q.w + (-a.x * q.x - a.y * q.y - a.z * q.z) * 0.5;
+    V3 nx = vadd(mk(step_v.x * dt, step_v.y * dt, step_v.z * dt), x);
+    double len = sqrt(nqx * nqx + nqy * nqy + nqz * nqz + nqw * nqw);
+    Q4 nq; nq.x = nqx / len; nq.y = nqy / len; nq.z = nqz / len; nq.w = nqw / len;
+    st3(d.pos + 3 * r, nx);
+    d.quat[4 * r] = nq.x; d.quat[4 * r + 1] = nq.y; d.quat[4 * r + 2] = nq.z; d.quat[4 * r + 3] = nq.w;
+    if (kind == 2) {
+      M33 I = inv_inertia_world(nq, ld3(d.inv_inertia + 3 * r));
+      double* m = d.iiw + 9 * r;
+      m[0] = I.m11; m[1] = I.m21; m[2] = I.m31; m[3] = I.m12; m[4] = I.m22; m[5] = I.m32; m[6] = I.m13; m[7] = I.m23; m[8] = I.m33;
+    }
+    d.force[3 * r] = 0; d.force[3 * r + 1] = 0; d.force[3 * r + 2] = 0;
+    d.torque[3 * r] = 0; d.torque[3 * r + 1] = 0; d.torque[3 * r + 2] = 0;
+  }
+}
+
+// warm-start upload helper: (re)build the hash of a frame from its slots
+__global__ void k_hash_slots(Dev d, FrameBuf fb, int n_slots) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+    if (fb.slot_ccount[s] <= 0) continue;
+    int r1 = fb.slot_row1[s], r2 = fb.slot_row2[s];
+    hash_insert(fb, d.hash_mask, pair_key(d.body_world[r1], d.body_id[r1], d.body_id[r2]), s);
+  }
+}
+
+}  // namespace ep

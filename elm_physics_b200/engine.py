@@ -1,0 +1,127 @@
+"""ctypes binding of the product library `csrc/libelm_physics_b200.so` (C ABI: include/elm_physics_b200.h)
+plus the `simulate` glue that mirrors `Physics.simulate` (reference: src/Physics.elm:522-583).
+
+There is NO CPU path here: if the CUDA library is missing or no GPU is usable, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libelm_physics_b200.so")
+_LIB = None
+
+EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
+           "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream")
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                              "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.ep_last_error.restype = C.c_char_p
+        lib.ep_stream.restype = C.c_void_p
+        lib.ep_destroy.restype = None
+        for name in EXPORTS:
+            getattr(lib, name)
+        _LIB = lib
+    return _LIB
+
+
+class Engine:
+    """One ep_ctx on one CUDA device."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.ep_create(C.byref(self.ctx), C.c_int(device))
+        if rc != 0:
+            raise EngineError(f"ep_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+        self._keep = []
+
+    def close(self):
+        if self.ctx:
+            self.lib.ep_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed with {rc}: {self.lib.ep_last_error(self.ctx).decode()}")
+
+    def upload_shapes(self, shapes):
+        self._ck(self.lib.ep_upload_shapes(self.ctx, C.byref(shapes.c)), "ep_upload_shapes")
+
+    def upload_worlds(self, bodies, params, warm=None):
+        self._ck(self.lib.ep_upload_worlds(self.ctx, C.byref(bodies.c), C.byref(params.c),
+                                           C.byref(warm.c) if warm is not None else None), "ep_upload_worlds")
+
+    def step_resident(self, n_steps=1):
+        self._ck(self.lib.ep_step_resident(self.ctx, C.c_int32(n_steps)), "ep_step_resident")
+
+    def sync(self):
+        self._ck(self.lib.ep_sync(self.ctx), "ep_sync")
+
+    def download_bodies(self, bodies):
+        self._ck(self.lib.ep_download_bodies(self.ctx, C.byref(bodies.c)), "ep_download_bodies")
+
+    def download_contacts(self, contacts):
+        self._ck(self.lib.ep_download_contacts(self.ctx, C.byref(contacts.c)), "ep_download_contacts")
+
+    def step(self, bodies, params, warm=None, out=None, n_steps=1):
+        self._ck(self.lib.ep_step(self.ctx, C.byref(bodies.c), C.byref(params.c),
+                                  C.byref(warm.c) if warm is not None else None,
+                                  C.byref(out.c) if out is not None else None, C.c_int32(n_steps)), "ep_step")
+
+    def stats(self):
+        out = np.zeros(abi.EP_STAT_COUNT, np.int64)
+        self._ck(self.lib.ep_stats(self.ctx, out.ctypes.data_as(C.POINTER(C.c_int64)), abi.EP_STAT_COUNT), "ep_stats")
+        return dict(kernel_launches=int(out[0]), candidate_pairs=int(out[1]), groups=int(out[2]),
+                    contacts=int(out[3]), islands=int(out[4]))
+
+    def stream_handle(self):
+        return self.lib.ep_stream(self.ctx)
+
+    # ---- Physics.simulate (src/Physics.elm:522-583) for one world ---------------------------------
+    def simulate(self, config, bodies_with_ids):
+        from . import pack
+        from . import physics as P
+        with_ids, _max_id = P.assign_ids(list(bodies_with_ids))
+        if not with_ids:
+            return [], P.Contacts(packed=None, iterations=0, bodies=[])
+        shapes, bodies, params = pack.pack_worlds([(config, with_ids)])
+        warm = None
+        if config.contacts is not None and config.contacts.packed is not None:
+            warm = pack.contacts_from_world_dicts([config.contacts.packed])
+        n = bodies.n_bodies
+        out = abi.Contacts(1, n * (n - 1) // 2 + 1, 16 * n + 64)
+        self.upload_shapes(shapes)
+        self.step(bodies, params, warm, out, 1)
+        new_bodies = pack.unpack_bodies(bodies, [(config, with_ids)])[0]
+        packed = pack.contacts_world_dict(out, 0)
+        return new_bodies, P.Contacts(packed=packed, iterations=packed["iterations"], bodies=new_bodies)
+
+
+_DEFAULT = None
+
+
+def default_engine():
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = Engine(0)
+    return _DEFAULT

@@ -1,0 +1,233 @@
+"""Synthetic inputs for the BASELINE.json configs, built with the host-side mirror of the
+reference's constructors.  Deterministic: SplitMix64 seeded with 0xE1F0 ^ (config << 32) ^ world index.
+Small scenes are lists of (Config, [(ext_id, Body)]); the batched C3 scene is generated directly as
+packed arrays (vectorised placement of template bodies) because 270k Python Body values would take minutes.
+"""
+import math
+
+import numpy as np
+
+from . import abi
+from . import math3d as m3
+from . import pack
+from . import physics as P
+
+MATERIALS = (P.wood, P.rubber, P.steel, P.ice, P.plastic)
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    """Vectorised SplitMix64 finaliser over uint64 arrays."""
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = x
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def uniforms(seed, shape):
+    """Uniform [0,1) doubles, counter-based: element k of stream `seed`."""
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        ctr = (np.uint64(seed) + np.arange(n, dtype=np.uint64) * np.uint64(0xD1342543DE82EF95)) & _M64
+    bits = splitmix64(splitmix64(ctr))
+    return ((bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)).reshape(shape)
+
+
+def scene_seed(config, world=0):
+    return 0xE1F0 ^ (config << 32) ^ world
+
+
+def random_quaternions(u):
+    """Shoemake: u (n,3) uniforms -> unit quaternions (n,4) x,y,z,w."""
+    s1, s2 = np.sqrt(1.0 - u[:, 0]), np.sqrt(u[:, 0])
+    a, b = 2 * math.pi * u[:, 1], 2 * math.pi * u[:, 2]
+    q = np.stack([s1 * np.sin(a), s1 * np.cos(a), s2 * np.sin(b), s2 * np.cos(b)], axis=1)
+    return q / np.sqrt((q * q).sum(axis=1, keepdims=True))
+
+
+# ---- C1: README scene (README.md:9-19) ---------------------------------------------------------------
+def readme_scene():
+    ball = P.move_to((0, 0, 5), P.sphere(0.5, P.rubber))
+    floor = P.plane(P.wood)
+    bodies, _ = P.assign_ids([("ball", ball), ("floor", floor)])
+    return [(P.on_earth(), bodies)]
+
+
+# ---- C2: 100 unit wood boxes at rest: 2-D pyramid base 13 (91 boxes) + 9-box stack ---------------------
+def boxes_scene(iterations=20):
+    bodies = [("floor", P.plane(P.wood))]
+    k = 0
+    for row in range(13):
+        for i in range(13 - row):
+            bodies.append((f"p{k}", P.move_to((i + 0.5 * row, 0.0, row + 0.5), P.block((1, 1, 1), P.wood))))
+            k += 1
+    for j in range(9):
+        bodies.append((f"s{j}", P.move_to((20.0, 0.0, j + 0.5), P.block((1, 1, 1), P.wood))))
+    cfg = P.on_earth()
+    cfg.solver_iterations = iterations
+    with_ids, _ = P.assign_ids(bodies)
+    return [(cfg, with_ids)]
+
+
+def stack_scene(n=5, iterations=7):
+    """sandbox/src/Stability/Scenarios.elm style stack of n unit boxes on a plane."""
+    bodies = [("floor", P.plane(P.wood))]
+    for j in range(n):
+        bodies.append((f"b{j}", P.move_to((0.0, 0.0, j + 0.5), P.block((1, 1, 1), P.wood))))
+    cfg = P.on_earth()
+    cfg.solver_iterations = iterations
+    with_ids, _ = P.assign_ids(bodies)
+    return [(cfg, with_ids)]
+
+
+# ---- C3: batched mixed worlds ---------------------------------------------------------------------------
+MIXED_KINDS = ("block", "sphere", "capsule", "cylinder")
+
+
+def _mixed_template(kind, mat):
+    if kind == "block":
+        return P.block((1, 1, 1), mat)
+    if kind == "sphere":
+        return P.sphere(0.5, mat)
+    if kind == "capsule":
+        return P.capsule(0.3, 1.0, mat)
+    return P.cylinder(0.5, 1.0, mat)
+
+
+def _qmul(a, b):
+    """Transform3d.mul (Transform3d.elm:406-412), vectorised: a (n,4), b (4,)."""
+    ax, ay, az, aw = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+    bx, by, bz, bw = b
+    return np.stack([ax * bw + ay * bz - az * by + aw * bx, -ax * bz + ay * bw + az * bx + aw * by,
+                     ax * by - ay * bx + az * bw + aw * bz, -ax * bx - ay * by - az * bz + aw * bw], axis=1)
+
+
+def _qrot(q, v):
+    """Transform3d.rotate (Transform3d.elm:415-432), vectorised: q (n,4), v (3,)."""
+    qx, qy, qz, qw = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    x, y, z = v
+    ix, iy, iz = 2 * (qy * z - qz * y), 2 * (qz * x - qx * z), 2 * (qx * y - qy * x)
+    return np.stack([x + qw * ix + qy * iz - qz * iy, y + qw * iy + qz * ix - qx * iz, z + qw * iz + qx * iy - qy * ix], axis=1)
+
+
+def _iiw(q, inv):
+    """Transform3d.invertedInertiaRotateIn (Transform3d.elm:181-205, 334-345), vectorised -> (n,9) m11,m21,m31,m12.."""
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    m11, m12, m13 = 1 - 2 * y * y - 2 * z * z, 2 * x * y - 2 * w * z, 2 * x * z + 2 * w * y
+    m21, m22, m23 = 2 * x * y + 2 * w * z, 1 - 2 * x * x - 2 * z * z, 2 * y * z - 2 * w * x
+    m31, m32, m33 = 2 * x * z - 2 * w * y, 2 * y * z + 2 * w * x, 1 - 2 * x * x - 2 * y * y
+    a, b, c = inv[:, 0], inv[:, 1], inv[:, 2]
+    return np.stack([
+        m11 * m11 * a + m12 * m12 * b + m13 * m13 * c, m21 * m11 * a + m22 * m12 * b + m23 * m13 * c,
+        m31 * m11 * a + m32 * m12 * b + m33 * m13 * c, m11 * m21 * a + m12 * m22 * b + m13 * m23 * c,
+        m21 * m21 * a + m22 * m22 * b + m23 * m23 * c, m31 * m21 * a + m32 * m22 * b + m33 * m23 * c,
+        m11 * m31 * a + m12 * m32 * b + m13 * m33 * c, m21 * m31 * a + m22 * m32 * b + m23 * m33 * c,
+        m31 * m31 * a + m32 * m32 * b + m33 * m33 * c], axis=1)
+
+
+def mixed_worlds(n_worlds, bodies_per_world=32, first_world=0, dt=1 / 60, iterations=20, config=3):
+    """C3: each world = wood plane + `bodies_per_world` dynamic bodies cycling block / sphere r0.5 / capsule
+    r0.3 l1 / 12-gon cylinder r0.5 l1, materials cycling wood/rubber/steel/ice/plastic, on a 4x4xL grid
+    (spacing 1.5 m, z0 = 1.0 + 1.5*layer), jitter +-0.1 m, uniformly random orientation.
+    Worlds are indexed first_world .. first_world+n_worlds-1 so shards of a batch are reproducible.
+    Returns packed (Shapes, Bodies, Params)."""
+    nb = bodies_per_world
+    table = pack.ShapeTable()
+    floor = P.plane(P.wood)
+    templates = {}
+    for k in MIXED_KINDS:
+        for mi, mat in enumerate(MATERIALS):
+            templates[(k, mi)] = _mixed_template(k, mat)
+    floor_shape = table.add(floor.shapes[0][0])
+    shape_of = {k: table.add(templates[(k, 0)].shapes[0][0]) for k in MIXED_KINDS}
+    per = nb + 1
+    n = n_worlds * per
+    kind_idx = np.arange(nb) % 4
+    mat_idx = np.arange(nb) % 5
+    tb = [templates[(MIXED_KINDS[kind_idx[i]], int(mat_idx[i]))] for i in range(nb)]
+
+    def col(fn, width):
+        one = np.array([fn(floor)] + [fn(b) for b in tb], dtype=np.float64).reshape(per, width)
+        return np.tile(one, (n_worlds, 1))
+
+    f = {}
+    f["inv_mass"] = col(lambda b: [b.inv_mass], 1)[:, 0]
+    f["inv_inertia"] = col(lambda b: b.inv_inertia, 3)
+    f["lin_damp_pow"] = col(lambda b: [(1.0 - b.linear_damping) ** dt], 1)[:, 0]
+    f["ang_damp_pow"] = col(lambda b: [(1.0 - b.angular_damping) ** dt], 1)[:, 0]
+    f["lin_lock"] = col(lambda b: b.linear_lock, 3)
+    f["ang_lock"] = col(lambda b: b.angular_lock, 3)
+    f["bounding_radius"] = col(lambda b: [b.bounding_sphere_radius], 1)[:, 0]
+    for name in ("vel", "angvel", "force", "torque"):
+        f[name] = np.zeros((n, 3))
+    # placement: body frame (origin, q) composed with each template's centre-of-mass frame
+    gi = np.arange(nb)
+    grid = np.stack([(gi % 4) * 1.5, ((gi // 4) % 4) * 1.5, 1.0 + 1.5 * (gi // 16)], axis=1)
+    pos = np.zeros((n_worlds, per, 3))
+    quat = np.zeros((n_worlds, per, 4))
+    quat[:, :, 3] = 1.0
+    iiw = np.zeros((n_worlds, per, 9))
+    world_ids = np.arange(first_world, first_world + n_worlds, dtype=np.uint64)
+    seeds = np.array([scene_seed(config, int(w)) for w in world_ids], dtype=np.uint64)
+    for i in range(nb):
+        with np.errstate(over="ignore"):
+            base = splitmix64(seeds + np.uint64(i) * np.uint64(0x2545F4914F6CDD1D))
+        uu = np.stack([((splitmix64(base + np.uint64(j)) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0) for j in range(6)], axis=1)
+        origin = grid[i] + (uu[:, 0:3] * 2.0 - 1.0) * 0.1
+        q = random_quaternions(uu[:, 3:6])
+        com_p, com_q = tb[i].center_of_mass_transform3d
+        pos[:, i + 1, :] = origin + _qrot(q, com_p)          # Transform3d.placeIn (Transform3d.elm:222-230)
+        qq = _qmul(q, com_q)
+        quat[:, i + 1, :] = qq
+        iiw[:, i + 1, :] = _iiw(qq, np.tile(np.array(tb[i].inv_inertia), (n_worlds, 1)))
+    fm = floor.inv_inertia_world
+    iiw[:, 0, :] = [fm[k] for k in pack.M_KEYS]
+    pos[:, 0, :] = floor.transform3d[0]
+    quat[:, 0, :] = floor.transform3d[1]
+    f["pos"], f["quat"], f["inv_inertia_world"] = pos.reshape(n, 3), quat.reshape(n, 4), iiw.reshape(n, 9)
+    body_id = np.tile(np.arange(per, dtype=np.int32), n_worlds)
+    kind = np.tile(np.array([1] + [2] * nb, dtype=np.int32), n_worlds)
+    inst_shape = np.tile(np.array([floor_shape] + [shape_of[MIXED_KINDS[k]] for k in kind_idx], dtype=np.int32), n_worlds)
+    fr = np.tile(np.array([P.wood.friction] + [MATERIALS[m].friction for m in mat_idx]), n_worlds)
+    bo = np.tile(np.array([P.wood.bounciness] + [MATERIALS[m].bounciness for m in mat_idx]), n_worlds)
+    bodies = abi.Bodies(np.arange(n_worlds + 1, dtype=np.int32) * per, body_id, kind, np.arange(n + 1, dtype=np.int32),
+                        inst_shape, fr, bo, **f)
+    params = abi.Params(np.tile(np.array([0.0, 0.0, -P.GEE]), (n_worlds, 1)), np.full(n_worlds, dt),
+                        np.full(n_worlds, iterations, np.int32))
+    return table.build(), bodies, params
+
+
+# ---- small mixed world built from Body values (tests: every shape kind, compound, kinematic, particle) ---
+def small_mixed_world(seed=1, n=12, with_extras=True):
+    rng = np.random.RandomState(seed)
+    bodies = [("floor", P.plane(P.wood))]
+    for i in range(n):
+        mat = MATERIALS[i % 5]
+        kind = i % 6
+        if kind == 0:
+            b = P.block((1.0, 0.8, 0.6), mat)
+        elif kind == 1:
+            b = P.sphere(0.45, mat)
+        elif kind == 2:
+            b = P.capsule(0.3, 1.0, mat)
+        elif kind == 3:
+            b = P.cylinder(0.5, 1.0, mat)
+        elif kind == 4:
+            b = P.cone(0.5, 1.0, mat)
+        else:
+            b = P.dynamic([(P.shape_block((0.6, 0.6, 0.6), center=(-0.5, 0, 0)), mat),
+                           (P.shape_sphere(0.35, center=(0.5, 0, 0)), mat)])
+        q = rng.normal(size=4)
+        q = q / np.linalg.norm(q)
+        origin = ((i % 3) * 1.1 + rng.uniform(-0.1, 0.1), ((i // 3) % 2) * 1.1 + rng.uniform(-0.1, 0.1), 0.8 + 0.9 * (i // 6) + rng.uniform(-0.1, 0.1))
+        bodies.append((f"b{i}", P.place_quaternion(origin, tuple(float(c) for c in q), b)))
+    if with_extras:
+        bodies.append(("pm", P.point_mass((0.5, 0.5, 3.5), 2.0, P.steel)))
+        lift = P.kinematic([(P.shape_block((1.5, 1.5, 0.2)), P.steel)])
+        lift = P.set_velocity_to((0, 0, 0.3), P.move_to((4.0, 0.0, 0.5), lift))
+        bodies.append(("lift", lift))
+        bodies.append(("rider", P.move_to((4.0, 0.0, 1.2), P.block((0.5, 0.5, 0.5), P.wood))))
+    with_ids, _ = P.assign_ids(bodies)
+    return [(P.on_earth(), with_ids)]
