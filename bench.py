@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — body-steps/s of the hot path behind Physics.simulate on BASELINE.json config 3
+(8192 independent worlds x 32 mixed dynamic bodies + a plane, per GPU; worlds sharded by index).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement on all host threads
+
+A "step" is one simulate call over every resident world (sort, broadphase, narrowphase, rows + warm start,
+islands, PGS, integrate).  `value` is the device-timed whole-job throughput with state resident in HBM;
+`e2e` is the same metric through the host-buffer C-ABI call (ep_step_frame: H2D of the bodies' state, one step,
+D2H of the state + the frame's contacts, every step).  The oracle (oracle/, test infrastructure) is used here
+only as the cpu_baseline / --impl reference leg and as the parity checker of the timed run.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "body_steps_per_sec"
+UNIT = "body-steps/s"
+BODIES_PER_WORLD = 32
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ---- algorithmic HBM bytes per launch of each kernel (DESIGN.md "Kernels"; SURVEY §8d per-unit figures) ----------
+def kernel_bytes(name, c):
+    nb, nd, K, P, G = c["bodies"], c["dynamic_bodies"], c["contacts"], c["candidate_pairs"], c["groups"]
+    table = {
+        # read pos+quat (56 B) per moving body, write the placed shape block (avg `placed_f64` doubles) per body
+        "k_place": nd * (56 + 8 * c["placed_f64_per_body"]),
+        # read pos (24 B) + write key (8) + read keys + write perm (4)
+        "k_sort": nb * (24 + 8 + 8 + 4),
+        # per body: pos, radius, kind (36 B); per candidate: 8 slot words (32 B)
+        "k_broadphase": nb * 36 + P * 32,
+        # per candidate: 2 placed shape blocks read; per contact: ContactRec written (104 B)
+        "k_narrowphase": P * 2 * 8 * c["placed_f64_per_body"] + K * 104,
+        # per group: 2 bodies x 41 doubles; per contact: ContactRec read (104) + warm-start read (56) + RowRec written (320)
+        "k_equations": G * 2 * 328 + K * (104 + 56 + 320),
+        # per candidate slot: rows/kinds/counts (20 B) read, root written (4), island list (4)
+        "k_islands": P * 28 + nb * 12,
+        # per contact: RowRec read once (320 B) + 3 lambdas written (24 B); per dynamic body: delta-v read+write (96 B)
+        "k_solve": K * 344 + nd * 96,
+        # 512 B per body-step (336 read + 176 written)
+        "k_integrate": nb * 512,
+    }
+    return table[name]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self._stop_evt = [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as ex:  # noqa: BLE001
+            self.err = str(ex)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def oracle_run(shapes, bodies, params, warm, steps, threads):
+    """`steps` oracle steps over all worlds of `bodies`, worlds split evenly over `threads` OS threads
+    (ctypes releases the GIL; the restatement is single-threaded per world like the reference).
+    Returns (seconds, [(Bodies, Contacts)] per chunk)."""
+    from elm_physics_b200 import abi, pack
+    from oracle import binding as oracle
+    import helpers as H
+    oracle.lib()
+    nw = bodies.n_worlds
+    threads = max(1, min(threads, nw))
+    cuts = [nw * i // threads for i in range(threads + 1)]
+    chunks = []
+    for i in range(threads):
+        b = bodies.slice_worlds(cuts[i], cuts[i + 1])
+        p = abi.slice_params(params, cuts[i], cuts[i + 1])
+        w = None
+        if warm is not None:
+            w = pack.contacts_from_world_dicts([pack.contacts_world_dict(warm, k) for k in range(cuts[i], cuts[i + 1])])
+        chunks.append([b, p, w, H.contacts_for(b)])
+    def work(c):
+        oracle.step(shapes, c[0], c[1], c[2], c[3], steps)
+    ts = [threading.Thread(target=work, args=(c,)) for c in chunks]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0, chunks, cuts
+
+
+def run_reference(args, rank, world_size):
+    """--impl reference: the CPU restatement of the reference's own path (the reference is pure Elm and cannot be
+    built here: no elm/node), all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from elm_physics_b200 import scenes
+    cores = host_threads()
+    sample_worlds = min(args.worlds, 64 * cores)
+    shapes, bodies, params = scenes.mixed_worlds(sample_worlds)
+    import helpers as H
+    from elm_physics_b200 import pack
+    # pre-roll on the CPU (untimed) so the timed steps see the same settled regime as the GPU arm
+    _, chunks, cuts = oracle_run(shapes, bodies, params, None, args.preroll, cores)
+    state = [(c[0], c[1], c[3]) for c in chunks]
+
+    spare = [H.contacts_for(b) for b, _, _ in state]      # ping-pong output buffers: no allocation in the timed loop
+
+    def pass_(n):
+        from oracle import binding as oracle
+        def work(i):
+            b, p, w = state[i]
+            oracle.step(shapes, b, p, w, spare[i], n)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(state))]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        for i in range(len(state)):
+            b, p, w = state[i]
+            state[i], spare[i] = (b, p, spare[i]), w
+        return dt
+
+    for _ in range(args.warmup):
+        pass_(1)
+    total = 0.0
+    for _ in range(args.steps):
+        total += pass_(1)
+    body_steps = sample_worlds * BODIES_PER_WORLD * args.steps
+    value = body_steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: independent worlds x (32 mixed dynamic bodies + plane), 20 iterations, dt 1/60",
+                   "worlds_per_step": sample_worlds, "bodies_per_world": BODIES_PER_WORLD, "preroll_steps": args.preroll},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_worlds} worlds x {args.steps} steps after {args.preroll} pre-roll steps, "
+                                   f"{cores} threads (C++ restatement of the Elm path; elm/node absent)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=8192, help="worlds per GPU (weak scaling)")
+    ap.add_argument("--preroll", type=int, default=120, help="untimed steps that drop and pile the bodies first")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world_size, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from elm_physics_b200 import abi, engine as eng, pack, scenes
+    import helpers as H
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    W = args.worlds
+    shapes, bodies, params = scenes.mixed_worlds(W, first_world=rank * W)     # shard = contiguous world-index range
+    e = eng.Engine(local_rank)
+    e.upload_shapes(shapes)
+    e.upload_worlds(bodies, params, None)
+    e.step_resident(args.preroll)
+    e.sync()
+    for _ in range(args.warmup):
+        e.step_resident(1)
+    e.sync()
+    # snapshot of the state the timed region starts from (for the CPU baseline + parity check)
+    start_bodies = bodies.copy()
+    e.download_bodies(start_bodies)
+    start_contacts = H.contacts_for(bodies)
+    e.download_contacts(start_contacts)
+    counts0 = e.stats()
+
+    stream = torch.cuda.ExternalStream(e.stream_handle(), device=torch.device("cuda", local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    launches0 = e.stats()["kernel_launches"]
+    e.profile(True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record(stream)
+    e.step_resident(args.steps)
+    ev1.record(stream)
+    e.sync()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ktimes = e.kernel_times()
+    e.profile(False)
+    launches = e.stats()["kernel_launches"] - launches0
+    end_bodies = bodies.copy()
+    e.download_bodies(end_bodies)
+    end_contacts = H.contacts_for(bodies)
+    e.download_contacts(end_contacts)
+    counts = e.stats()
+
+    n_dyn = W * BODIES_PER_WORLD
+    body_steps_all = n_dyn * args.steps * world_size
+    value = body_steps_all / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call, one frame per call --------------------------------------
+    eb = end_bodies.copy()
+    eo = H.contacts_for(eb)
+    warm = end_contacts
+    h2d = d2h = 0
+    barrier()
+    e.step(eb, params, warm, eo, 1)       # untimed warm-up of the host path
+    warm = eo
+    t_e2e = 0.0
+    for _ in range(args.e2e_steps):
+        eo2 = H.contacts_for(eb)
+        barrier()
+        t0 = time.perf_counter()
+        e.step(eb, params, warm, eo2, 1)
+        t_e2e += max_over_ranks(time.perf_counter() - t0)
+        h2d = eb.nbytes_in() + warm.n_contacts * 56 + warm.n_groups * 12
+        d2h = eb.nbytes_out() + eo2.n_contacts * 160 + eo2.n_groups * 80
+        warm = eo2
+    e2e_value = n_dyn * args.e2e_steps * world_size / t_e2e
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C3: independent worlds x (32 mixed dynamic bodies + plane), 20 iterations, dt 1/60",
+                   "worlds_per_gpu": W, "bodies_per_world": BODIES_PER_WORLD, "preroll_steps": args.preroll,
+                   "sharding": "contiguous world-index range per rank, no data-path collective",
+                   "l2": "resident state (bodies + contacts + rows) exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": args.e2e_steps, "call": "ep_step(host buffers, n_steps=1), contacts fed back from the host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if rank == 0:
+        # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region) ------------
+        dom = max(ktimes, key=lambda k: ktimes[k][0])
+        total_k = sum(v[0] for v in ktimes.values())
+        c = {"bodies": bodies.n_bodies, "dynamic_bodies": n_dyn, "contacts": (counts0["contacts"] + counts["contacts"]) / 2,
+             "candidate_pairs": (counts0["candidate_pairs"] + counts["candidate_pairs"]) / 2,
+             "groups": (counts0["groups"] + counts["groups"]) / 2,
+             "placed_f64_per_body": float(shapes.f64_off[-1] - shapes.f64_off[1]) / 4.0}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dur_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
+        ach = kernel_bytes(dom, c) / (dur_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                            "avg_launch_ms": dur_ms, "share_of_step": ktimes[dom][0] / total_k if total_k else None}
+        line["kernels"] = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1], "share": v[0] / total_k if total_k else None,
+                               "algorithmic_GBps": kernel_bytes(k, c) / (max(v[0], 1e-9) / max(v[1], 1) * 1e-3) / 1e9}
+                           for k, v in ktimes.items()}
+        line["workload_counts"] = {k: c[k] for k in ("bodies", "contacts", "candidate_pairs", "groups")}
+        line["workload_counts"]["islands"] = counts["islands"]
+        # ---- CPU baseline on a bounded sample of the same timed steps + parity of the timed run (N=1 only) -----
+        if world_size == 1 and not args.no_cpu_baseline:
+            cores = host_threads()
+            sample = min(W, max(cores * 8, 64))
+            sb = start_bodies.slice_worlds(0, sample)
+            sp = abi.slice_params(params, 0, sample)
+            sw = pack.contacts_from_world_dicts([pack.contacts_world_dict(start_contacts, k) for k in range(sample)])
+            secs, chunks, cuts = oracle_run(shapes, sb, sp, sw, args.steps, cores)
+            cpu_value = sample * BODIES_PER_WORLD * args.steps / secs
+            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"worlds [0,{sample}) of the timed state x {args.steps} steps, {cores} threads"}
+            exact = True
+            for i, ch in enumerate(chunks):
+                r0, r1 = int(bodies.world_body_off[cuts[i]]), int(bodies.world_body_off[cuts[i + 1]])
+                for name in abi.BODY_INOUT:
+                    exact = exact and getattr(end_bodies, name)[r0:r1].tobytes() == getattr(ch[0], name).tobytes()
+            line["parity"] = {"worlds": sample, "steps": args.steps, "bit_exact_vs_oracle": bool(exact)}
+        print(json.dumps(line), flush=True)
+    e.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

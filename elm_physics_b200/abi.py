@@ -14,6 +14,7 @@ EP_STATIC, EP_DYNAMIC, EP_KINEMATIC = 1, 2, 3
 EP_POINT_TO_POINT, EP_HINGE, EP_LOCK, EP_DISTANCE = 0, 1, 2, 3
 EP_CONVEX_F64_HEADER, EP_CONVEX_I32_HEADER, EP_GROUP_F64, EP_GROUP_I32, EP_EDGE_I32 = 15, 4, 8, 5, 2
 EP_STAT_COUNT = 8
+EP_K_COUNT = 8
 
 _pi32 = C.POINTER(C.c_int32)
 _pi64 = C.POINTER(C.c_int64)
@@ -107,6 +108,14 @@ class Bodies:
                       self.inst_friction, self.inst_bounciness,
                       **{name: getattr(self, name) for name, _ in BODY_F64_FIELDS})
 
+    def slice_worlds(self, w0, w1):
+        """Worlds [w0, w1) as an independent Bodies (rows, instances and offsets rebased)."""
+        r0, r1 = int(self.world_body_off[w0]), int(self.world_body_off[w1])
+        i0, i1 = int(self.inst_off[r0]), int(self.inst_off[r1])
+        return Bodies(self.world_body_off[w0:w1 + 1] - r0, self.body_id[r0:r1], self.kind[r0:r1],
+                      self.inst_off[r0:r1 + 1] - i0, self.inst_shape[i0:i1], self.inst_friction[i0:i1],
+                      self.inst_bounciness[i0:i1], **{name: getattr(self, name)[r0:r1] for name, _ in BODY_F64_FIELDS})
+
     def state_bytes(self):
         """In/out state as one byte string (for bit-exact comparisons)."""
         return b"".join(getattr(self, n).tobytes() for n in BODY_INOUT)
@@ -141,6 +150,12 @@ class Params:
 CONTACT_FIELDS = (("shape_key", np.int32, 1), ("feature_key", np.int64, 1), ("ni", np.float64, 3),
                   ("pi", np.float64, 3), ("pj", np.float64, 3), ("friction", np.float64, 1),
                   ("bounciness", np.float64, 1), ("lambda_", np.float64, 1), ("t1", np.float64, 3))
+
+
+def slice_params(p, w0, w1):
+    """Worlds [w0, w1) of a Params without callbacks/constraints (batched scenes)."""
+    assert p.collide is None and p.n_constraints == 0
+    return Params(p.gravity[w0:w1], p.dt[w0:w1], p.iterations[w0:w1])
 
 
 class Contacts:

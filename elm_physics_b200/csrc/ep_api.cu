@@ -37,6 +37,14 @@ struct ep_ctx {
   std::vector<int32_t> h_world_body_off, h_body_id, h_iterations;
   int sm_count = 148;
   int64_t launches = 0;
+  // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Pending { int kernel; cudaEvent_t a, b; };
+  std::vector<Pending> ev_pending;
+  double k_ms[EP_K_COUNT] = {0};
+  int64_t k_launches[EP_K_COUNT] = {0};
   int64_t stats[EP_STAT_COUNT] = {0};
 };
 
@@ -102,6 +110,7 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_pool(ctx->world_allocs);
   free_pool(ctx->shape_allocs);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -358,6 +367,58 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   return EP_OK;
 }
 
+static cudaEvent_t next_event(ep_ctx* ctx) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    ctx->ev_pool.push_back(e);
+  }
+  return ctx->ev_pool[ctx->ev_used++];
+}
+// Launch bracket: when profiling, every kernel gets its own start/end event on the context's stream.
+struct Timed {
+  ep_ctx* ctx; int kernel; cudaEvent_t a = nullptr;
+  Timed(ep_ctx* c, int k) : ctx(c), kernel(k) {
+    ctx->launches++; ctx->k_launches[k]++;
+    if (ctx->profiling && ctx->ev_pending.size() < (1u << 16)) { a = next_event(ctx); if (a) cudaEventRecord(a, ctx->stream); }
+  }
+  ~Timed() {
+    if (!a) return;
+    cudaEvent_t b = next_event(ctx);
+    if (b) { cudaEventRecord(b, ctx->stream); ctx->ev_pending.push_back({kernel, a, b}); }
+  }
+};
+static void resolve_events(ep_ctx* ctx) {     // stream must be idle
+  for (auto& p : ctx->ev_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->k_ms[p.kernel] += ms;
+  }
+  ctx->ev_pending.clear();
+  ctx->ev_used = 0;
+}
+
+extern "C" int ep_profile(ep_ctx* ctx, int enable) {
+  if (!ctx) return EP_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  resolve_events(ctx);
+  ctx->profiling = enable != 0;
+  for (int i = 0; i < EP_K_COUNT; i++) { ctx->k_ms[i] = 0; ctx->k_launches[i] = 0; }
+  return EP_OK;
+}
+extern "C" int ep_kernel_times(ep_ctx* ctx, double* ms, int64_t* launches, int32_t n) {
+  if (!ctx) return EP_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  resolve_events(ctx);
+  for (int i = 0; i < n && i < EP_K_COUNT; i++) { if (ms) ms[i] = ctx->k_ms[i]; if (launches) launches[i] = ctx->k_launches[i]; }
+  return EP_OK;
+}
+extern "C" const char* ep_kernel_name(int32_t k) {
+  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate"};
+  return (k >= 0 && k < EP_K_COUNT) ? names[k] : "";
+}
+
 extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   if (!ctx || n_steps < 0) return EP_EINVAL;
   if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
@@ -370,16 +431,15 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   for (int s = 0; s < n_steps; s++) {
     CK(cudaMemsetAsync(d.cur.counters, 0, CNT_COUNT * sizeof(int32_t), st));
     CK(cudaMemsetAsync(d.cur.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), st));
-    if (d.n_pl_moving > 0) k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving);
-    k_sort<<<gw, 128, 0, st>>>(d);
-    k_broadphase<<<gw, 128, 0, st>>>(d);
-    k_narrowphase<<<gwide, 128, 0, st>>>(d);
-    k_equations<<<gwide, 128, 0, st>>>(d);
-    k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d);
-    k_solve<<<gwide, 128, 0, st>>>(d);
-    k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d);
+    if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
+    { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
+    { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }
+    { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d); }
+    { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
+    { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d); }
+    { Timed t(ctx, EP_K_SOLVE); k_solve<<<gwide, 128, 0, st>>>(d); }
+    { Timed t(ctx, EP_K_INTEGRATE); k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d); }
     CK(cudaGetLastError());
-    ctx->launches += (d.n_pl_moving > 0 ? 8 : 7);
     std::swap(d.cur, d.prev);     // the frame just computed becomes the warm-start cache
   }
   return EP_OK;

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libelm_physics_b200.so")
 _LIB = None
 
 EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
-           "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream")
+           "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream",
+           "ep_profile", "ep_kernel_times", "ep_kernel_name")
 
 
 class EngineError(RuntimeError):
@@ -31,6 +32,7 @@ def load_library():
         lib = C.CDLL(LIB_PATH)
         lib.ep_last_error.restype = C.c_char_p
         lib.ep_stream.restype = C.c_void_p
+        lib.ep_kernel_name.restype = C.c_char_p
         lib.ep_destroy.restype = None
         for name in EXPORTS:
             getattr(lib, name)
@@ -93,6 +95,17 @@ class Engine:
         self._ck(self.lib.ep_stats(self.ctx, out.ctypes.data_as(C.POINTER(C.c_int64)), abi.EP_STAT_COUNT), "ep_stats")
         return dict(kernel_launches=int(out[0]), candidate_pairs=int(out[1]), groups=int(out[2]),
                     contacts=int(out[3]), islands=int(out[4]))
+
+    def profile(self, enable=True):
+        self._ck(self.lib.ep_profile(self.ctx, C.c_int(1 if enable else 0)), "ep_profile")
+
+    def kernel_times(self):
+        """{kernel name: (accumulated ms, launches)} since the last profile() call."""
+        n = abi.EP_K_COUNT
+        ms, cnt = np.zeros(n, np.float64), np.zeros(n, np.int64)
+        self._ck(self.lib.ep_kernel_times(self.ctx, ms.ctypes.data_as(C.POINTER(C.c_double)),
+                                          cnt.ctypes.data_as(C.POINTER(C.c_int64)), n), "ep_kernel_times")
+        return {self.lib.ep_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     def stream_handle(self):
         return self.lib.ep_stream(self.ctx)

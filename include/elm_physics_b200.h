@@ -195,6 +195,14 @@ int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_co
 int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n);   /* see EP_STAT_* */
 enum { EP_STAT_KERNEL_LAUNCHES = 0, EP_STAT_CANDIDATE_PAIRS = 1, EP_STAT_GROUPS = 2, EP_STAT_CONTACTS = 3,
        EP_STAT_ISLANDS = 4, EP_STAT_SOLVE_NS = 5, EP_STAT_COUNT = 8 };
+/* Per-kernel device timing.  ep_profile(ctx, 1) makes ep_step_resident bracket every kernel launch with
+ * CUDA events on the context's stream and resets the accumulators; ep_kernel_times synchronises and returns
+ * the accumulated milliseconds and launch counts per kernel kind (EP_K_*).  Launch counts are always kept. */
+enum { EP_K_PLACE = 0, EP_K_SORT = 1, EP_K_BROADPHASE = 2, EP_K_NARROWPHASE = 3, EP_K_EQUATIONS = 4, EP_K_ISLANDS = 5,
+       EP_K_SOLVE = 6, EP_K_INTEGRATE = 7, EP_K_COUNT = 8 };
+int ep_profile(ep_ctx* ctx, int enable);
+int ep_kernel_times(ep_ctx* ctx, double* ms_out, int64_t* launches_out, int32_t n);
+const char* ep_kernel_name(int32_t kernel);
 /* Raw CUDA stream handle (cudaStream_t) so callers can record CUDA events on it. */
 void* ep_stream(ep_ctx* ctx);
 

@@ -397,8 +397,8 @@ static void stepWorld(const ep_shapes* S, const ep_bodies* B, WorldIn& W, const 
         for (auto& r : W.regs[order[i]]) if (r.first == order[j]) g.constraints.push_back(r.second);
         if (g.constraints.empty())
           for (auto& r : W.regs[order[j]]) if (r.first == order[i]) {
-            ConstraintIn c = r.second; ConstraintIn f = c;
-            memcpy(f.side1, c.side2, sizeof f.side1); memcpy(f.side2, c.side1, sizeof f.side2);
+            ConstraintIn c = r.second; ConstraintIn f = c;   // relativeToCenterOfMassFlipped, Constraint.elm:64-95
+            if (c.kind != EP_DISTANCE) { memcpy(f.side1, c.side2, sizeof f.side1); memcpy(f.side2, c.side1, sizeof f.side2); }   // Distance length -> Distance length
             g.constraints.push_back(f);
           }
       }

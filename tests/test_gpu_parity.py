@@ -1,0 +1,241 @@
+"""GPU parity tests proper: the CUDA path through the C ABI (include/elm_physics_b200.h) against the
+CPU oracle (oracle/, test infrastructure) on the same seeded inputs.  The bar is BIT-EXACT for the whole
+state and the whole contact block (pair sets, island roots, keys, ni/pi/pj, lambdas, iteration counts),
+which implies the north-star's <= 1e-9 per-step fp64 tolerance; `max_rel_dev` is reported for the record.
+
+Reference behaviour under test: src/Physics.elm:522-583 (simulate), src/Internal/BroadPhase.elm,
+src/Internal/NarrowPhase.elm + src/Collision/*.elm, src/Internal/Equation.elm, src/Internal/Islands.elm,
+src/Internal/Solver.elm, src/Internal/SolverBody.elm.
+"""
+import numpy as np
+import pytest
+
+from elm_physics_b200 import abi
+from elm_physics_b200 import pack
+from elm_physics_b200 import physics as P
+from elm_physics_b200 import scenes
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9   # north_star per-step relative tolerance; the tests below assert the stronger bit-exact bar
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from elm_physics_b200 import engine as eng
+    e = eng.Engine(0)
+    yield e
+    e.close()
+
+
+def _packed(worlds):
+    return pack.pack_worlds(worlds)
+
+
+def test_library_is_the_cuda_build(engine):
+    import os
+    from elm_physics_b200 import engine as eng
+    assert os.path.exists(eng.LIB_PATH)
+    assert engine.stream_handle() is not None
+
+
+def test_readme_scene_lockstep_1000_steps(engine, oracle):
+    """C1: README.md:9-19 — rubber sphere on a wood plane, 1000 steps @ 60 Hz, compared every step."""
+    shapes, bodies, params = _packed(scenes.readme_scene())
+    bo, bg, _, _ = H.lockstep(oracle, engine, shapes, bodies, params, 1000, what="readme")
+    assert H.max_rel_dev(bo, bg) <= REL_TOL
+    # the ball has come to rest on the plane (z = radius within the contact tolerance)
+    assert abs(bg.pos[0][2] - 0.5) < 5e-3
+
+
+def test_stack_of_five_lockstep(engine, oracle):
+    """sandbox/tests/StabilityTest.elm:339-360 scene (7 iterations, warm-started), 240 lockstep frames."""
+    shapes, bodies, params = _packed(scenes.stack_scene(5, 7))
+    bo, bg, _, wg = H.lockstep(oracle, engine, shapes, bodies, params, 240, what="stack5")
+    # stable: max speed < 0.05 m/s as the reference's stability test requires
+    assert float(np.abs(bg.vel).max()) < 0.05
+    # one island containing the whole stack, rooted at the lowest dynamic id
+    assert wg.world_n_islands[0] == 1
+
+
+def test_boxes_scene_resident(engine, oracle):
+    """C2: 100 boxes (pyramid + stack), 40 resident GPU steps (contacts fed back on device) == 40 oracle steps."""
+    shapes, bodies, params = _packed(scenes.boxes_scene())
+    _, bg, oo, og = H.resident_vs_oracle(oracle, engine, shapes, bodies, params, 40, what="boxes")
+    assert og.n_contacts > 500
+    assert og.world_n_islands[0] == 2
+
+
+@pytest.mark.parametrize("seed,gravity", [(11, (0.0, 0.0, -9.80665)), (12, (0.0, 0.0, 0.0)), (13, (3.0, -2.0, -6.0))])
+def test_narrowphase_matrix_pair_worlds(engine, oracle, seed, gravity):
+    """Every (shape kind x shape kind) cell of NarrowPhase.elm:86-286 incl. compound, static, kinematic, particle:
+    726 two-body worlds, 4 lockstep frames each."""
+    worlds = H.pair_worlds(seed, per_combo=6, gravity=gravity)
+    shapes, bodies, params = _packed(worlds)
+    _, _, _, wg = H.lockstep(oracle, engine, shapes, bodies, params, 4, what=f"pairs{seed}")
+    assert wg.n_contacts > 200     # the scene generator does make most pairs touch
+
+
+def test_small_mixed_world_lockstep(engine, oracle):
+    """Blocks, spheres, capsules, cylinders, cones, compounds, a point mass and a kinematic lift: 300 frames."""
+    shapes, bodies, params = _packed(scenes.small_mixed_world(seed=3))
+    H.lockstep(oracle, engine, shapes, bodies, params, 300, check_every=1, what="mixed")
+
+
+def test_batched_mixed_worlds_resident(engine, oracle):
+    """C3 at test size: 48 worlds x 32 bodies, 150 resident steps (drop + first settling)."""
+    shapes, bodies, params = scenes.mixed_worlds(48)
+    _, _, _, og = H.resident_vs_oracle(oracle, engine, shapes, bodies, params, 150, what="c3x48")
+    assert og.n_contacts > 48 * 20
+
+
+def test_batch_equals_single_worlds(engine):
+    """Worlds are independent (src/Physics.elm:522-525): a world stepped inside a batch equals the same world
+    stepped alone, bit for bit — the property the multi-GPU sharding relies on."""
+    shapes, bodies, params = scenes.mixed_worlds(32)
+    engine.upload_shapes(shapes)
+    bb = bodies.copy()
+    ob = H.contacts_for(bb)
+    engine.step(bb, params, None, ob, 60)
+    for w in (0, 17, 31):
+        s1, b1, p1 = scenes.mixed_worlds(1, first_world=w)
+        engine.upload_shapes(s1)
+        o1 = H.contacts_for(b1)
+        engine.step(b1, p1, None, o1, 60)
+        r0, r1 = bodies.world_body_off[w], bodies.world_body_off[w + 1]
+        for name in abi.BODY_INOUT:
+            assert getattr(bb, name)[r0:r1].tobytes() == getattr(b1, name).tobytes(), (w, name)
+        d_b, d_1 = pack.contacts_world_dict(ob, w), pack.contacts_world_dict(o1, 0)
+        for k in ("feature_key", "shape_key", "lambda_", "ni", "pi", "pj", "group_id1", "group_id2"):
+            assert d_b[k].tobytes() == d_1[k].tobytes(), (w, k)
+
+
+def test_determinism_run_twice(engine):
+    shapes, bodies, params = scenes.mixed_worlds(64)
+    engine.upload_shapes(shapes)
+    outs = []
+    for _ in range(2):
+        b = bodies.copy()
+        o = H.contacts_for(b)
+        engine.step(b, params, None, o, 80)
+        outs.append((b.state_bytes(), {k: v.tobytes() for k, v in o.canonical().items()}))
+    assert outs[0] == outs[1]
+
+
+def _joint_world(kind):
+    """Two/three-body worlds exercising Equation.elm:157-361 joint rows, incl. a flipped registration."""
+    base = P.static([(P.shape_block((1.0, 1.0, 1.0)), P.wood)])
+    base = P.move_to((0.0, 0.0, 3.0), base)
+    arm = P.move_to((1.2, 0.1, 3.0), P.block((1.0, 0.4, 0.4), P.wood))
+    arm = P.set_angular_velocity_to((0.3, 0.5, -0.2), arm)
+    bob = P.move_to((2.4, 0.0, 2.5), P.sphere(0.3, P.steel))
+    floor = P.plane(P.wood)
+    bodies = [("floor", floor), ("base", base), ("arm", arm), ("bob", bob)]
+    if kind == "hinge":
+        cons = {("base", "arm"): [P.Hinge((0.5, 0, 0), (0, 1, 0), (-0.6, 0, 0), (0, 1, 0))],
+                ("bob", "arm"): [P.PointToPoint((-0.5, 0, 0.3), (0.6, 0, 0))]}      # registered on the later body
+    elif kind == "lock":
+        cons = {("base", "arm"): [P.Lock((0.5, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (-0.6, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1))],
+                ("arm", "bob"): [P.Distance(1.3)]}
+    else:
+        cons = {("arm", "base"): [P.PointToPoint((-0.6, 0, 0), (0.5, 0, 0)), P.Distance(1.25)],
+                ("arm", "bob"): [P.Distance(1.4), P.PointToPoint((0.6, 0, 0), (-0.5, 0, 0.3))]}
+    cfg = P.on_earth()
+
+    def constrain(a):
+        tab = {b: v for (x, b), v in cons.items() if x == a}
+        return (lambda b: tab.get(b, [])) if tab else None
+    cfg.constrain = constrain
+    with_ids, _ = P.assign_ids(bodies)
+    return [(cfg, with_ids)]
+
+
+@pytest.mark.parametrize("kind", ["hinge", "lock", "mixed"])
+def test_joint_constraints_lockstep(engine, oracle, kind):
+    shapes, bodies, params = _packed(_joint_world(kind))
+    assert params.n_constraints >= 2
+    _, bg, _, wg = H.lockstep(oracle, engine, shapes, bodies, params, 200, what=f"joints-{kind}")
+    assert int(wg.group_n_constraints[:wg.n_groups].sum()) >= 2
+    assert np.isfinite(bg.pos).all()
+
+
+def test_collide_callback_mask(engine, oracle):
+    """`collide` evaluated caller-side (BroadPhase.elm:189-215): boxes that ignore each other fall through."""
+    worlds = scenes.stack_scene(3, 10)
+    cfg, bodies = worlds[0]
+    cfg.collide = lambda a, b: not ({a, b} == {"b0", "b1"})
+    shapes, pb, params = _packed(worlds)
+    assert params.collide is not None
+    _, bg, _, wg = H.lockstep(oracle, engine, shapes, pb, params, 90, what="collide")
+    ids = {(int(wg.group_id1[g]), int(wg.group_id2[g])) for g in range(wg.n_groups)}
+    assert (1, 2) not in ids and (2, 1) not in ids
+
+
+def test_empty_ragged_and_sparse_ids(engine, oracle):
+    """Edge cases of SURVEY §9.8: empty world, single static body, free fall (iterations = 1), sparse ids."""
+    from dataclasses import replace
+    w_empty = (P.on_earth(), [])
+    w_plane = (P.on_earth(), P.assign_ids([("f", P.plane(P.wood))])[0])
+    w_fall = (P.on_earth(), P.assign_ids([("a", P.move_to((0, 0, 50), P.sphere(0.5, P.rubber))), ("f", P.plane(P.wood))])[0])
+    sparse = [("f", replace(P.plane(P.wood), id=7)), ("a", replace(P.move_to((0, 0, 0.45), P.block((1, 1, 1), P.wood)), id=3)),
+              ("b", replace(P.move_to((0, 0, 1.4), P.block((1, 1, 1), P.wood)), id=40))]
+    w_sparse = (P.on_earth(), P.assign_ids(sparse)[0])
+    shapes, bodies, params = _packed([w_empty, w_plane, w_fall, w_sparse, w_empty])
+    _, _, _, wg = H.lockstep(oracle, engine, shapes, bodies, params, 30, what="edge")
+    assert list(wg.iterations[:5]) [0] == 0 and wg.iterations[2] == 1
+    assert {int(x) for x in wg.group_id1[:wg.n_groups]} | {int(x) for x in wg.group_id2[:wg.n_groups]} == {3, 7, 40}
+
+
+def test_warm_start_roundtrip_through_host(engine, oracle):
+    """Contacts downloaded to the host and uploaded again as warm start == contacts kept resident on the device."""
+    shapes, bodies, params = scenes.mixed_worlds(8)
+    engine.upload_shapes(shapes)
+    a = bodies.copy()
+    oa = H.contacts_for(a)
+    engine.step(a, params, None, oa, 90)
+    b = bodies.copy()
+    wb = None
+    for _ in range(3):
+        ob = H.contacts_for(b)
+        engine.step(b, params, wb, ob, 30)
+        wb = ob
+    H.assert_bodies_equal(a, b, "resident vs host round trip")
+    H.assert_contacts_equal(oa, wb, "resident vs host round trip")
+
+
+def test_python_simulate_mirror(engine):
+    """The host-side mirror of Physics.simulate (physics.simulate) steps the README scene like the reference's
+    own doc example: contacts fed back, ball ends on the floor; contactPoints reports the touching point."""
+    cfg, bodies = scenes.readme_scene()[0]
+    contacts = P.empty_contacts()
+    for _ in range(200):
+        cfg.contacts = contacts
+        bodies, contacts = P.simulate(cfg, bodies, engine=engine)
+    ball = dict(bodies)["ball"]
+    assert abs(P.origin_point(ball)[2] - 0.5) < 2e-2
+    pts = P.contact_points(lambda a, b: True, contacts)
+    assert len(pts) == 1 and abs(pts[0][2][0][2]) < 2e-2
+
+
+def test_full_size_c3_properties(engine):
+    """BASELINE config 3 at full size (8192 worlds x 32 bodies): size-independent properties —
+    (1) worlds [0,16) of the full batch are bit-identical to the same worlds stepped as their own batch,
+    (2) no capacity overflow, every world reports 1 <= iterations <= 20, state finite."""
+    steps = 30
+    shapes, bodies, params = scenes.mixed_worlds(8192)
+    engine.upload_shapes(shapes)
+    engine.upload_worlds(bodies, params, None)
+    engine.step_resident(steps)
+    engine.sync()
+    engine.download_bodies(bodies)
+    assert np.isfinite(bodies.pos).all() and np.isfinite(bodies.vel).all()
+    s1, b1, p1 = scenes.mixed_worlds(16)
+    engine.upload_shapes(s1)
+    o1 = H.contacts_for(b1)
+    engine.step(b1, p1, None, o1, steps)
+    r1 = b1.n_bodies
+    for name in abi.BODY_INOUT:
+        assert getattr(bodies, name)[:r1].tobytes() == getattr(b1, name).tobytes(), name
+    assert (o1.iterations[:16] >= 1).all() and (o1.iterations[:16] <= 20).all()
