@@ -53,6 +53,9 @@ def kernel_bytes(name, c):
         "k_solve": K * 344 + nd * 96,
         # 512 B per body-step (336 read + 176 written)
         "k_integrate": nb * 512,
+        # fused front end: body state read (30 doubles + kind, 244 B); per contact: warm-start read (56 B),
+        # ContactRec (104 B) + RowRec (320 B) written; per group: 8 slot words (32 B) + island list (4 B)
+        "k_world_front": nb * 244 + K * (56 + 104 + 320) + G * 36,
     }
     return table[name]
 

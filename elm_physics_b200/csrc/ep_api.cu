@@ -13,6 +13,7 @@
 #include "ep_device.cuh"
 
 #include "ep_kernels.cuh"
+#include "ep_fused.cuh"
 
 namespace ep {
 __global__ void k_export_lambda(const RowRec* rows, int n, double* lam, double* t1) {
@@ -34,9 +35,12 @@ struct ep_ctx {
   // host mirrors needed for marshalling
   std::vector<int32_t> h_sh_kind, h_sh_f64_off, h_sh_i32_off, h_sh_i32;
   std::vector<double> h_sh_f64;
+  std::vector<int32_t> h_pl_off, h_pl_code;
   std::vector<int32_t> h_world_body_off, h_body_id, h_iterations;
   int sm_count = 148;
   int64_t launches = 0;
+  int64_t opt[EP_OPT_COUNT] = {0};
+  size_t fused_smem = 0; int fused_grid = 0;
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -115,6 +119,11 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   delete ctx;
 }
 
+extern "C" int ep_configure(ep_ctx* ctx, int32_t option, int64_t value) {
+  if (!ctx || option < 0 || option >= EP_OPT_COUNT) return EP_EINVAL;
+  ctx->opt[option] = value;
+  return EP_OK;
+}
 extern "C" const char* ep_last_error(const ep_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* ep_stream(ep_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
@@ -134,6 +143,33 @@ extern "C" int ep_upload_shapes(ep_ctx* ctx, const ep_shapes* S) {
   TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_i32_off, ctx->h_sh_i32_off.data(), ns + 1));
   TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_f64, ctx->h_sh_f64.data(), ctx->h_sh_f64.size()));
   TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_i32, ctx->h_sh_i32.data(), ctx->h_sh_i32.size()));
+  // placement program of each template: which f64 triples are points (0) / directions (1) to be placed every step
+  std::vector<int32_t> pl_off(ns + 1, 0), pl_code;
+  for (int s = 0; s < ns; s++) {
+    const int32_t* ib = ctx->h_sh_i32.data() + ctx->h_sh_i32_off[s];
+    auto item = [&](int rel, int dir) { pl_code.push_back(rel * 2 + dir); };
+    switch (ctx->h_sh_kind[s]) {
+      case EP_SPHERE: case EP_PARTICLE: item(0, 0); break;
+      case EP_CAPSULE: case EP_PLANE: item(0, 0); item(3, 1); break;
+      case EP_CONVEX: {
+        int nv = ib[1], ng = ib[2];
+        item(0, 0);
+        if (ib[0]) { item(3, 1); item(6, 1); item(9, 1); }
+        for (int v = 0; v < nv; v++) item(EP_CONVEX_F64_HEADER + 3 * v, 0);
+        for (int g = 0; g < ng; g++) {
+          int base = EP_CONVEX_F64_HEADER + 3 * nv + EP_GROUP_F64 * g;
+          item(base, 1);
+          if (ib[EP_CONVEX_I32_HEADER + EP_GROUP_I32 * g]) item(base + 4, 1);
+        }
+        break;
+      }
+      default: ctx->err = "unknown shape kind"; return EP_EINVAL;
+    }
+    pl_off[s + 1] = (int32_t)pl_code.size();
+  }
+  ctx->h_pl_off = pl_off; ctx->h_pl_code = pl_code;
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_pl_off, pl_off.data(), pl_off.size()));
+  TRY(dev_upload(ctx, ctx->shape_allocs, &ctx->d.sh_pl_code, pl_code.data(), pl_code.size()));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_shapes = true;
   return EP_OK;
@@ -147,10 +183,11 @@ static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
   TRY(dev_alloc(ctx, pool, &f.slot_cstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_ccount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_jstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_jcount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_ncon, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_root, d.slot_cap));
-  TRY(dev_alloc(ctx, pool, &f.hkeys, (size_t)d.hash_mask + 1)); TRY(dev_alloc(ctx, pool, &f.hvals, (size_t)d.hash_mask + 1));
+  const size_t hn = d.fused ? 1 : (size_t)d.hash_mask + 1;
+  TRY(dev_alloc(ctx, pool, &f.hkeys, hn)); TRY(dev_alloc(ctx, pool, &f.hvals, hn));
   TRY(dev_alloc(ctx, pool, &f.cand_base, d.n_worlds)); TRY(dev_alloc(ctx, pool, &f.cand_n, d.n_worlds));
   TRY(dev_alloc(ctx, pool, &f.counters, CNT_COUNT));
-  CK(cudaMemsetAsync(f.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), ctx->stream));
+  CK(cudaMemsetAsync(f.hkeys, 0xFF, hn * sizeof(int64_t), ctx->stream));
   CK(cudaMemsetAsync(f.counters, 0, CNT_COUNT * sizeof(int32_t), ctx->stream));
   CK(cudaMemsetAsync(f.cand_base, 0, std::max(d.n_worlds, 1) * sizeof(int32_t), ctx->stream));
   CK(cudaMemsetAsync(f.cand_n, 0, std::max(d.n_worlds, 1) * sizeof(int32_t), ctx->stream));
@@ -224,35 +261,45 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     woff[k] = wtotal;
     wtotal += ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s];
   }
-  std::vector<double> wf(std::max<int64_t>(wtotal, 1));
+  // Path choice: batches of small worlds take the fused front end (one CTA per world, everything in shared memory);
+  // anything larger takes the general multi-kernel path.  EP_OPT_PATH: 0 auto, 1 general, 2 fused (error if it does not fit).
+  {
+    int nb_max = 1, inst_max = 1; int64_t wf_max = 1;
+    for (int w = 0; w < nw; w++) {
+      int a = B->world_body_off[w], b = B->world_body_off[w + 1];
+      nb_max = std::max(nb_max, b - a);
+      inst_max = std::max(inst_max, B->inst_off[b] - B->inst_off[a]);
+      int64_t wsum = 0;
+      for (int k = B->inst_off[a]; k < B->inst_off[b]; k++) wsum += ctx->h_sh_f64_off[B->inst_shape[k] + 1] - ctx->h_sh_f64_off[B->inst_shape[k]];
+      wf_max = std::max(wf_max, wsum);
+    }
+    int cand = std::max(1, nb_max * (nb_max - 1) / 2);
+    int raw = ctx->opt[EP_OPT_RAW_CAP] > 0 ? (int)ctx->opt[EP_OPT_RAW_CAP] : std::max(128, 12 * nb_max);
+    size_t bytes = fused_smem_bytes(nb_max, inst_max, (int)wf_max, cand, raw);
+    bool fits = nb_max <= 255 && cand <= 32767 && raw <= 32767 && bytes <= 200 * 1024;
+    if (ctx->opt[EP_OPT_PATH] == 2 && !fits) { ctx->err = "fused path requested but a world does not fit one CTA's shared memory"; return EP_ECAPACITY; }
+    d.fused = (ctx->opt[EP_OPT_PATH] == 2 || (ctx->opt[EP_OPT_PATH] == 0 && fits)) ? 1 : 0;
+    d.f_nb_max = nb_max; d.f_inst_max = inst_max; d.f_wf64_max = (int)wf_max; d.f_cand_cap = cand; d.f_raw_cap = raw;
+    ctx->fused_smem = bytes;
+    if (d.fused) {
+      CK(cudaFuncSetAttribute(k_world_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_world_front, kFusedThreads, bytes));
+      if (per_sm < 1) { ctx->err = "fused kernel does not fit an SM"; return EP_ECAPACITY; }
+      ctx->fused_grid = std::max(1, std::min(nw, per_sm * ctx->sm_count));
+    }
+  }
+  std::vector<double> wf(d.fused ? 1 : std::max<int64_t>(wtotal, 1));
   std::vector<int32_t> pl_inst, pl_code;
   int n_moving = 0;
-  for (int pass = 0; pass < 2; pass++) {
+  for (int pass = 0; pass < 2 && !d.fused; pass++) {
     for (int k = 0; k < ni; k++) {
       bool moving = B->kind[inst_body[k]] != EP_STATIC;
       if (moving != (pass == 0)) continue;
       int s = B->inst_shape[k];
       const double* f = ctx->h_sh_f64.data() + ctx->h_sh_f64_off[s];
-      const int32_t* ib = ctx->h_sh_i32.data() + ctx->h_sh_i32_off[s];
-      if (pass == 0 || true) std::copy(f, f + (ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s]), wf.begin() + woff[k]);
-      auto item = [&](int rel, int dir) { pl_inst.push_back(k); pl_code.push_back(rel * 2 + dir); };
-      switch (ctx->h_sh_kind[s]) {
-        case EP_SPHERE: case EP_PARTICLE: item(0, 0); break;
-        case EP_CAPSULE: case EP_PLANE: item(0, 0); item(3, 1); break;
-        case EP_CONVEX: {
-          int nv = ib[1], ng = ib[2];
-          item(0, 0);
-          if (ib[0]) { item(3, 1); item(6, 1); item(9, 1); }
-          for (int v = 0; v < nv; v++) item(EP_CONVEX_F64_HEADER + 3 * v, 0);
-          for (int g = 0; g < ng; g++) {
-            int base = EP_CONVEX_F64_HEADER + 3 * nv + EP_GROUP_F64 * g;
-            item(base, 1);
-            if (ib[EP_CONVEX_I32_HEADER + EP_GROUP_I32 * g]) item(base + 4, 1);
-          }
-          break;
-        }
-        default: ctx->err = "unknown shape kind"; return EP_EINVAL;
-      }
+      std::copy(f, f + (ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s]), wf.begin() + woff[k]);
+      for (int x = ctx->h_pl_off[s]; x < ctx->h_pl_off[s + 1]; x++) { pl_inst.push_back(k); pl_code.push_back(ctx->h_pl_code[x]); }
     }
     if (pass == 0) n_moving = (int)pl_inst.size();
   }
@@ -298,7 +345,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   // capacities
   d.slot_cap = std::max<int64_t>(slot_cap, 1);
   int64_t ccap = std::max<int64_t>(1 << 14, 16 * (int64_t)nb);
-  if (const char* e = getenv("EP_CONTACT_CAP")) ccap = std::max<int64_t>(atoll(e), 64);
+  if (ctx->opt[EP_OPT_CONTACT_CAP] > 0) ccap = std::max<int64_t>(ctx->opt[EP_OPT_CONTACT_CAP], 64);
   if (warm && warm->world_group_off) ccap = std::max<int64_t>(ccap, warm->group_contact_off[warm->world_group_off[nw]]);
   d.contact_cap = (int32_t)std::min<int64_t>(ccap, (1ll << 31) - 64);
   int64_t h = 1; while (h < 2 * (int64_t)d.contact_cap) h <<= 1;
@@ -311,6 +358,9 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.uf_parent, nb)); TRY(dev_alloc(ctx, pool, &d.uf_count, nb)); TRY(dev_alloc(ctx, pool, &d.uf_fill, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_off, nb)); TRY(dev_alloc(ctx, pool, &d.isl_cnt, nb)); TRY(dev_alloc(ctx, pool, &d.isl_world, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_groups, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &d.bin_items, (size_t)kBins * std::max(nb, 1)));
+  d.phase_cycles = nullptr;
+  if (getenv("EP_PHASE_TIMING")) { TRY(dev_alloc(ctx, pool, &d.phase_cycles, 16)); CK(cudaMemsetAsync(d.phase_cycles, 0, 16 * sizeof(unsigned long long), ctx->stream)); }
   TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));
   CK(cudaMemcpyAsync(d.world_min_rem, P->iterations, nw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d.world_n_islands, 0, std::max(nw, 1) * sizeof(int32_t), ctx->stream));
@@ -346,18 +396,21 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
       }
     }
     FrameBuf& f = d.prev;
+    std::vector<int32_t> wg_base(nw), wg_n(nw);
+    for (int w = 0; w < nw; w++) { wg_base[w] = warm->world_group_off[w]; wg_n[w] = warm->world_group_off[w + 1] - warm->world_group_off[w]; }
+    CK(cudaMemcpyAsync(f.cand_base, wg_base.data(), nw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.cand_n, wg_n.data(), nw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.slot_row1, row1.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.slot_row2, row2.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.slot_cstart, cstart.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.slot_ccount, ccount.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.contacts, crec.data(), nc * sizeof(ContactRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.rows, rrec.data(), nc * sizeof(RowRec), cudaMemcpyHostToDevice, ctx->stream));
-    k_hash_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng);
-    CK(cudaGetLastError());
+    if (!d.fused) { k_hash_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng); CK(cudaGetLastError()); }
     CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
   }
   // place every shape once (static bodies are never re-placed)
-  if (d.n_pl_all > 0) {
+  if (!d.fused && d.n_pl_all > 0) {
     k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, ctx->stream>>>(d, d.n_pl_all);
     CK(cudaGetLastError());
     // static items sit after the moving ones, so the per-step launch covers [0, n_pl_moving)
@@ -415,7 +468,7 @@ extern "C" int ep_kernel_times(ep_ctx* ctx, double* ms, int64_t* launches, int32
   return EP_OK;
 }
 extern "C" const char* ep_kernel_name(int32_t k) {
-  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate"};
+  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate", "k_world_front"};
   return (k >= 0 && k < EP_K_COUNT) ? names[k] : "";
 }
 
@@ -430,13 +483,17 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   const int gwide = ctx->sm_count * 8;
   for (int s = 0; s < n_steps; s++) {
     CK(cudaMemsetAsync(d.cur.counters, 0, CNT_COUNT * sizeof(int32_t), st));
-    CK(cudaMemsetAsync(d.cur.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), st));
-    if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
-    { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
-    { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }
-    { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d); }
-    { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
-    { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d); }
+    if (d.fused) {
+      { Timed t(ctx, EP_K_WORLD_FRONT); k_world_front<<<ctx->fused_grid, kFusedThreads, ctx->fused_smem, st>>>(d); }
+    } else {
+      CK(cudaMemsetAsync(d.cur.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), st));
+      if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
+      { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
+      { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }
+      { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d); }
+      { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
+      { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d); }
+    }
     { Timed t(ctx, EP_K_SOLVE); k_solve<<<gwide, 128, 0, st>>>(d); }
     { Timed t(ctx, EP_K_INTEGRATE); k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d); }
     CK(cudaGetLastError());
@@ -493,7 +550,7 @@ extern "C" int ep_download_contacts(ep_ctx* ctx, ep_contacts* out) {
   int32_t cnt[CNT_COUNT];
   CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const int ns = cnt[CNT_CAND], nc = cnt[CNT_CONTACTS];
+  const int ns = d.fused ? cnt[CNT_GROUPS] : cnt[CNT_CAND], nc = cnt[CNT_CONTACTS];
   std::vector<int32_t> base(nw), num(nw), row1(ns), row2(ns), cstart(ns), ccount(ns), jcount(ns), ncon(ns), root(ns), minrem(nw), nisl(nw);
   std::vector<ContactRec> crec(std::max(nc, 1));
   std::vector<double> lam(std::max(nc, 1)), t1(3 * (size_t)std::max(nc, 1)), prepos(3 * (size_t)d.n_bodies), prequat(4 * (size_t)d.n_bodies);
@@ -552,7 +609,7 @@ extern "C" int ep_download_contacts(ep_ctx* ctx, ep_contacts* out) {
   }
   out->world_group_off[nw] = g;
   out->group_contact_off[g] = c;
-  ctx->stats[EP_STAT_CANDIDATE_PAIRS] = ns; ctx->stats[EP_STAT_GROUPS] = g; ctx->stats[EP_STAT_CONTACTS] = c;
+  ctx->stats[EP_STAT_CANDIDATE_PAIRS] = cnt[CNT_CAND]; ctx->stats[EP_STAT_GROUPS] = g; ctx->stats[EP_STAT_CONTACTS] = c;
   ctx->stats[EP_STAT_ISLANDS] = cnt[CNT_ISLANDS];
   return EP_OK;
 }
@@ -567,6 +624,15 @@ extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, 
 
 extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
   if (!ctx || !out) return EP_EINVAL;
+  if (ctx->have_worlds && ctx->d.phase_cycles) {      // EP_PHASE_TIMING=1: dump and reset the fused kernel's phase clocks
+    unsigned long long pc[16];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(pc, ctx->d.phase_cycles, sizeof pc, cudaMemcpyDeviceToHost);
+    cudaMemset(ctx->d.phase_cycles, 0, sizeof pc);
+    fprintf(stderr, "[ep] k_world_front phase cycles (thread 0, summed over worlds):");
+    for (int i = 0; i < 8; i++) fprintf(stderr, " p%d=%llu", i, pc[i]);
+    fprintf(stderr, "\n");
+  }
   ctx->stats[EP_STAT_KERNEL_LAUNCHES] = ctx->launches;
   for (int i = 0; i < n && i < EP_STAT_COUNT; i++) out[i] = ctx->stats[i];
   return EP_OK;

@@ -25,7 +25,9 @@ struct RowRec {
 // `ConstraintEquation` (src/Internal/Equation.elm:503-511); bounds are the constants -1e6 / 1e6.
 struct JointRow { double J[9]; double B, invC, eps, lam; double pad[3]; };   // 16 doubles
 
-enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_COUNT = 8 };
+constexpr int kBins = 8;     // island size classes for the solver's work list (ep_solve.cuh)
+enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_GROUPS = 5, CNT_WORK = 6,
+       CNT_BIN0 = 8, CNT_COUNT = 16 };
 enum { FLAG_POOL_OVERFLOW = 0, FLAG_PAIR_OVERFLOW = 1, FLAG_POLY_OVERFLOW = 2, FLAG_JOINT_OVERFLOW = 3, FLAG_COUNT = 4 };
 
 struct FrameBuf {        // double-buffered: the previous frame is the warm-start cache
@@ -79,6 +81,14 @@ struct Dev {
   JointRow* jrows;
   int32_t* flags;             // [FLAG_COUNT]
   int64_t slot_cap; int32_t contact_cap; int32_t hash_mask; int32_t jrow_cap;
+  // solver work list: islands binned by row count (largest class first)
+  int32_t* bin_items;         // [kBins][n_bodies] island indices
+  // fused small-world front end (ep_fused.cuh): every world fits one CTA's shared memory
+  int32_t fused;              // 1: k_world_front replaces place/sort/broadphase/narrowphase/equations/islands
+  int32_t f_nb_max, f_inst_max, f_wf64_max, f_cand_cap, f_raw_cap;
+  unsigned long long* phase_cycles;   // [16] per-phase clock64 sums of k_world_front (thread 0 of each CTA), debugging aid
+  const int32_t* sh_pl_off;   // [n_shapes+1] placement program of each shape template
+  const int32_t* sh_pl_code;  // rel offset * 2 + isDirection
   FrameBuf cur, prev;
 };
 

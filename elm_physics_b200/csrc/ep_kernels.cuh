@@ -323,6 +323,69 @@ __device__ void rot_row(JointRow& r, double dt, V3 gravity, const Spook& sp, con
 }
 __device__ __forceinline__ int constraint_rows(int kind) { return kind == 0 ? 3 : (kind == 1 ? 5 : (kind == 2 ? 6 : 1)); }
 
+// contactEquations (Equation.elm:364-450) for one contact; lam/ct1 = cached normal lambda and friction-1 direction
+__device__ __forceinline__ void contact_row(RowRec& r, V3 ni, V3 pi, V3 pj, double bounciness, double friction, double lam, V3 ct1,
+                                            double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2) {
+  V3 ri = vsub(pi, b1.x), rj = vsub(pj, b2.x);
+  V3 t1, t2; stable_tangents(ct1, ni, t1, t2);
+  contact_jac(ni, ri, rj, r.nJ); contact_jac(t1, ri, rj, r.f1J); contact_jac(t2, ri, rj, r.f2J);
+  r.nB = compute_contact_b(sp.a, sp.b, bounciness, pi, pj, ni, b1, b2, r.nJ) - (dt * compute_gimf(gravity, b1, b2, r.nJ));
+  r.nInvC = 1 / (compute_gimgt(b1, b2, r.nJ) + sp.eps);
+  r.f1B = (-compute_gw(b1, b2, r.f1J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f1J));
+  r.f1InvC = 1 / (compute_gimgt(b1, b2, r.f1J) + sp.eps);
+  r.f2B = (-compute_gw(b1, b2, r.f2J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f2J));
+  r.f2InvC = 1 / (compute_gimgt(b1, b2, r.f2J) + sp.eps);
+  r.eps = sp.eps; r.mu = friction;
+  r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.pad = 0;
+}
+// addConstraintEquations (Equation.elm:157-361) for the pair (r1, r2) (global body rows; ncon < 0 == flipped registration):
+// rows are emitted per constraint in list order and consed, so the solver order is the reverse of emission:
+// row e of E lands at jstart + E-1-e.
+__device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, const BodyE& b1, const BodyE& b2, double dt, V3 gravity,
+                                    const Spook& sp, int& jstart, int& jcount) {
+  bool flipped = ncon < 0;
+  int ra = flipped ? r2 : r1, rb = flipped ? r1 : r2;
+  int E = 0;
+  for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1]; c++) if (d.con_b[c] == rb) E += constraint_rows(d.con_kind[c]);
+  int j0 = atomicAdd(&d.cur.counters[CNT_JROWS], E);
+  if (j0 + E > d.jrow_cap) { d.flags[FLAG_JOINT_OVERFLOW] = 1; E = 0; j0 = 0; }
+  int e = 0;
+  for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1] && E > 0; c++) {
+    if (d.con_b[c] != rb) continue;
+    const double* A = d.con_data + 24 * c;      // registering body's side
+    const double* Bd = A + 12;                   // partner's side
+    const double* s1 = flipped ? Bd : A;         // relativeToCenterOfMassFlipped, Constraint.elm:64-95
+    const double* s2 = flipped ? A : Bd;
+    int kind = d.con_kind[c];
+    JointRow tmp[6];
+    int nr = constraint_rows(kind);
+    if (kind == 3) {                              // Distance, Equation.elm:175-228
+      double half = A[0] / 2;
+      V3 ni = vdirection(b2.x, b1.x);
+      V3 ri = vscale(half, ni), rj = vscale(-half, ni);
+      V3 pi = vadd(ri, b1.x), pj = vadd(rj, b2.x);
+      contact_jac(ni, ri, rj, tmp[0].J);
+      joint_row(tmp[0], dt, gravity, b1, b2, compute_contact_b(sp.a, sp.b, 0, pi, pj, ni, b1, b2, tmp[0].J), sp.eps);
+    } else {
+      p2p_rows(tmp, dt, gravity, sp, b1, b2, ld3(s1), ld3(s2));
+      if (kind == 1) {                            // Hinge, Equation.elm:231-242
+        V3 worldAxis2 = rotate(b2.q, ld3(s2 + 3));
+        V3 n1, n2; tangents(rotate(b1.q, ld3(s1 + 3)), n1, n2);
+        rot_row(tmp[3], dt, gravity, sp, b1, b2, n1, worldAxis2);
+        rot_row(tmp[4], dt, gravity, sp, b1, b2, n2, worldAxis2);
+      } else if (kind == 2) {                     // Lock, Equation.elm:245-269
+        V3 x1 = rotate(b1.q, ld3(s1 + 3)), y1 = rotate(b1.q, ld3(s1 + 6)), z1 = rotate(b1.q, ld3(s1 + 9));
+        V3 x2 = rotate(b2.q, ld3(s2 + 3)), y2 = rotate(b2.q, ld3(s2 + 6)), z2 = rotate(b2.q, ld3(s2 + 9));
+        rot_row(tmp[3], dt, gravity, sp, b1, b2, x1, y2);
+        rot_row(tmp[4], dt, gravity, sp, b1, b2, y1, z2);
+        rot_row(tmp[5], dt, gravity, sp, b1, b2, z1, x2);
+      }
+    }
+    for (int k = 0; k < nr; k++, e++) { tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
+  }
+  jstart = j0; jcount = E;
+}
+
 __global__ void __launch_bounds__(128) k_equations(Dev d) {
   const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
@@ -347,66 +410,14 @@ __global__ void __launch_bounds__(128) k_equations(Dev d) {
           const ContactRec& p = d.prev.contacts[pc0 + m];
           if ((p.fk - c.fk == 0) && (p.sk - c.sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
         }
-        // contactEquations, Equation.elm:364-450
-        V3 ni = ld3(c.ni), pi = ld3(c.pi), pj = ld3(c.pj);
-        V3 ri = vsub(pi, b1.x), rj = vsub(pj, b2.x);
-        V3 t1, t2; stable_tangents(ct1, ni, t1, t2);
         RowRec r;
-        contact_jac(ni, ri, rj, r.nJ); contact_jac(t1, ri, rj, r.f1J); contact_jac(t2, ri, rj, r.f2J);
-        r.nB = compute_contact_b(sp.a, sp.b, c.bounciness, pi, pj, ni, b1, b2, r.nJ) - (dt * compute_gimf(gravity, b1, b2, r.nJ));
-        r.nInvC = 1 / (compute_gimgt(b1, b2, r.nJ) + sp.eps);
-        r.f1B = (-compute_gw(b1, b2, r.f1J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f1J));
-        r.f1InvC = 1 / (compute_gimgt(b1, b2, r.f1J) + sp.eps);
-        r.f2B = (-compute_gw(b1, b2, r.f2J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f2J));
-        r.f2InvC = 1 / (compute_gimgt(b1, b2, r.f2J) + sp.eps);
-        r.eps = sp.eps; r.mu = c.friction;
-        r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.pad = 0;
+        contact_row(r, ld3(c.ni), ld3(c.pi), ld3(c.pj), c.bounciness, c.friction, lam, ct1, dt, gravity, sp, b1, b2);
         d.cur.rows[c0 + k] = r;
       }
     }
     if (ncon != 0) {
-      // addConstraintEquations (Equation.elm:157-361): rows are emitted per constraint in list order and consed,
-      // so the solver order is the reverse of emission: row e of E lands at jstart + E-1-e.
-      bool flipped = ncon < 0;
-      int ra = flipped ? r2 : r1, rb = flipped ? r1 : r2;
-      int E = 0;
-      for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1]; c++) if (d.con_b[c] == rb) E += constraint_rows(d.con_kind[c]);
-      int j0 = atomicAdd(&d.cur.counters[CNT_JROWS], E);
-      if (j0 + E > d.jrow_cap) { d.flags[FLAG_JOINT_OVERFLOW] = 1; E = 0; j0 = 0; }
-      int e = 0;
-      for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1] && E > 0; c++) {
-        if (d.con_b[c] != rb) continue;
-        const double* A = d.con_data + 24 * c;      // registering body's side
-        const double* Bd = A + 12;                   // partner's side
-        const double* s1 = flipped ? Bd : A;         // relativeToCenterOfMassFlipped, Constraint.elm:64-95
-        const double* s2 = flipped ? A : Bd;
-        int kind = d.con_kind[c];
-        JointRow tmp[6];
-        int nr = constraint_rows(kind);
-        if (kind == 3) {                              // Distance, Equation.elm:175-228
-          double half = A[0] / 2;
-          V3 ni = vdirection(b2.x, b1.x);
-          V3 ri = vscale(half, ni), rj = vscale(-half, ni);
-          V3 pi = vadd(ri, b1.x), pj = vadd(rj, b2.x);
-          contact_jac(ni, ri, rj, tmp[0].J);
-          joint_row(tmp[0], dt, gravity, b1, b2, compute_contact_b(sp.a, sp.b, 0, pi, pj, ni, b1, b2, tmp[0].J), sp.eps);
-        } else {
-          p2p_rows(tmp, dt, gravity, sp, b1, b2, ld3(s1), ld3(s2));
-          if (kind == 1) {                            // Hinge, Equation.elm:231-242
-            V3 worldAxis2 = rotate(b2.q, ld3(s2 + 3));
-            V3 n1, n2; tangents(rotate(b1.q, ld3(s1 + 3)), n1, n2);
-            rot_row(tmp[3], dt, gravity, sp, b1, b2, n1, worldAxis2);
-            rot_row(tmp[4], dt, gravity, sp, b1, b2, n2, worldAxis2);
-          } else if (kind == 2) {                     // Lock, Equation.elm:245-269
-            V3 x1 = rotate(b1.q, ld3(s1 + 3)), y1 = rotate(b1.q, ld3(s1 + 6)), z1 = rotate(b1.q, ld3(s1 + 9));
-            V3 x2 = rotate(b2.q, ld3(s2 + 3)), y2 = rotate(b2.q, ld3(s2 + 6)), z2 = rotate(b2.q, ld3(s2 + 9));
-            rot_row(tmp[3], dt, gravity, sp, b1, b2, x1, y2);
-            rot_row(tmp[4], dt, gravity, sp, b1, b2, y1, z2);
-            rot_row(tmp[5], dt, gravity, sp, b1, b2, z1, x2);
-          }
-        }
-        for (int k = 0; k < nr; k++, e++) { tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
-      }
+      int j0, E;
+      joint_rows_for_pair(d, r1, r2, ncon, b1, b2, dt, gravity, sp, j0, E);
       d.cur.slot_jstart[s] = j0; d.cur.slot_jcount[s] = E;
     }
   }
@@ -422,6 +433,12 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {       // Islands.el
     parent[x] = g;
     x = g;
   }
+}
+// island size class: row count (3 per contact + joint rows) on a log2 scale; class kBins-1 runs first
+__device__ __forceinline__ int island_bin(int rows) {
+  int b = 0;
+  while (b < kBins - 1 && rows > (3 << b)) b++;
+  return b;
 }
 __global__ void k_islands(Dev d) {
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < d.n_worlds; w += gridDim.x * blockDim.x) {
@@ -453,9 +470,18 @@ __global__ void k_islands(Dev d) {
     if (nisl == 0) continue;
     int ibase = atomicAdd(&d.cur.counters[CNT_ISLANDS], nisl);
     int gbase = atomicAdd(&d.cur.counters[CNT_ISL_GROUPS], valid);
+    for (int l = 0; l < n; l++) fill[l] = 0;
+    for (int s = s0; s < s0 + sn; s++) {                // island size class = row count (ep_solve work list)
+      int root = d.cur.slot_root[s];
+      if (root >= 0) fill[root - r0] += 3 * max(d.cur.slot_ccount[s], 0) + d.cur.slot_jcount[s];
+    }
     int k = 0, goff = gbase;
     for (int l = 0; l < n; l++) if (count[l] > 0) {
-      d.isl_off[ibase + k] = goff; d.isl_cnt[ibase + k] = count[l]; d.isl_world[ibase + k] = w;
+      int isl = ibase + k;
+      d.isl_off[isl] = goff; d.isl_cnt[isl] = count[l]; d.isl_world[isl] = w;
+      int bin = island_bin(fill[l]);
+      int at = atomicAdd(&d.cur.counters[CNT_BIN0 + bin], 1);
+      d.bin_items[(size_t)bin * d.n_bodies + at] = isl;
       fill[l] = goff; goff += count[l]; k++;
     }
     for (int s = s0; s < s0 + sn; s++) {                // groups of an island stay in enumeration order
@@ -582,7 +608,11 @@ __device__ double sweep_friction(const Dev& d, int s, double tot) {
 
 __global__ void __launch_bounds__(128) k_solve(Dev d) {
   const int total = d.cur.counters[CNT_ISLANDS];
-  for (int isl = blockIdx.x * blockDim.x + threadIdx.x; isl < total; isl += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    // work list: size classes from the largest down, so the longest islands start first and warps hold islands of similar length
+    int at = t, bin = kBins - 1;
+    while (bin > 0 && at >= d.cur.counters[CNT_BIN0 + bin]) { at -= d.cur.counters[CNT_BIN0 + bin]; bin--; }
+    const int isl = d.bin_items[(size_t)bin * d.n_bodies + at];
     int g0 = d.isl_off[isl], gn = d.isl_cnt[isl], w = d.isl_world[isl];
     // warm start in reverse enumeration order (buildAndWarmStart walks pairGroups, Solver.elm:122-208)
     for (int gi = gn - 1; gi >= 0; gi--) {

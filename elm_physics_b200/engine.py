@@ -16,7 +16,7 @@ _LIB = None
 
 EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
            "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream",
-           "ep_profile", "ep_kernel_times", "ep_kernel_name")
+           "ep_profile", "ep_kernel_times", "ep_kernel_name", "ep_configure")
 
 
 class EngineError(RuntimeError):
@@ -65,6 +65,15 @@ class Engine:
     def _ck(self, rc, what):
         if rc != 0:
             raise EngineError(f"{what} failed with {rc}: {self.lib.ep_last_error(self.ctx).decode()}")
+
+    def configure(self, path=None, contact_cap=None, raw_cap=None):
+        """ep_configure: path 'auto' | 'general' | 'fused'; capacities in contacts."""
+        if path is not None:
+            self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_PATH, C.c_int64({"auto": 0, "general": 1, "fused": 2}[path])), "ep_configure")
+        if contact_cap is not None:
+            self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_CONTACT_CAP, C.c_int64(contact_cap)), "ep_configure")
+        if raw_cap is not None:
+            self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_RAW_CAP, C.c_int64(raw_cap)), "ep_configure")
 
     def upload_shapes(self, shapes):
         self._ck(self.lib.ep_upload_shapes(self.ctx, C.byref(shapes.c)), "ep_upload_shapes")
