@@ -183,6 +183,7 @@ static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
   TRY(dev_alloc(ctx, pool, &f.slot_cstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_ccount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_jstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_jcount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_ncon, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_root, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &f.slot_item0, d.fused ? 1 : d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_nitems, d.fused ? 1 : d.slot_cap));
   const size_t hn = d.fused ? 1 : (size_t)d.hash_mask + 1;
   TRY(dev_alloc(ctx, pool, &f.hkeys, hn)); TRY(dev_alloc(ctx, pool, &f.hvals, hn));
   TRY(dev_alloc(ctx, pool, &f.cand_base, d.n_worlds)); TRY(dev_alloc(ctx, pool, &f.cand_n, d.n_worlds));
@@ -278,7 +279,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     size_t bytes = fused_smem_bytes(nb_max, inst_max, (int)wf_max, cand, raw);
     bool fits = nb_max <= 255 && cand <= 32767 && raw <= 32767 && bytes <= 200 * 1024;
     if (ctx->opt[EP_OPT_PATH] == 2 && !fits) { ctx->err = "fused path requested but a world does not fit one CTA's shared memory"; return EP_ECAPACITY; }
-    d.fused = (ctx->opt[EP_OPT_PATH] == 2 || (ctx->opt[EP_OPT_PATH] == 0 && fits)) ? 1 : 0;
+    d.fused = ctx->opt[EP_OPT_PATH] == 2 ? 1 : 0;      // auto = general: measured faster on B200 (profiles/r01_*)
     d.f_nb_max = nb_max; d.f_inst_max = inst_max; d.f_wf64_max = (int)wf_max; d.f_cand_cap = cand; d.f_raw_cap = raw;
     ctx->fused_smem = bytes;
     if (d.fused) {
@@ -359,6 +360,14 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.isl_off, nb)); TRY(dev_alloc(ctx, pool, &d.isl_cnt, nb)); TRY(dev_alloc(ctx, pool, &d.isl_world, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_groups, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &d.bin_items, (size_t)kBins * std::max(nb, 1)));
+  {
+    int64_t icap = std::max<int64_t>(1 << 16, 8 * (int64_t)ni);
+    if (ctx->opt[EP_OPT_ITEM_CAP] > 0) icap = std::max<int64_t>(ctx->opt[EP_OPT_ITEM_CAP], 64);
+    d.item_cap = d.fused ? 1 : (int32_t)std::min<int64_t>(icap, (1ll << 28));
+    TRY(dev_alloc(ctx, pool, &d.items, (size_t)kClasses * d.item_cap));
+    TRY(dev_alloc(ctx, pool, &d.raw, (size_t)d.item_cap * kRawStride));
+    TRY(dev_alloc(ctx, pool, &d.raw_cnt, d.item_cap));
+  }
   d.phase_cycles = nullptr;
   if (getenv("EP_PHASE_TIMING")) { TRY(dev_alloc(ctx, pool, &d.phase_cycles, 16)); CK(cudaMemsetAsync(d.phase_cycles, 0, 16 * sizeof(unsigned long long), ctx->stream)); }
   TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));

@@ -4,6 +4,8 @@
 
 namespace ep {
 
+struct RawContact;
+
 // One solved contact's geometry + identity: `Contact`/`SolverContact` (src/Internal/Contact.elm:16-33).
 struct ContactRec {
   int64_t fk;            // featureKey < 2^48 (ContactId.elm:94-96)
@@ -26,8 +28,10 @@ struct RowRec {
 struct JointRow { double J[9]; double B, invC, eps, lam; double pad[3]; };   // 16 doubles
 
 constexpr int kBins = 8;     // island size classes for the solver's work list (ep_solve.cuh)
-enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_GROUPS = 5, CNT_WORK = 6,
-       CNT_BIN0 = 8, CNT_COUNT = 16 };
+constexpr int kClasses = 36; // narrowphase work-item classes: unordered pair of shape sub-kinds, lo * 6 + hi (ep_kernels.cuh)
+constexpr int kRawStride = 8;// raw contacts reserved per work item (plane-box emits up to 8)
+enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_GROUPS = 5, CNT_WORK = 6, CNT_ITEMS = 7,
+       CNT_BIN0 = 8, CNT_CLASS0 = 16, CNT_COUNT = 16 + kClasses };
 enum { FLAG_POOL_OVERFLOW = 0, FLAG_PAIR_OVERFLOW = 1, FLAG_POLY_OVERFLOW = 2, FLAG_JOINT_OVERFLOW = 3, FLAG_COUNT = 4 };
 
 struct FrameBuf {        // double-buffered: the previous frame is the warm-start cache
@@ -41,6 +45,8 @@ struct FrameBuf {        // double-buffered: the previous frame is the warm-star
   int32_t* slot_jcount;
   int32_t* slot_ncon;    // user constraints carried by the pair
   int32_t* slot_root;    // island root body row (-1 when the slot is not a pair group)
+  int32_t* slot_item0;   // first narrowphase work item (shape pair) of the slot; items are numbered shape1-major
+  int32_t* slot_nitems;  // shapes1 x shapes2 when the pair passed the bounding-sphere test, else 0
   int64_t* hkeys;        // open-addressing table (world << 36 | bodyKey) -> slot
   int32_t* hvals;
   int32_t* cand_base;    // [n_worlds] first slot of the world (enumeration order inside)
@@ -81,6 +87,11 @@ struct Dev {
   JointRow* jrows;
   int32_t* flags;             // [FLAG_COUNT]
   int64_t slot_cap; int32_t contact_cap; int32_t hash_mask; int32_t jrow_cap;
+  // narrowphase work items, binned by class so that the lanes of a warp run the same Collision.* module
+  int32_t item_cap;
+  int4* items;                // [kClasses][item_cap] (slot, instance a, instance b, item id)
+  struct RawContact* raw;     // [item_cap][kRawStride] contacts of each item, solver order
+  int32_t* raw_cnt;           // [item_cap]
   // solver work list: islands binned by row count (largest class first)
   int32_t* bin_items;         // [kBins][n_bodies] island indices
   // fused small-world front end (ep_fused.cuh): every world fits one CTA's shared memory

@@ -116,66 +116,108 @@ __device__ __forceinline__ bool may_contact(const Dev& d, int w, int r0, int n, 
   return true;
 }
 
+// Work-item classes: shape sub-kind = convex box 0, convex other 1, plane 2, sphere 3, capsule 4, particle 5;
+// class = lo * 6 + hi of the unordered pair, so every lane of a warp in k_narrowphase runs the same Collision.* module.
+__device__ __forceinline__ int shape_subkind(const Dev& d, int inst) {
+  int sh = d.inst_shape[inst], k = d.sh_kind[sh];
+  return k == SH_CONVEX ? (d.sh_i32[d.sh_i32_off[sh]] != 0 ? 0 : 1) : k + 1;
+}
+__device__ __forceinline__ int item_class(int ka, int kb) { return ka < kb ? ka * 6 + kb : kb * 6 + ka; }
+// classes in descending expected cost: the work list starts the long items first
+__constant__ int kClassOrder[kClasses] = {7, 1, 10, 0, 4, 9, 8, 3, 2, 22, 28, 21, 16, 11, 5, 29, 17, 23, 35, 14, 15, 20, 6, 12, 13, 18, 19, 24, 25, 26, 27, 30, 31, 32, 33, 34};
+
 __global__ void k_broadphase(Dev d) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base;
+  __shared__ int s_warp[32], s_warp2[32];
+  __shared__ int s_base, s_ibase, s_dead;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
     int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
     int64_t P = (int64_t)n * (n - 1) / 2;
-    // pass A: count candidate pairs
-    int cnt = 0;
+    // pass A: count candidate pairs and their shape pairs (work items)
+    int cnt = 0, icnt = 0;
     for (int64_t p = threadIdx.x; p < P; p += blockDim.x) {
       int i, j; pair_from_index(p, n, i, j);
       int r1 = d.sorted[r0 + i], r2 = d.sorted[r0 + j];
-      cnt += (may_contact(d, w, r0, n, r1, r2) || constraints_between(d, r1, r2) != 0) ? 1 : 0;
+      bool may = may_contact(d, w, r0, n, r1, r2);
+      cnt += (may || constraints_between(d, r1, r2) != 0) ? 1 : 0;
+      if (may) icnt += (d.inst_off[r1 + 1] - d.inst_off[r1]) * (d.inst_off[r2 + 1] - d.inst_off[r2]);
     }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-    if (lane == 0) s_warp[wid] = cnt;
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); icnt += __shfl_down_sync(0xffffffffu, icnt, o); }
+    if (lane == 0) { s_warp[wid] = cnt; s_warp2[wid] = icnt; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int k = 0; k < nwarps; k++) tot += s_warp[k];
+      int tot = 0, itot = 0;
+      for (int k = 0; k < nwarps; k++) { tot += s_warp[k]; itot += s_warp2[k]; }
       int base = atomicAdd(&d.cur.counters[CNT_CAND], tot);
-      if ((int64_t)base + tot > d.slot_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 1; tot = 0; base = 0; }
+      int ibase = atomicAdd(&d.cur.counters[CNT_ITEMS], itot);
+      bool dead = false;
+      if ((int64_t)base + tot > d.slot_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 1; dead = true; }
+      if ((int64_t)ibase + itot > d.item_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 5; dead = true; }
+      if (dead) { tot = 0; base = 0; ibase = 0; }
       d.cur.cand_base[w] = base; d.cur.cand_n[w] = tot;
-      s_base = base;
+      s_base = base; s_ibase = ibase; s_dead = dead || tot == 0;
       d.world_min_rem[w] = d.iterations[w];
     }
     __syncthreads();
-    bool dead = d.cur.cand_n[w] == 0;
-    // pass B: ordered (enumeration order) ballot compaction
-    int running = s_base;
+    const bool dead = s_dead != 0;
+    // pass B: ordered (enumeration order) ballot compaction of the slots; work items scattered into class bins
+    int running = s_base, irunning = s_ibase;
     for (int64_t p0 = 0; p0 < P && !dead; p0 += blockDim.x) {
       int64_t p = p0 + threadIdx.x;
-      bool flag = false; int r1 = 0, r2 = 0, ncon = 0; bool may = false;
+      bool flag = false; int r1 = 0, r2 = 0, ncon = 0, nit = 0, ns2 = 0; bool may = false;
       if (p < P) {
         int i, j; pair_from_index(p, n, i, j);
         r1 = d.sorted[r0 + i]; r2 = d.sorted[r0 + j];
         may = may_contact(d, w, r0, n, r1, r2);
         ncon = constraints_between(d, r1, r2);
         flag = may || ncon != 0;
+        if (may) { ns2 = d.inst_off[r2 + 1] - d.inst_off[r2]; nit = (d.inst_off[r1 + 1] - d.inst_off[r1]) * ns2; }
       }
       unsigned bal = __ballot_sync(0xffffffffu, flag);
+      int iscan = nit;                                            // inclusive warp scan of the item counts
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, iscan, o); if (lane >= o) iscan += v; }
       __syncthreads();
       if (lane == 0) s_warp[wid] = __popc(bal);
+      if (lane == 31) s_warp2[wid] = iscan;
       __syncthreads();
-      int before = 0, total = 0;
-      for (int k = 0; k < nwarps; k++) { int c = s_warp[k]; if (k < wid) before += c; total += c; }
+      int before = 0, total = 0, ibefore = 0, itotal = 0;
+      for (int k = 0; k < nwarps; k++) { int c = s_warp[k], ic = s_warp2[k]; if (k < wid) { before += c; ibefore += ic; } total += c; itotal += ic; }
+      int s = running + before + __popc(bal & ((1u << lane) - 1u));
+      int item0 = irunning + ibefore + iscan - nit;
       if (flag) {
-        int s = running + before + __popc(bal & ((1u << lane) - 1u));
         d.cur.slot_row1[s] = r1; d.cur.slot_row2[s] = r2;
-        d.cur.slot_ccount[s] = may ? -1 : 0;      // -1: narrowphase pending
-        d.cur.slot_cstart[s] = 0; d.cur.slot_jcount[s] = 0; d.cur.slot_jstart[s] = 0;
+        d.cur.slot_ccount[s] = 0; d.cur.slot_cstart[s] = 0; d.cur.slot_jcount[s] = 0; d.cur.slot_jstart[s] = 0;
         d.cur.slot_ncon[s] = ncon; d.cur.slot_root[s] = -1;
+        d.cur.slot_item0[s] = item0; d.cur.slot_nitems[s] = nit;
       }
-      running += total;
+      // scatter the shape pairs of this candidate into the class bins (warp-aggregated atomics per class)
+      int maxit = nit;
+      for (int o = 16; o > 0; o >>= 1) maxit = max(maxit, __shfl_xor_sync(0xffffffffu, maxit, o));
+      for (int k = 0; k < maxit; k++) {
+        bool act = k < nit;
+        int ia = 0, ib = 0, cls = kClasses;
+        if (act) {
+          ia = d.inst_off[r1] + k / ns2; ib = d.inst_off[r2] + k % ns2;
+          int ka = shape_subkind(d, ia), kb = shape_subkind(d, ib);
+          if ((ka == 2 && kb == 2) || (ka == 5 && kb == 5)) { d.raw_cnt[item0 + k] = 0; act = false; }   // NarrowPhase.elm:132-134, 235-237
+          else cls = item_class(ka, kb);
+        }
+        unsigned peers = __match_any_sync(0xffffffffu, cls);
+        if (act) {
+          int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+          int basec = 0;
+          if (lane == leader) basec = atomicAdd(&d.cur.counters[CNT_CLASS0 + cls], __popc(peers));
+          basec = __shfl_sync(peers, basec, leader);
+          d.items[(size_t)cls * d.item_cap + basec + rank] = make_int4(s, ia, ib, item0 + k);
+        }
+      }
+      running += total; irunning += itotal;
     }
     __syncthreads();
   }
 }
 
-// ---- k_narrowphase : one thread per candidate pair ------------------------------------------------------
+// ---- k_narrowphase : one lane per work item, warps homogeneous in class ---------------------------------------
 __device__ __forceinline__ ShapeRef shape_ref(const Dev& d, int inst) {
   ShapeRef s; int sh = d.inst_shape[inst];
   s.kind = d.sh_kind[sh]; s.f = d.wf64 + d.inst_woff[inst]; s.ib = d.sh_i32 + d.sh_i32_off[sh];
@@ -183,49 +225,27 @@ __device__ __forceinline__ ShapeRef shape_ref(const Dev& d, int inst) {
 }
 
 __global__ void __launch_bounds__(128) k_narrowphase(Dev d) {
-  const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
-  RawContact buf[kMaxPairContacts];
   TagPt pa[kMaxPoly], pb[kMaxPoly];
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
-    if (d.cur.slot_ccount[s] != -1) continue;
-    int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-    ContactSink sink; sink.buf = buf; sink.n = 0; sink.cap = kMaxPairContacts; sink.overflow = false;
-    bool polyOvf = false;
-    unsigned short sks[kMaxPairContacts];
-    int i1b = d.inst_off[r1], i1e = d.inst_off[r1 + 1], i2b = d.inst_off[r2], i2e = d.inst_off[r2 + 1];
-    for (int a = i1b; a < i1e; a++) {
-      ShapeRef sa = shape_ref(d, a);
-      for (int b = i2b; b < i2e; b++) {
-        int n0 = sink.n;
-        shape_pair_contacts(sa, shape_ref(d, b), sink, pa, pb, polyOvf);
-        // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
-        for (int x = n0, y = sink.n - 1; x < y; x++, y--) { RawContact t = buf[x]; buf[x] = buf[y]; buf[y] = t; }
-        unsigned short sk = (unsigned short)((a - i1b + 1) * 256 + (b - i2b + 1));
-        for (int x = n0; x < sink.n; x++) sks[x] = sk;
-      }
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  int cls_i = 0, cls = kClassOrder[0], cnt = min(d.cur.counters[CNT_CLASS0 + cls], d.item_cap), first = 0;   // chunk range of the current class
+  for (int chunk = warp;; chunk += nwarps) {
+    while (cls_i < kClasses && chunk >= first + ((cnt + 31) >> 5)) {
+      first += (cnt + 31) >> 5; cls_i++;
+      if (cls_i < kClasses) { cls = kClassOrder[cls_i]; cnt = min(d.cur.counters[CNT_CLASS0 + cls], d.item_cap); }
     }
+    if (cls_i >= kClasses) break;
+    int idx = (chunk - first) * 32 + lane;
+    if (idx >= cnt) continue;
+    int4 it = d.items[(size_t)cls * d.item_cap + idx];
+    ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
+    bool polyOvf = false;
+    shape_pair_contacts(shape_ref(d, it.y), shape_ref(d, it.z), sink, pa, pb, polyOvf);
+    // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
+    for (int x = 0, y = sink.n - 1; x < y; x++, y--) { RawContact t = sink.buf[x]; sink.buf[x] = sink.buf[y]; sink.buf[y] = t; }
     if (sink.overflow) d.flags[FLAG_PAIR_OVERFLOW] = 2;
     if (polyOvf) d.flags[FLAG_POLY_OVERFLOW] = 1;
-    int n = sink.n, base = 0;
-    if (n > 0) {
-      base = atomicAdd(&d.cur.counters[CNT_CONTACTS], n);
-      if (base + n > d.contact_cap) { d.flags[FLAG_POOL_OVERFLOW] = 1; n = 0; base = 0; }
-    }
-    for (int k = 0; k < n; k++) {
-      ContactRec c;
-      int sk = sks[k];
-      int a = i1b + (sk >> 8) - 1, b = i2b + (sk & 255) - 1;
-      double f1 = d.inst_friction[a], f2 = d.inst_friction[b], b1 = d.inst_bounciness[a], b2 = d.inst_bounciness[b];
-      c.fk = buf[k].fk; c.sk = sk; c.slot = s;
-      c.ni[0] = buf[k].ni.x; c.ni[1] = buf[k].ni.y; c.ni[2] = buf[k].ni.z;
-      c.pi[0] = buf[k].pi.x; c.pi[1] = buf[k].pi.y; c.pi[2] = buf[k].pi.z;
-      c.pj[0] = buf[k].pj.x; c.pj[1] = buf[k].pj.y; c.pj[2] = buf[k].pj.z;
-      c.friction = sqrt(f1 * f2);                         // Material.elm:23-25
-      c.bounciness = (b1 + b2 + eabs(b1 - b2)) * 0.5;     // Material.elm:31-33
-      d.cur.contacts[base + k] = c;
-    }
-    d.cur.slot_cstart[s] = base; d.cur.slot_ccount[s] = n;
-    if (n > 0) hash_insert(d.cur, d.hash_mask, pair_key(d.body_world[r1], d.body_id[r1], d.body_id[r2]), s);
+    d.raw_cnt[it.w] = sink.n;
   }
 }
 
@@ -389,7 +409,10 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
 __global__ void __launch_bounds__(128) k_equations(Dev d) {
   const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
-    int nc = d.cur.slot_ccount[s], ncon = d.cur.slot_ncon[s];
+    int ncon = d.cur.slot_ncon[s];
+    const int it0 = d.cur.slot_item0[s], nit = d.cur.slot_nitems[s];
+    int nc = 0;
+    for (int k = 0; k < nit; k++) nc += d.raw_cnt[it0 + k];
     if (nc <= 0 && ncon == 0) continue;
     int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
     int w = d.body_world[r1];
@@ -397,22 +420,43 @@ __global__ void __launch_bounds__(128) k_equations(Dev d) {
     Spook sp = spook(dt);
     BodyE b1 = load_bodye(d, r1), b2 = load_bodye(d, r2);
     if (nc > 0) {
+      int c0 = atomicAdd(&d.cur.counters[CNT_CONTACTS], nc);
+      if (c0 + nc > d.contact_cap) { d.flags[FLAG_POOL_OVERFLOW] = 1; nc = 0; c0 = 0; }
+      d.cur.slot_cstart[s] = c0; d.cur.slot_ccount[s] = nc;
+      if (nc > 0) hash_insert(d.cur, d.hash_mask, pair_key(w, d.body_id[r1], d.body_id[r2]), s);
       // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128
       int ps = hash_find(d.prev, d.hash_mask, pair_key(w, d.body_id[r1], d.body_id[r2]));
       int pc0 = 0, pcn = 0;
       if (ps >= 0) { pc0 = d.prev.slot_cstart[ps]; pcn = d.prev.slot_ccount[ps]; }
-      int c0 = d.cur.slot_cstart[s];
-      for (int k = 0; k < nc; k++) {
-        const ContactRec& c = d.cur.contacts[c0 + k];
-        // Cache.lookup: first match in pairGroup.contacts order == LAST match in solver order (ContactCache.elm:76-87)
-        double lam = 0; V3 ct1 = mk(0, 0, 0);
-        for (int m = pcn - 1; m >= 0; m--) {
-          const ContactRec& p = d.prev.contacts[pc0 + m];
-          if ((p.fk - c.fk == 0) && (p.sk - c.sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
+      const int i1b = d.inst_off[r1], i2b = d.inst_off[r2], ns2 = d.inst_off[r2 + 1] - i2b;
+      int out = c0;
+      for (int k = 0; k < nit && nc > 0; k++) {          // shape1 outer, shape2 inner (NarrowPhase.elm:33-59)
+        int n = d.raw_cnt[it0 + k];
+        if (n == 0) continue;
+        int a = i1b + k / ns2, b = i2b + k % ns2;
+        int sk = (k / ns2 + 1) * 256 + (k % ns2 + 1);     // ContactId.elm:75-77
+        double f1 = d.inst_friction[a], f2 = d.inst_friction[b], e1 = d.inst_bounciness[a], e2 = d.inst_bounciness[b];
+        double friction = sqrt(f1 * f2);                          // Material.elm:23-25
+        double bounciness = (e1 + e2 + eabs(e1 - e2)) * 0.5;      // Material.elm:31-33
+        for (int x = 0; x < n; x++, out++) {
+          const RawContact rc = d.raw[(size_t)(it0 + k) * kRawStride + x];
+          ContactRec c;
+          c.fk = rc.fk; c.sk = sk; c.slot = s;
+          c.ni[0] = rc.ni.x; c.ni[1] = rc.ni.y; c.ni[2] = rc.ni.z;
+          c.pi[0] = rc.pi.x; c.pi[1] = rc.pi.y; c.pi[2] = rc.pi.z;
+          c.pj[0] = rc.pj.x; c.pj[1] = rc.pj.y; c.pj[2] = rc.pj.z;
+          c.friction = friction; c.bounciness = bounciness;
+          d.cur.contacts[out] = c;
+          // Cache.lookup: first match in pairGroup.contacts order == LAST match in solver order (ContactCache.elm:76-87)
+          double lam = 0; V3 ct1 = mk(0, 0, 0);
+          for (int m = pcn - 1; m >= 0; m--) {
+            const ContactRec& p = d.prev.contacts[pc0 + m];
+            if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
+          }
+          RowRec r;
+          contact_row(r, rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, sp, b1, b2);
+          d.cur.rows[out] = r;
         }
-        RowRec r;
-        contact_row(r, ld3(c.ni), ld3(c.pi), ld3(c.pj), c.bounciness, c.friction, lam, ct1, dt, gravity, sp, b1, b2);
-        d.cur.rows[c0 + k] = r;
       }
     }
     if (ncon != 0) {

@@ -50,6 +50,7 @@ class Engine:
         if rc != 0:
             raise EngineError(f"ep_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
         self._keep = []
+        self.path = "auto"          # 'auto' | 'general' | 'fused' (ep_configure EP_OPT_PATH), applied at upload
 
     def close(self):
         if self.ctx:
@@ -79,6 +80,7 @@ class Engine:
         self._ck(self.lib.ep_upload_shapes(self.ctx, C.byref(shapes.c)), "ep_upload_shapes")
 
     def upload_worlds(self, bodies, params, warm=None):
+        self.configure(path=self.path)
         self._ck(self.lib.ep_upload_worlds(self.ctx, C.byref(bodies.c), C.byref(params.c),
                                            C.byref(warm.c) if warm is not None else None), "ep_upload_worlds")
 
@@ -95,6 +97,7 @@ class Engine:
         self._ck(self.lib.ep_download_contacts(self.ctx, C.byref(contacts.c)), "ep_download_contacts")
 
     def step(self, bodies, params, warm=None, out=None, n_steps=1):
+        self.configure(path=self.path)
         self._ck(self.lib.ep_step(self.ctx, C.byref(bodies.c), C.byref(params.c),
                                   C.byref(warm.c) if warm is not None else None,
                                   C.byref(out.c) if out is not None else None, C.c_int32(n_steps)), "ep_step")

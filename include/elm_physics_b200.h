@@ -170,9 +170,10 @@ const char* ep_last_error(const ep_ctx* ctx);
 /* Tuning knobs, read by the next ep_upload_worlds.  EP_OPT_PATH: 0 = auto (batches of small worlds take the fused
  * one-CTA-per-world front end, everything else the general multi-kernel path), 1 = general, 2 = fused.
  * EP_OPT_CONTACT_CAP: device contact pool size (default max(16384, 16 x bodies)).  EP_OPT_RAW_CAP: per-world raw
- * contact pool of the fused path (default max(128, 12 x bodies per world)).  Exceeding a capacity is reported as
+ * contact pool of the fused path (default max(128, 12 x bodies per world)).  EP_OPT_ITEM_CAP: narrowphase work items
+ * (shape pairs of candidate body pairs) per step, general path (default max(65536, 8 x shape instances)).  Exceeding a capacity is reported as
  * EP_ECAPACITY by ep_sync / the downloads, never silently. */
-enum { EP_OPT_PATH = 0, EP_OPT_CONTACT_CAP = 1, EP_OPT_RAW_CAP = 2, EP_OPT_COUNT = 4 };
+enum { EP_OPT_PATH = 0, EP_OPT_CONTACT_CAP = 1, EP_OPT_RAW_CAP = 2, EP_OPT_ITEM_CAP = 3, EP_OPT_COUNT = 4 };
 int ep_configure(ep_ctx* ctx, int32_t option, int64_t value);
 
 /* Upload the immutable shape table (replaces nothing in the reference: shapes are Elm values
