@@ -14,6 +14,7 @@
 
 #include "ep_kernels.cuh"
 #include "ep_fused.cuh"
+#include "ep_solve.cuh"
 
 namespace ep {
 __global__ void k_export_lambda(const RowRec* rows, int n, double* lam, double* t1) {
@@ -41,6 +42,11 @@ struct ep_ctx {
   int64_t launches = 0;
   int64_t opt[EP_OPT_COUNT] = {0};
   size_t fused_smem = 0; int fused_grid = 0;
+  // solver: tiled size classes run on side streams next to the big-island kernel
+  static constexpr int kTileBins = 4;
+  cudaStream_t aux[kTileBins] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kTileBins] = {nullptr, nullptr, nullptr, nullptr};
+  int tile_grid[kTileBins] = {0, 0, 0, 0};
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -104,6 +110,18 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < ep_ctx::kTileBins && ok; i++)
+    ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_bytes(tile_dims(ep_ctx::kTileBins - 1))) == cudaSuccess;
+  for (int i = 0; i < ep_ctx::kTileBins && ok; i++) {
+    int per_sm = 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tiles, 32, tile_bytes(tile_dims(i))) == cudaSuccess && per_sm >= 1;
+    ctx->tile_grid[i] = per_sm * ctx->sm_count;
+  }
+  if (!ok) { cudaStreamDestroy(ctx->stream); delete ctx; return EP_ENODEVICE; }
   *out = ctx;
   return EP_OK;
 }
@@ -115,6 +133,8 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   free_pool(ctx->world_allocs);
   free_pool(ctx->shape_allocs);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < ep_ctx::kTileBins; i++) { if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -503,7 +523,19 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d); }
     }
-    { Timed t(ctx, EP_K_SOLVE); k_solve<<<gwide, 128, 0, st>>>(d); }
+    {   // islands by size class: classes 0..3 from shared-memory tiles on side streams, the large ones from global memory
+      Timed t(ctx, EP_K_SOLVE);
+      CK(cudaEventRecord(ctx->ev_fork, st));
+      k_solve<<<gwide, 128, 0, st>>>(d, ep_ctx::kTileBins, kBins - 1);
+      for (int i = ep_ctx::kTileBins - 1; i >= 0; i--) {
+        CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+        int grid = std::max(1, std::min(ctx->tile_grid[i], (d.n_bodies + 31) / 32));
+        k_solve_tiles<<<grid, 32, tile_bytes(tile_dims(i)), ctx->aux[i]>>>(d, i, i, i);
+        CK(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+        ctx->launches++;
+      }
+      for (int i = 0; i < ep_ctx::kTileBins; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+    }
     { Timed t(ctx, EP_K_INTEGRATE); k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d); }
     CK(cudaGetLastError());
     std::swap(d.cur, d.prev);     // the frame just computed becomes the warm-start cache

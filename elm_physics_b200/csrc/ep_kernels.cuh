@@ -564,6 +564,59 @@ __device__ __forceinline__ double gw_lambda(const double* J, const SB& b1, const
          + (J[3] * b2.vX + J[4] * b2.vY + J[5] * b2.vZ)
          + (J[6] * b2.wX + J[7] * b2.wY + J[8] * b2.wZ);
 }
+// One joint / contact-normal row (solveVelocityConstraints 572-619, solveVelocityNormals 625-672): returns deltaLambda
+__device__ __forceinline__ double row_solve(const double* J, double B, double invC, double eps, double lo, double hi, double& lam,
+                                            const BodyK& k1, const BodyK& k2, SB& s1, SB& s2) {
+  double prev = invC * (B - gw_lambda(J, s1, s2) - eps * lam);
+  double dl = (lam + prev - lo < 0) ? lo - lam : ((lam + prev - hi > 0) ? hi - lam : prev);
+  apply_row(dl, J, k1, k2, s1, s2);
+  lam = lam + dl;
+  return dl;
+}
+// One contact's friction pair (solveVelocityFrictions, Solver.elm:678-844): friction1 then friction2, cone +-mu*lambda_n
+__device__ __forceinline__ double friction_pair(const double* e1, const double* e2, double f1B, double f1InvC, double f2B, double f2InvC,
+                                                double eps, double mu, double nl, double& lamF1, double& lamF2,
+                                                const BodyK& k1, const BodyK& k2, SB& s1, SB& s2, double tot) {
+  const M33 &I1 = k1.I, &I2 = k2.I;
+  double cap1 = mu * nl;
+  double gW1 = gw_lambda(e1, s1, s2);
+  double dPrev1 = f1InvC * (f1B - gW1 - eps * lamF1);
+  double d1 = (lamF1 + dPrev1 + cap1 < 0) ? -cap1 - lamF1 : ((lamF1 + dPrev1 - cap1 > 0) ? cap1 - lamF1 : dPrev1);
+  double k1a = d1 * k1.invMass;
+  double b1vX = s1.vX - k1a * e1[3], b1vY = s1.vY - k1a * e1[4], b1vZ = s1.vZ - k1a * e1[5];
+  double b1wX = s1.wX + (I1.m11 * e1[0] + I1.m12 * e1[1] + I1.m13 * e1[2]) * d1;
+  double b1wY = s1.wY + (I1.m21 * e1[0] + I1.m22 * e1[1] + I1.m23 * e1[2]) * d1;
+  double b1wZ = s1.wZ + (I1.m31 * e1[0] + I1.m32 * e1[1] + I1.m33 * e1[2]) * d1;
+  double k1b = d1 * k2.invMass;
+  double b2vX = s2.vX + k1b * e1[3], b2vY = s2.vY + k1b * e1[4], b2vZ = s2.vZ + k1b * e1[5];
+  double b2wX = s2.wX + (I2.m11 * e1[6] + I2.m12 * e1[7] + I2.m13 * e1[8]) * d1;
+  double b2wY = s2.wY + (I2.m21 * e1[6] + I2.m22 * e1[7] + I2.m23 * e1[8]) * d1;
+  double b2wZ = s2.wZ + (I2.m31 * e1[6] + I2.m32 * e1[7] + I2.m33 * e1[8]) * d1;
+  double cap2 = mu * nl;
+  double gW2 = -(e2[3] * b1vX + e2[4] * b1vY + e2[5] * b1vZ)
+               + (e2[0] * b1wX + e2[1] * b1wY + e2[2] * b1wZ)
+               + (e2[3] * b2vX + e2[4] * b2vY + e2[5] * b2vZ)
+               + (e2[6] * b2wX + e2[7] * b2wY + e2[8] * b2wZ);
+  double dPrev2 = f2InvC * (f2B - gW2 - eps * lamF2);
+  double d2 = (lamF2 + dPrev2 + cap2 < 0) ? -cap2 - lamF2 : ((lamF2 + dPrev2 - cap2 > 0) ? cap2 - lamF2 : dPrev2);
+  if (k1.kind == 2) {
+    double k2a = d2 * k1.invMass;
+    s1.vX = b1vX - k2a * e2[3]; s1.vY = b1vY - k2a * e2[4]; s1.vZ = b1vZ - k2a * e2[5];
+    s1.wX = b1wX + (I1.m11 * e2[0] + I1.m12 * e2[1] + I1.m13 * e2[2]) * d2;
+    s1.wY = b1wY + (I1.m21 * e2[0] + I1.m22 * e2[1] + I1.m23 * e2[2]) * d2;
+    s1.wZ = b1wZ + (I1.m31 * e2[0] + I1.m32 * e2[1] + I1.m33 * e2[2]) * d2;
+  }
+  if (k2.kind == 2) {
+    double k2b = d2 * k2.invMass;
+    s2.vX = b2vX + k2b * e2[3]; s2.vY = b2vY + k2b * e2[4]; s2.vZ = b2vZ + k2b * e2[5];
+    s2.wX = b2wX + (I2.m11 * e2[6] + I2.m12 * e2[7] + I2.m13 * e2[8]) * d2;
+    s2.wY = b2wY + (I2.m21 * e2[6] + I2.m22 * e2[7] + I2.m23 * e2[8]) * d2;
+    s2.wZ = b2wZ + (I2.m31 * e2[6] + I2.m32 * e2[7] + I2.m33 * e2[8]) * d2;
+  }
+  lamF1 = lamF1 + d1;
+  lamF2 = lamF2 + d2;
+  return tot + eabs(d1) + eabs(d2);
+}
 // velocityNonFrictionGroup (Solver.elm:850-864): joints (572-619) then contact normals (625-672)
 __device__ double sweep_nonfriction(const Dev& d, int s, double tot) {
   int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
@@ -573,20 +626,16 @@ __device__ double sweep_nonfriction(const Dev& d, int s, double tot) {
   for (int k = 0; k < jn; k++) {
     JointRow& r = d.jrows[j0 + k];
     double lam = r.lam;
-    double prev = r.invC * (r.B - gw_lambda(r.J, s1, s2) - r.eps * lam);
-    double dl = (lam + prev - (-kMaxImpulse) < 0) ? (-kMaxImpulse) - lam : ((lam + prev - kMaxImpulse > 0) ? kMaxImpulse - lam : prev);
-    apply_row(dl, r.J, k1, k2, s1, s2);
-    r.lam = lam + dl;
+    double dl = row_solve(r.J, r.B, r.invC, r.eps, -kMaxImpulse, kMaxImpulse, lam, k1, k2, s1, s2);
+    r.lam = lam;
     tot = tot + eabs(dl);
   }
   int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
   for (int k = 0; k < cn; k++) {
     RowRec& r = d.cur.rows[c0 + k];
     double lam = r.lamN;
-    double prev = r.nInvC * (r.nB - gw_lambda(r.nJ, s1, s2) - r.eps * lam);
-    double dl = (lam + prev - 0.0 < 0) ? 0.0 - lam : ((lam + prev - kMaxImpulse > 0) ? kMaxImpulse - lam : prev);
-    apply_row(dl, r.nJ, k1, k2, s1, s2);
-    r.lamN = lam + dl;
+    double dl = row_solve(r.nJ, r.nB, r.nInvC, r.eps, 0.0, kMaxImpulse, lam, k1, k2, s1, s2);
+    r.lamN = lam;
     tot = tot + eabs(dl);
   }
   if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
@@ -600,94 +649,65 @@ __device__ double sweep_friction(const Dev& d, int s, double tot) {
   int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
   BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
   SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
-  const M33 &I1 = k1.I, &I2 = k2.I;
   for (int k = 0; k < cn; k++) {
     RowRec& r = d.cur.rows[c0 + k];
-    double nl = r.lamN;
-    const double* e1 = r.f1J;
-    double cap1 = r.mu * nl;
-    double gW1 = gw_lambda(e1, s1, s2);
-    double dPrev1 = r.f1InvC * (r.f1B - gW1 - r.eps * r.lamF1);
-    double d1 = (r.lamF1 + dPrev1 + cap1 < 0) ? -cap1 - r.lamF1 : ((r.lamF1 + dPrev1 - cap1 > 0) ? cap1 - r.lamF1 : dPrev1);
-    double k1a = d1 * k1.invMass;
-    double b1vX = s1.vX - k1a * e1[3], b1vY = s1.vY - k1a * e1[4], b1vZ = s1.vZ - k1a * e1[5];
-    double b1wX = s1.wX + (I1.m11 * e1[0] + I1.m12 * e1[1] + I1.m13 * e1[2]) * d1;
-    double b1wY = s1.wY + (I1.m21 * e1[0] + I1.m22 * e1[1] + I1.m23 * e1[2]) * d1;
-    double b1wZ = s1.wZ + (I1.m31 * e1[0] + I1.m32 * e1[1] + I1.m33 * e1[2]) * d1;
-    double k1b = d1 * k2.invMass;
-    double b2vX = s2.vX + k1b * e1[3], b2vY = s2.vY + k1b * e1[4], b2vZ = s2.vZ + k1b * e1[5];
-    double b2wX = s2.wX + (I2.m11 * e1[6] + I2.m12 * e1[7] + I2.m13 * e1[8]) * d1;
-    double b2wY = s2.wY + (I2.m21 * e1[6] + I2.m22 * e1[7] + I2.m23 * e1[8]) * d1;
-    double b2wZ = s2.wZ + (I2.m31 * e1[6] + I2.m32 * e1[7] + I2.m33 * e1[8]) * d1;
-    const double* e2 = r.f2J;
-    double cap2 = r.mu * nl;
-    double gW2 = -(e2[3] * b1vX + e2[4] * b1vY + e2[5] * b1vZ)
-                 + (e2[0] * b1wX + e2[1] * b1wY + e2[2] * b1wZ)
-                 + (e2[3] * b2vX + e2[4] * b2vY + e2[5] * b2vZ)
-                 + (e2[6] * b2wX + e2[7] * b2wY + e2[8] * b2wZ);
-    double dPrev2 = r.f2InvC * (r.f2B - gW2 - r.eps * r.lamF2);
-    double d2 = (r.lamF2 + dPrev2 + cap2 < 0) ? -cap2 - r.lamF2 : ((r.lamF2 + dPrev2 - cap2 > 0) ? cap2 - r.lamF2 : dPrev2);
-    if (k1.kind == 2) {
-      double k2a = d2 * k1.invMass;
-      s1.vX = b1vX - k2a * e2[3]; s1.vY = b1vY - k2a * e2[4]; s1.vZ = b1vZ - k2a * e2[5];
-      s1.wX = b1wX + (I1.m11 * e2[0] + I1.m12 * e2[1] + I1.m13 * e2[2]) * d2;
-      s1.wY = b1wY + (I1.m21 * e2[0] + I1.m22 * e2[1] + I1.m23 * e2[2]) * d2;
-      s1.wZ = b1wZ + (I1.m31 * e2[0] + I1.m32 * e2[1] + I1.m33 * e2[2]) * d2;
-    }
-    if (k2.kind == 2) {
-      double k2b = d2 * k2.invMass;
-      s2.vX = b2vX + k2b * e2[3]; s2.vY = b2vY + k2b * e2[4]; s2.vZ = b2vZ + k2b * e2[5];
-      s2.wX = b2wX + (I2.m11 * e2[6] + I2.m12 * e2[7] + I2.m13 * e2[8]) * d2;
-      s2.wY = b2wY + (I2.m21 * e2[6] + I2.m22 * e2[7] + I2.m23 * e2[8]) * d2;
-      s2.wZ = b2wZ + (I2.m31 * e2[6] + I2.m32 * e2[7] + I2.m33 * e2[8]) * d2;
-    }
-    r.lamF1 = r.lamF1 + d1;
-    r.lamF2 = r.lamF2 + d2;
-    tot = tot + eabs(d1) + eabs(d2);
+    double l1 = r.lamF1, l2 = r.lamF2;
+    tot = friction_pair(r.f1J, r.f2J, r.f1B, r.f1InvC, r.f2B, r.f2InvC, r.eps, r.mu, r.lamN, l1, l2, k1, k2, s1, s2, tot);
+    r.lamF1 = l1; r.lamF2 = l2;
   }
   if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
   if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
   return tot;
 }
 
-__global__ void __launch_bounds__(128) k_solve(Dev d) {
-  const int total = d.cur.counters[CNT_ISLANDS];
+// thread-per-island solve straight from the slot-order rows in global memory: the path of islands too large for a
+// shared-memory tile (ep_solve.cuh), and of every island in the first-correct version
+__device__ void solve_island_global(const Dev& d, int isl) {
+  int g0 = d.isl_off[isl], gn = d.isl_cnt[isl], w = d.isl_world[isl];
+  // warm start in reverse enumeration order (buildAndWarmStart walks pairGroups, Solver.elm:122-208)
+  for (int gi = gn - 1; gi >= 0; gi--) {
+    int s = d.isl_groups[g0 + gi];
+    int cn = d.cur.slot_ccount[s];
+    if (cn <= 0) continue;
+    int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+    BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
+    SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
+    int c0 = d.cur.slot_cstart[s];
+    for (int k = 0; k < cn; k++) {
+      const RowRec& r = d.cur.rows[c0 + k];
+      if (r.lamN == 0) continue;                      // Solver.elm:41
+      apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
+    }
+    if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
+    if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
+  }
+  int remaining = d.iterations[w], rem;
+  for (;;) {
+    double p1 = 0, p2;
+    for (int gi = 0; gi < gn; gi++) p1 = sweep_nonfriction(d, d.isl_groups[g0 + gi], p1);
+    // solve2Body keeps ONE running sum through both phases (Solver.elm:473-489); step adds two sums (345-358)
+    p2 = (gn == 1) ? p1 : 0;
+    for (int gi = 0; gi < gn; gi++) p2 = sweep_friction(d, d.isl_groups[g0 + gi], p2);
+    double deltaTot = (gn == 1) ? p2 : p1 + p2;
+    if (remaining == 1) { rem = 0; break; }
+    if (deltaTot - kSolverTolerance < 0) { rem = remaining - 1; break; }
+    remaining--;
+  }
+  atomicMin(&d.world_min_rem[w], rem);
+}
+
+// islands of size classes [bin_lo, bin_hi], largest class first
+__device__ __forceinline__ int island_from_worklist(const Dev& d, int t, int bin_lo, int bin_hi) {
+  int at = t, bin = bin_hi;
+  while (bin >= bin_lo && at >= d.cur.counters[CNT_BIN0 + bin]) { at -= d.cur.counters[CNT_BIN0 + bin]; bin--; }
+  return bin < bin_lo ? -1 : d.bin_items[(size_t)bin * d.n_bodies + at];
+}
+__global__ void __launch_bounds__(128) k_solve(Dev d, int bin_lo, int bin_hi) {
+  int total = 0;
+  for (int b = bin_lo; b <= bin_hi; b++) total += d.cur.counters[CNT_BIN0 + b];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    // work list: size classes from the largest down, so the longest islands start first and warps hold islands of similar length
-    int at = t, bin = kBins - 1;
-    while (bin > 0 && at >= d.cur.counters[CNT_BIN0 + bin]) { at -= d.cur.counters[CNT_BIN0 + bin]; bin--; }
-    const int isl = d.bin_items[(size_t)bin * d.n_bodies + at];
-    int g0 = d.isl_off[isl], gn = d.isl_cnt[isl], w = d.isl_world[isl];
-    // warm start in reverse enumeration order (buildAndWarmStart walks pairGroups, Solver.elm:122-208)
-    for (int gi = gn - 1; gi >= 0; gi--) {
-      int s = d.isl_groups[g0 + gi];
-      int cn = d.cur.slot_ccount[s];
-      if (cn <= 0) continue;
-      int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-      BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
-      SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
-      int c0 = d.cur.slot_cstart[s];
-      for (int k = 0; k < cn; k++) {
-        const RowRec& r = d.cur.rows[c0 + k];
-        if (r.lamN == 0) continue;                      // Solver.elm:41
-        apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
-      }
-      if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
-      if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
-    }
-    int remaining = d.iterations[w], rem;
-    for (;;) {
-      double p1 = 0, p2;
-      for (int gi = 0; gi < gn; gi++) p1 = sweep_nonfriction(d, d.isl_groups[g0 + gi], p1);
-      // solve2Body keeps ONE running sum through both phases (Solver.elm:473-489); step adds two sums (345-358)
-      p2 = (gn == 1) ? p1 : 0;
-      for (int gi = 0; gi < gn; gi++) p2 = sweep_friction(d, d.isl_groups[g0 + gi], p2);
-      double deltaTot = (gn == 1) ? p2 : p1 + p2;
-      if (remaining == 1) { rem = 0; break; }
-      if (deltaTot - kSolverTolerance < 0) { rem = remaining - 1; break; }
-      remaining--;
-    }
-    atomicMin(&d.world_min_rem[w], rem);
+    int isl = island_from_worklist(d, t, bin_lo, bin_hi);
+    if (isl >= 0) solve_island_global(d, isl);
   }
 }
 
