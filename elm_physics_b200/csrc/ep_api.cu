@@ -13,7 +13,6 @@
 #include "ep_device.cuh"
 
 #include "ep_kernels.cuh"
-#include "ep_fused.cuh"
 #include "ep_solve.cuh"
 
 namespace ep {
@@ -41,12 +40,15 @@ struct ep_ctx {
   int sm_count = 148;
   int64_t launches = 0;
   int64_t opt[EP_OPT_COUNT] = {0};
-  size_t fused_smem = 0; int fused_grid = 0;
   // solver: tiled size classes run on side streams next to the big-island kernel
   static constexpr int kTileBins = 4;
-  cudaStream_t aux[kTileBins] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kTileBins] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kAux = 8;                   // side streams of the solver's concurrent launches
+  cudaStream_t aux[kAux] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
   int tile_grid[kTileBins] = {0, 0, 0, 0};
+  int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
+  int full_grid[3] = {0, 0, 0}, head_grid[6] = {0, 0, 0, 0, 0, 0};
+  int lanes_grid = 0, build_grid = 0;
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -111,15 +113,33 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; i < ep_ctx::kTileBins && ok; i++)
+  for (int i = 0; i < ep_ctx::kAux && ok; i++)
     ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)tile_bytes(tile_dims(ep_ctx::kTileBins - 1))) == cudaSuccess;
-  for (int i = 0; i < ep_ctx::kTileBins && ok; i++) {
+  // Shared memory of the lane-solver launches, sized for the typical tile of each class: classes 0..2 stage the whole image
+  // (stand-in + 2 dynamic bodies, 2^class rows); classes 3..5 stage bodies + descriptors only (2^(class-1)+1 dynamic bodies,
+  // 2^class rows) and stream the rows.  Tiles that need more fall to the next residency mode (k_tile_build).
+  for (int i = 0; i < 3; i++) { TileDims t; t.maxB = 3; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_words(t) * 8); }
+  for (int i = 3; i < 6; i++) { TileDims t; t.maxB = (1 << (i - 1)) + 2; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_head_words(t) * 8); }
+  ok = ok && cudaFuncSetAttribute(k_solve_lanes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->tile_smem[2]) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_solve_lanes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->tile_smem[5]) == cudaSuccess;
+  for (int i = 0; i < 6 && ok; i++) {
     int per_sm = 0;
-    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tiles, 32, tile_bytes(tile_dims(i))) == cudaSuccess && per_sm >= 1;
-    ctx->tile_grid[i] = per_sm * ctx->sm_count;
+    if (i < 3) {
+      ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<2>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
+      ctx->full_grid[i] = per_sm * ctx->sm_count;
+    }
+    if (i >= 3) {
+      ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<1>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
+      ctx->head_grid[i] = per_sm * ctx->sm_count;
+    }
+  }
+  if (ok) {
+    int per_sm = 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<0>, 128, 0) == cudaSuccess && per_sm >= 1;
+    ctx->lanes_grid = per_sm * ctx->sm_count;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_build, 128, 0) == cudaSuccess && per_sm >= 1;
+    ctx->build_grid = per_sm * ctx->sm_count;
   }
   if (!ok) { cudaStreamDestroy(ctx->stream); delete ctx; return EP_ENODEVICE; }
   *out = ctx;
@@ -133,7 +153,7 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   free_pool(ctx->world_allocs);
   free_pool(ctx->shape_allocs);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-  for (int i = 0; i < ep_ctx::kTileBins; i++) { if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  for (int i = 0; i < ep_ctx::kAux; i++) { if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -203,8 +223,8 @@ static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
   TRY(dev_alloc(ctx, pool, &f.slot_cstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_ccount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_jstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_jcount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_ncon, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_root, d.slot_cap));
-  TRY(dev_alloc(ctx, pool, &f.slot_item0, d.fused ? 1 : d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_nitems, d.fused ? 1 : d.slot_cap));
-  const size_t hn = d.fused ? 1 : (size_t)d.hash_mask + 1;
+  TRY(dev_alloc(ctx, pool, &f.slot_item0, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_nitems, d.slot_cap));
+  const size_t hn = (size_t)d.hash_mask + 1;
   TRY(dev_alloc(ctx, pool, &f.hkeys, hn)); TRY(dev_alloc(ctx, pool, &f.hvals, hn));
   TRY(dev_alloc(ctx, pool, &f.cand_base, d.n_worlds)); TRY(dev_alloc(ctx, pool, &f.cand_n, d.n_worlds));
   TRY(dev_alloc(ctx, pool, &f.counters, CNT_COUNT));
@@ -282,38 +302,15 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     woff[k] = wtotal;
     wtotal += ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s];
   }
-  // Path choice: batches of small worlds take the fused front end (one CTA per world, everything in shared memory);
-  // anything larger takes the general multi-kernel path.  EP_OPT_PATH: 0 auto, 1 general, 2 fused (error if it does not fit).
   {
-    int nb_max = 1, inst_max = 1; int64_t wf_max = 1;
-    for (int w = 0; w < nw; w++) {
-      int a = B->world_body_off[w], b = B->world_body_off[w + 1];
-      nb_max = std::max(nb_max, b - a);
-      inst_max = std::max(inst_max, B->inst_off[b] - B->inst_off[a]);
-      int64_t wsum = 0;
-      for (int k = B->inst_off[a]; k < B->inst_off[b]; k++) wsum += ctx->h_sh_f64_off[B->inst_shape[k] + 1] - ctx->h_sh_f64_off[B->inst_shape[k]];
-      wf_max = std::max(wf_max, wsum);
-    }
-    int cand = std::max(1, nb_max * (nb_max - 1) / 2);
-    int raw = ctx->opt[EP_OPT_RAW_CAP] > 0 ? (int)ctx->opt[EP_OPT_RAW_CAP] : std::max(128, 12 * nb_max);
-    size_t bytes = fused_smem_bytes(nb_max, inst_max, (int)wf_max, cand, raw);
-    bool fits = nb_max <= 255 && cand <= 32767 && raw <= 32767 && bytes <= 200 * 1024;
-    if (ctx->opt[EP_OPT_PATH] == 2 && !fits) { ctx->err = "fused path requested but a world does not fit one CTA's shared memory"; return EP_ECAPACITY; }
-    d.fused = ctx->opt[EP_OPT_PATH] == 2 ? 1 : 0;      // auto = general: measured faster on B200 (profiles/r01_*)
-    d.f_nb_max = nb_max; d.f_inst_max = inst_max; d.f_wf64_max = (int)wf_max; d.f_cand_cap = cand; d.f_raw_cap = raw;
-    ctx->fused_smem = bytes;
-    if (d.fused) {
-      CK(cudaFuncSetAttribute(k_world_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      int per_sm = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_world_front, kFusedThreads, bytes));
-      if (per_sm < 1) { ctx->err = "fused kernel does not fit an SM"; return EP_ECAPACITY; }
-      ctx->fused_grid = std::max(1, std::min(nw, per_sm * ctx->sm_count));
-    }
+    int nb_max = 1;
+    for (int w = 0; w < nw; w++) nb_max = std::max(nb_max, B->world_body_off[w + 1] - B->world_body_off[w]);
+    d.nb_max = nb_max;
   }
-  std::vector<double> wf(d.fused ? 1 : std::max<int64_t>(wtotal, 1));
+  std::vector<double> wf(std::max<int64_t>(wtotal, 1));
   std::vector<int32_t> pl_inst, pl_code;
   int n_moving = 0;
-  for (int pass = 0; pass < 2 && !d.fused; pass++) {
+  for (int pass = 0; pass < 2; pass++) {
     for (int k = 0; k < ni; k++) {
       bool moving = B->kind[inst_body[k]] != EP_STATIC;
       if (moving != (pass == 0)) continue;
@@ -379,21 +376,31 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.uf_parent, nb)); TRY(dev_alloc(ctx, pool, &d.uf_count, nb)); TRY(dev_alloc(ctx, pool, &d.uf_fill, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_off, nb)); TRY(dev_alloc(ctx, pool, &d.isl_cnt, nb)); TRY(dev_alloc(ctx, pool, &d.isl_world, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_groups, d.slot_cap));
-  TRY(dev_alloc(ctx, pool, &d.bin_items, (size_t)kBins * std::max(nb, 1)));
+  TRY(dev_alloc(ctx, pool, &d.sched, d.slot_cap)); TRY(dev_alloc(ctx, pool, &d.sched_lvl, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &d.lvl_off, d.slot_cap)); TRY(dev_alloc(ctx, pool, &d.lvl_cur, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &d.isl_key, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nc, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nb, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nj, nb));
+  TRY(dev_alloc(ctx, pool, &d.isl_root, nb)); TRY(dev_alloc(ctx, pool, &d.isl_sorted, nb));
+  TRY(dev_alloc(ctx, pool, &d.key_cnt, 2 * kKeys));
+  TRY(dev_alloc(ctx, pool, &d.body_iters, nb)); TRY(dev_alloc(ctx, pool, &d.body_mark, nb));
+  CK(cudaMemsetAsync(d.body_iters, 0, std::max(nb, 1) * sizeof(int32_t), ctx->stream));
+  TRY(dev_alloc(ctx, pool, &d.tile_top, 1));
+  TRY(dev_alloc(ctx, pool, &d.tile_dir, (size_t)nb / 32 + kBins + 1));
+  for (int i = 0; i < 6; i++) d.tile_smem[i] = ctx->tile_smem[i];
   {
     int64_t icap = std::max<int64_t>(1 << 16, 8 * (int64_t)ni);
     if (ctx->opt[EP_OPT_ITEM_CAP] > 0) icap = std::max<int64_t>(ctx->opt[EP_OPT_ITEM_CAP], 64);
-    d.item_cap = d.fused ? 1 : (int32_t)std::min<int64_t>(icap, (1ll << 28));
+    d.item_cap = (int32_t)std::min<int64_t>(icap, (1ll << 28));
     TRY(dev_alloc(ctx, pool, &d.items, (size_t)kClasses * d.item_cap));
     TRY(dev_alloc(ctx, pool, &d.raw, (size_t)d.item_cap * kRawStride));
     TRY(dev_alloc(ctx, pool, &d.raw_cnt, d.item_cap));
   }
-  d.phase_cycles = nullptr;
-  if (getenv("EP_PHASE_TIMING")) { TRY(dev_alloc(ctx, pool, &d.phase_cycles, 16)); CK(cudaMemsetAsync(d.phase_cycles, 0, 16 * sizeof(unsigned long long), ctx->stream)); }
   TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));
   CK(cudaMemcpyAsync(d.world_min_rem, P->iterations, nw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d.world_n_islands, 0, std::max(nw, 1) * sizeof(int32_t), ctx->stream));
   TRY(dev_alloc(ctx, pool, &d.jrows, d.jrow_cap));
+  // tile images: 37 doubles per contact + 16 per dynamic body, with slack for the max-over-lanes padding of a tile
+  d.tile_arena_cap = (int64_t)d.contact_cap * 48 + (int64_t)d.jrow_cap * 16 + (int64_t)nb * 40 + 4096;
+  TRY(dev_alloc(ctx, pool, &d.tile_arena, (size_t)d.tile_arena_cap));
   TRY(dev_alloc(ctx, pool, &d.flags, FLAG_COUNT));
   CK(cudaMemsetAsync(d.flags, 0, FLAG_COUNT * sizeof(int32_t), ctx->stream));
   TRY(alloc_frame(ctx, d.cur, d));
@@ -435,11 +442,11 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     CK(cudaMemcpyAsync(f.slot_ccount, ccount.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.contacts, crec.data(), nc * sizeof(ContactRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.rows, rrec.data(), nc * sizeof(RowRec), cudaMemcpyHostToDevice, ctx->stream));
-    if (!d.fused) { k_hash_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng); CK(cudaGetLastError()); }
+    k_hash_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng); CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
   }
   // place every shape once (static bodies are never re-placed)
-  if (!d.fused && d.n_pl_all > 0) {
+  if (d.n_pl_all > 0) {
     k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, ctx->stream>>>(d, d.n_pl_all);
     CK(cudaGetLastError());
     // static items sit after the moving ones, so the per-step launch covers [0, n_pl_moving)
@@ -459,15 +466,16 @@ static cudaEvent_t next_event(ep_ctx* ctx) {
 }
 // Launch bracket: when profiling, every kernel gets its own start/end event on the context's stream.
 struct Timed {
-  ep_ctx* ctx; int kernel; cudaEvent_t a = nullptr;
-  Timed(ep_ctx* c, int k) : ctx(c), kernel(k) {
-    ctx->launches++; ctx->k_launches[k]++;
-    if (ctx->profiling && ctx->ev_pending.size() < (1u << 16)) { a = next_event(ctx); if (a) cudaEventRecord(a, ctx->stream); }
+  ep_ctx* ctx; int kernel; cudaStream_t st; cudaEvent_t a = nullptr;
+  Timed(ep_ctx* c, int k, cudaStream_t s = nullptr, bool count = true) : ctx(c), kernel(k), st(s ? s : c->stream) {
+    if (count) ctx->launches++;
+    ctx->k_launches[k]++;
+    if (ctx->profiling && ctx->ev_pending.size() < (1u << 16)) { a = next_event(ctx); if (a) cudaEventRecord(a, st); }
   }
   ~Timed() {
     if (!a) return;
     cudaEvent_t b = next_event(ctx);
-    if (b) { cudaEventRecord(b, ctx->stream); ctx->ev_pending.push_back({kernel, a, b}); }
+    if (b) { cudaEventRecord(b, st); ctx->ev_pending.push_back({kernel, a, b}); }
   }
 };
 static void resolve_events(ep_ctx* ctx) {     // stream must be idle
@@ -497,7 +505,8 @@ extern "C" int ep_kernel_times(ep_ctx* ctx, double* ms, int64_t* launches, int32
   return EP_OK;
 }
 extern "C" const char* ep_kernel_name(int32_t k) {
-  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate", "k_world_front"};
+  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate", "k_tile_build",
+                                          "k_solve_lanes_smem_b0", "k_solve_lanes_smem_b1", "k_solve_lanes_smem_b2", "k_solve_lanes_rows_l2", "k_solve_lanes_inplace", "k_solve_team_warp", "k_solve_team_cta"};
   return (k >= 0 && k < EP_K_COUNT) ? names[k] : "";
 }
 
@@ -512,29 +521,46 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   const int gwide = ctx->sm_count * 8;
   for (int s = 0; s < n_steps; s++) {
     CK(cudaMemsetAsync(d.cur.counters, 0, CNT_COUNT * sizeof(int32_t), st));
-    if (d.fused) {
-      { Timed t(ctx, EP_K_WORLD_FRONT); k_world_front<<<ctx->fused_grid, kFusedThreads, ctx->fused_smem, st>>>(d); }
-    } else {
+    CK(cudaMemsetAsync(d.key_cnt, 0, 2 * kKeys * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(d.tile_top, 0, sizeof(unsigned long long), st));
+    {
       CK(cudaMemsetAsync(d.cur.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), st));
       if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
       { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
-      { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d); }
+      { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d);
+        k_island_sort<<<grid_for(ctx, d.n_bodies / 2 + 1, 256, 4), 256, 0, st>>>(d); ctx->launches++; }
+      { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
     }
-    {   // islands by size class: classes 0..3 from shared-memory tiles on side streams, the large ones from global memory
-      Timed t(ctx, EP_K_SOLVE);
+    {   // islands by size class, all launches concurrent: classes 0..3 lane-per-island from shared-memory tiles, 4..6 one warp
+        // per island, 7.. one CTA per island (level-scheduled, ep_solve.cuh).  EP_K_SOLVE brackets the whole fork/join.
+      Timed t(ctx, EP_K_SOLVE, nullptr, false);
+      static const bool serial = getenv("EP_SOLVE_SERIAL") != nullptr;     // profiling aid: one class after the other
       CK(cudaEventRecord(ctx->ev_fork, st));
-      k_solve<<<gwide, 128, 0, st>>>(d, ep_ctx::kTileBins, kBins - 1);
-      for (int i = ep_ctx::kTileBins - 1; i >= 0; i--) {
-        CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
-        int grid = std::max(1, std::min(ctx->tile_grid[i], (d.n_bodies + 31) / 32));
-        k_solve_tiles<<<grid, 32, tile_bytes(tile_dims(i)), ctx->aux[i]>>>(d, i, i, i);
-        CK(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
-        ctx->launches++;
-      }
-      for (int i = 0; i < ep_ctx::kTileBins; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+      int ax = 0;
+      auto side = [&](int kind, auto&& launch) -> int {
+        cudaStream_t sx = serial ? st : ctx->aux[ax];
+        CK(cudaStreamWaitEvent(sx, ctx->ev_fork, 0));
+        { Timed tt(ctx, kind, sx); launch(sx); }
+        CK(cudaEventRecord(ctx->ev_join[ax], sx));
+        ax++;
+        return EP_OK;
+      };
+      const int tiles_cap = (d.n_bodies + 31) / 32 + 1;
+      // longest first: CTA-per-island teams, warp-per-island teams, then the lane classes from the largest down
+      TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256><<<ctx->sm_count * 2, 256, 0, sx>>>(d, 8, kBins - 1); }));
+      TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32><<<ctx->sm_count * 16, 32, 0, sx>>>(d, kLaneBinMax + 1, 7); }));
+      TRY(side(EP_K_SOLVE_LANES_ROWS_L2, [&](cudaStream_t sx) {
+        k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5);
+        k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4);
+        k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3);
+        ctx->launches += 2; }));
+      for (int i = 2; i >= 0; i--)
+        TRY(side(EP_K_SOLVE_LANES_SMEM0 + i, [&](cudaStream_t sx) { k_solve_lanes<2><<<std::min(ctx->full_grid[i], tiles_cap), 32, ctx->tile_smem[i], sx>>>(d, i, i); }));
+      { Timed tt(ctx, EP_K_SOLVE_LANES_INPLACE, st); k_solve_lanes<0><<<std::min(ctx->lanes_grid, tiles_cap / 4 + 1), 128, 0, st>>>(d, 0, kLaneBinMax); }
+      for (int i = 0; i < ax; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }
     { Timed t(ctx, EP_K_INTEGRATE); k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d); }
     CK(cudaGetLastError());
@@ -591,7 +617,7 @@ extern "C" int ep_download_contacts(ep_ctx* ctx, ep_contacts* out) {
   int32_t cnt[CNT_COUNT];
   CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const int ns = d.fused ? cnt[CNT_GROUPS] : cnt[CNT_CAND], nc = cnt[CNT_CONTACTS];
+  const int ns = cnt[CNT_CAND], nc = cnt[CNT_CONTACTS];
   std::vector<int32_t> base(nw), num(nw), row1(ns), row2(ns), cstart(ns), ccount(ns), jcount(ns), ncon(ns), root(ns), minrem(nw), nisl(nw);
   std::vector<ContactRec> crec(std::max(nc, 1));
   std::vector<double> lam(std::max(nc, 1)), t1(3 * (size_t)std::max(nc, 1)), prepos(3 * (size_t)d.n_bodies), prequat(4 * (size_t)d.n_bodies);
@@ -665,15 +691,6 @@ extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, 
 
 extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
   if (!ctx || !out) return EP_EINVAL;
-  if (ctx->have_worlds && ctx->d.phase_cycles) {      // EP_PHASE_TIMING=1: dump and reset the fused kernel's phase clocks
-    unsigned long long pc[16];
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemcpy(pc, ctx->d.phase_cycles, sizeof pc, cudaMemcpyDeviceToHost);
-    cudaMemset(ctx->d.phase_cycles, 0, sizeof pc);
-    fprintf(stderr, "[ep] k_world_front phase cycles (thread 0, summed over worlds):");
-    for (int i = 0; i < 8; i++) fprintf(stderr, " p%d=%llu", i, pc[i]);
-    fprintf(stderr, "\n");
-  }
   ctx->stats[EP_STAT_KERNEL_LAUNCHES] = ctx->launches;
   for (int i = 0; i < n && i < EP_STAT_COUNT; i++) out[i] = ctx->stats[i];
   return EP_OK;

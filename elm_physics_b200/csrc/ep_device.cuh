@@ -17,21 +17,23 @@ struct ContactRec {
 
 // `ContactEquations` + `ContactData` (src/Internal/Equation.elm:63-93): three Jacobian rows (wA, vB, wB;
 // vA = -vB) and their Spook scalars; min/max normal impulse are the constants 0 / 1e6.
+// Spook eps is the same for every row of a world (it depends on dt only) and is recomputed where needed.
 struct RowRec {
-  double nJ[9], f1J[9], f2J[9];
-  double nB, nInvC, f1B, f1InvC, f2B, f2InvC, eps, mu;
-  double lamN, lamF1, lamF2;
-  double pad;            // 40 doubles = 320 B: rows stay 64 B aligned
-};
+  double nJ[9], nB, nInvC, lamN;                                        // sweep 1 reads these 12 doubles (96 B)
+  double f1J[9], f2J[9], f1B, f1InvC, f2B, f2InvC, mu, lamF1, lamF2;   // sweep 2 reads these 25 (+ lamN)
+  double dN, dF1, dF2;   // |deltaLambda| of the last iteration, for the canonical-order sum of the team solver
+};                       // 40 doubles = 320 B: rows stay 64 B aligned
 
 // `ConstraintEquation` (src/Internal/Equation.elm:503-511); bounds are the constants -1e6 / 1e6.
-struct JointRow { double J[9]; double B, invC, eps, lam; double pad[3]; };   // 16 doubles
+struct JointRow { double J[9]; double B, invC, eps, lam; double dl; double pad[2]; };   // 16 doubles; dl = |deltaLambda| of the last iteration
 
-constexpr int kBins = 8;     // island size classes for the solver's work list (ep_solve.cuh)
+constexpr int kIterKeys = 32, kGroupKeys = 4;
+constexpr int kBins = 10;    // island size classes for the solver's work list (ep_solve.cuh)
+constexpr int kKeys = kBins * kIterKeys * kGroupKeys;
 constexpr int kClasses = 36; // narrowphase work-item classes: unordered pair of shape sub-kinds, lo * 6 + hi (ep_kernels.cuh)
 constexpr int kRawStride = 8;// raw contacts reserved per work item (plane-box emits up to 8)
 enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_GROUPS = 5, CNT_WORK = 6, CNT_ITEMS = 7,
-       CNT_BIN0 = 8, CNT_CLASS0 = 16, CNT_COUNT = 16 + kClasses };
+       CNT_BIN0 = 8, CNT_CLASS0 = CNT_BIN0 + kBins, CNT_COUNT = CNT_CLASS0 + kClasses };
 enum { FLAG_POOL_OVERFLOW = 0, FLAG_PAIR_OVERFLOW = 1, FLAG_POLY_OVERFLOW = 2, FLAG_JOINT_OVERFLOW = 3, FLAG_COUNT = 4 };
 
 struct FrameBuf {        // double-buffered: the previous frame is the warm-start cache
@@ -82,6 +84,7 @@ struct Dev {
   int32_t* uf_count;          // [n_bodies]
   int32_t* uf_fill;           // [n_bodies]
   int32_t* isl_off; int32_t* isl_cnt; int32_t* isl_world; int32_t* isl_groups;
+  int32_t *sched, *sched_lvl, *lvl_off, *lvl_cur;   // [slot_cap] level schedule of each island's groups (k_solve_team), parallel to isl_groups
   int32_t* world_min_rem;     // [n_worlds] min over islands of remaining iterations
   int32_t* world_n_islands;   // [n_worlds]
   JointRow* jrows;
@@ -92,12 +95,23 @@ struct Dev {
   int4* items;                // [kClasses][item_cap] (slot, instance a, instance b, item id)
   struct RawContact* raw;     // [item_cap][kRawStride] contacts of each item, solver order
   int32_t* raw_cnt;           // [item_cap]
-  // solver work list: islands binned by row count (largest class first)
-  int32_t* bin_items;         // [kBins][n_bodies] island indices
-  // fused small-world front end (ep_fused.cuh): every world fits one CTA's shared memory
-  int32_t fused;              // 1: k_world_front replaces place/sort/broadphase/narrowphase/equations/islands
-  int32_t f_nb_max, f_inst_max, f_wf64_max, f_cand_cap, f_raw_cap;
-  unsigned long long* phase_cycles;   // [16] per-phase clock64 sums of k_world_front (thread 0 of each CTA), debugging aid
+  // solver work list: islands sorted by (size class, predicted iterations, group count), largest / longest first, so that the
+  // 32 islands of a lane-per-island tile run about the same number of rows for about the same number of iterations
+  int32_t* isl_key;           // [n_bodies] sort key of each island
+  int32_t* isl_nc;            // [n_bodies] contacts of the island
+  int32_t* isl_nb;            // [n_bodies] dynamic bodies of the island
+  int32_t* isl_nj;            // [n_bodies] joint rows of the island
+  int32_t* isl_root;          // [n_bodies] root body row (Islands.elm:39-46)
+  int32_t* isl_sorted;        // [n_bodies] island indices in work-list order
+  int32_t* key_cnt;           // [kKeys] histogram, [kKeys..2*kKeys) scatter cursors
+  int32_t* body_iters;        // [n_bodies] iterations the island rooted at this body used last frame (the predictor)
+  int32_t* body_mark;         // [n_bodies] local index of the body inside its island's tile (0 = not yet assigned)
+  // tile images: lane-transposed copies of the islands of a tile (ep_solve.cuh)
+  double* tile_arena; int64_t tile_arena_cap;   // in doubles
+  unsigned long long* tile_top;                 // bump pointer (doubles)
+  int4* tile_dir;             // [n_bodies / 32 + kBins] (offset lo, offset hi, maxB | maxR << 16, maxC | residency mode << 28)
+  int32_t tile_smem[6];       // bytes of dynamic shared memory of the launch that serves each lane class
+  int32_t nb_max;             // largest world (bodies)
   const int32_t* sh_pl_off;   // [n_shapes+1] placement program of each shape template
   const int32_t* sh_pl_code;  // rel offset * 2 + isDirection
   FrameBuf cur, prev;

@@ -355,8 +355,8 @@ __device__ __forceinline__ void contact_row(RowRec& r, V3 ni, V3 pi, V3 pj, doub
   r.f1InvC = 1 / (compute_gimgt(b1, b2, r.f1J) + sp.eps);
   r.f2B = (-compute_gw(b1, b2, r.f2J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f2J));
   r.f2InvC = 1 / (compute_gimgt(b1, b2, r.f2J) + sp.eps);
-  r.eps = sp.eps; r.mu = friction;
-  r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.pad = 0;
+  r.mu = friction;
+  r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.dN = 0; r.dF1 = 0; r.dF2 = 0;
 }
 // addConstraintEquations (Equation.elm:157-361) for the pair (r1, r2) (global body rows; ncon < 0 == flipped registration):
 // rows are emitted per constraint in list order and consed, so the solver order is the reverse of emission:
@@ -401,7 +401,7 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
         rot_row(tmp[5], dt, gravity, sp, b1, b2, z1, x2);
       }
     }
-    for (int k = 0; k < nr; k++, e++) { tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
+    for (int k = 0; k < nr; k++, e++) { tmp[k].dl = 0; tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
   }
   jstart = j0; jcount = E;
 }
@@ -484,11 +484,16 @@ __device__ __forceinline__ int island_bin(int rows) {
   while (b < kBins - 1 && rows > (3 << b)) b++;
   return b;
 }
+__device__ __forceinline__ int island_key(int bin, int pred_iters, int groups) {
+  int it = min(max(pred_iters, 0), kIterKeys - 1);
+  int gk = groups <= 1 ? 0 : (groups == 2 ? 1 : (groups <= 4 ? 2 : 3));
+  return (bin * kIterKeys + it) * kGroupKeys + gk;
+}
 __global__ void k_islands(Dev d) {
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < d.n_worlds; w += gridDim.x * blockDim.x) {
     int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
     int* parent = d.uf_parent + r0; int* count = d.uf_count + r0; int* fill = d.uf_fill + r0;
-    for (int l = 0; l < n; l++) { parent[l] = l; count[l] = 0; }
+    for (int l = 0; l < n; l++) { parent[l] = l; count[l] = 0; d.body_mark[r0 + l] = 0; }
     int s0 = d.cur.cand_base[w], sn = d.cur.cand_n[w];
     int valid = 0;
     for (int s = s0 + sn - 1; s >= s0; s--) {           // Islands.connect inside buildAndWarmStart (Solver.elm:201-206)
@@ -514,24 +519,70 @@ __global__ void k_islands(Dev d) {
     if (nisl == 0) continue;
     int ibase = atomicAdd(&d.cur.counters[CNT_ISLANDS], nisl);
     int gbase = atomicAdd(&d.cur.counters[CNT_ISL_GROUPS], valid);
+    // per island: rows (size class), contacts, dynamic bodies
     for (int l = 0; l < n; l++) fill[l] = 0;
-    for (int s = s0; s < s0 + sn; s++) {                // island size class = row count (ep_solve work list)
+    for (int s = s0; s < s0 + sn; s++) {
       int root = d.cur.slot_root[s];
       if (root >= 0) fill[root - r0] += 3 * max(d.cur.slot_ccount[s], 0) + d.cur.slot_jcount[s];
     }
     int k = 0, goff = gbase;
     for (int l = 0; l < n; l++) if (count[l] > 0) {
       int isl = ibase + k;
-      d.isl_off[isl] = goff; d.isl_cnt[isl] = count[l]; d.isl_world[isl] = w;
+      d.isl_off[isl] = goff; d.isl_cnt[isl] = count[l]; d.isl_world[isl] = w; d.isl_root[isl] = r0 + l;
       int bin = island_bin(fill[l]);
-      int at = atomicAdd(&d.cur.counters[CNT_BIN0 + bin], 1);
-      d.bin_items[(size_t)bin * d.n_bodies + at] = isl;
+      int key = island_key(bin, d.body_iters[r0 + l], count[l]);
+      d.isl_key[isl] = key;
+      atomicAdd(&d.key_cnt[key], 1);
+      atomicAdd(&d.cur.counters[CNT_BIN0 + bin], 1);
+      d.isl_nc[isl] = 0; d.isl_nb[isl] = 0; d.isl_nj[isl] = 0;
       fill[l] = goff; goff += count[l]; k++;
+      count[l] = isl + 1;                               // root -> island index + 1 from here on (0 = no island)
     }
     for (int s = s0; s < s0 + sn; s++) {                // groups of an island stay in enumeration order
       int root = d.cur.slot_root[s];
-      if (root >= 0) d.isl_groups[fill[root - r0]++] = s;
+      if (root >= 0) {
+        d.isl_groups[fill[root - r0]++] = s;
+        d.isl_nc[count[root - r0] - 1] += max(d.cur.slot_ccount[s], 0); d.isl_nj[count[root - r0] - 1] += max(d.cur.slot_jcount[s], 0);
+      }
     }
+    for (int l = 0; l < n; l++) {                       // dynamic bodies of an island = its union-find component
+      if (d.kind[r0 + l] != 2) continue;
+      int c = count[uf_find(parent, l)];
+      if (c > 0) d.isl_nb[c - 1]++;
+    }
+  }
+}
+
+// Work-list order: every block recomputes the (tiny) exclusive prefix of the key histogram in DESCENDING key order, then
+// scatters its share of the islands.  The order inside one key is arbitrary and never influences results.
+__global__ void __launch_bounds__(256) k_island_sort(Dev d) {
+  __shared__ int s_start[kKeys];
+  __shared__ int s_warp[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int kPer = (kKeys + 255) / 256;
+  int local[kPer], sum = 0;
+  for (int j = 0; j < kPer; j++) {
+    int pos = tid * kPer + j;                       // position in descending key order
+    local[j] = pos < kKeys ? d.key_cnt[kKeys - 1 - pos] : 0;
+    sum += local[j];
+  }
+  int scan = sum;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, scan, o); if (lane >= o) scan += v; }
+  if (lane == 31) s_warp[wid] = scan;
+  __syncthreads();
+  int before = 0;
+  for (int k2 = 0; k2 < wid; k2++) before += s_warp[k2];
+  int run = before + scan - sum;
+  for (int j = 0; j < kPer; j++) {
+    int pos = tid * kPer + j;
+    if (pos < kKeys) s_start[kKeys - 1 - pos] = run;
+    run += local[j];
+  }
+  __syncthreads();
+  const int n = d.cur.counters[CNT_ISLANDS];
+  for (int isl = blockIdx.x * blockDim.x + tid; isl < n; isl += gridDim.x * blockDim.x) {
+    int key = d.isl_key[isl];
+    d.isl_sorted[s_start[key] + atomicAdd(&d.key_cnt[kKeys + key], 1)] = isl;
   }
 }
 
@@ -576,7 +627,7 @@ __device__ __forceinline__ double row_solve(const double* J, double B, double in
 // One contact's friction pair (solveVelocityFrictions, Solver.elm:678-844): friction1 then friction2, cone +-mu*lambda_n
 __device__ __forceinline__ double friction_pair(const double* e1, const double* e2, double f1B, double f1InvC, double f2B, double f2InvC,
                                                 double eps, double mu, double nl, double& lamF1, double& lamF2,
-                                                const BodyK& k1, const BodyK& k2, SB& s1, SB& s2, double tot) {
+                                                const BodyK& k1, const BodyK& k2, SB& s1, SB& s2, double tot, double& a1, double& a2) {
   const M33 &I1 = k1.I, &I2 = k2.I;
   double cap1 = mu * nl;
   double gW1 = gw_lambda(e1, s1, s2);
@@ -615,10 +666,11 @@ __device__ __forceinline__ double friction_pair(const double* e1, const double* 
   }
   lamF1 = lamF1 + d1;
   lamF2 = lamF2 + d2;
-  return tot + eabs(d1) + eabs(d2);
+  a1 = eabs(d1); a2 = eabs(d2);
+  return tot + a1 + a2;
 }
 // velocityNonFrictionGroup (Solver.elm:850-864): joints (572-619) then contact normals (625-672)
-__device__ double sweep_nonfriction(const Dev& d, int s, double tot) {
+__device__ double sweep_nonfriction(const Dev& d, int s, double eps, double tot) {
   int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
   BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
   SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
@@ -627,15 +679,15 @@ __device__ double sweep_nonfriction(const Dev& d, int s, double tot) {
     JointRow& r = d.jrows[j0 + k];
     double lam = r.lam;
     double dl = row_solve(r.J, r.B, r.invC, r.eps, -kMaxImpulse, kMaxImpulse, lam, k1, k2, s1, s2);
-    r.lam = lam;
+    r.lam = lam; r.dl = eabs(dl);
     tot = tot + eabs(dl);
   }
   int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
   for (int k = 0; k < cn; k++) {
     RowRec& r = d.cur.rows[c0 + k];
     double lam = r.lamN;
-    double dl = row_solve(r.nJ, r.nB, r.nInvC, r.eps, 0.0, kMaxImpulse, lam, k1, k2, s1, s2);
-    r.lamN = lam;
+    double dl = row_solve(r.nJ, r.nB, r.nInvC, eps, 0.0, kMaxImpulse, lam, k1, k2, s1, s2);
+    r.lamN = lam; r.dN = eabs(dl);
     tot = tot + eabs(dl);
   }
   if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
@@ -643,7 +695,7 @@ __device__ double sweep_nonfriction(const Dev& d, int s, double tot) {
   return tot;
 }
 // velocityFrictionGroup / solveVelocityFrictions (Solver.elm:678-844)
-__device__ double sweep_friction(const Dev& d, int s, double tot) {
+__device__ double sweep_friction(const Dev& d, int s, double eps, double tot) {
   int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
   if (cn <= 0) return tot;
   int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
@@ -652,65 +704,40 @@ __device__ double sweep_friction(const Dev& d, int s, double tot) {
   for (int k = 0; k < cn; k++) {
     RowRec& r = d.cur.rows[c0 + k];
     double l1 = r.lamF1, l2 = r.lamF2;
-    tot = friction_pair(r.f1J, r.f2J, r.f1B, r.f1InvC, r.f2B, r.f2InvC, r.eps, r.mu, r.lamN, l1, l2, k1, k2, s1, s2, tot);
-    r.lamF1 = l1; r.lamF2 = l2;
+    double a1, a2;
+    tot = friction_pair(r.f1J, r.f2J, r.f1B, r.f1InvC, r.f2B, r.f2InvC, eps, r.mu, r.lamN, l1, l2, k1, k2, s1, s2, tot, a1, a2);
+    r.lamF1 = l1; r.lamF2 = l2; r.dF1 = a1; r.dF2 = a2;
   }
   if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
   if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
   return tot;
 }
 
-// thread-per-island solve straight from the slot-order rows in global memory: the path of islands too large for a
-// shared-memory tile (ep_solve.cuh), and of every island in the first-correct version
-__device__ void solve_island_global(const Dev& d, int isl) {
-  int g0 = d.isl_off[isl], gn = d.isl_cnt[isl], w = d.isl_world[isl];
-  // warm start in reverse enumeration order (buildAndWarmStart walks pairGroups, Solver.elm:122-208)
-  for (int gi = gn - 1; gi >= 0; gi--) {
-    int s = d.isl_groups[g0 + gi];
-    int cn = d.cur.slot_ccount[s];
-    if (cn <= 0) continue;
-    int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-    BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
-    SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
-    int c0 = d.cur.slot_cstart[s];
-    for (int k = 0; k < cn; k++) {
-      const RowRec& r = d.cur.rows[c0 + k];
-      if (r.lamN == 0) continue;                      // Solver.elm:41
-      apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
-    }
-    if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
-    if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
+// applyContactsWarmStart of one pair group (Solver.elm:102-119): the seeded normal impulses, solver order
+__device__ void warm_group(const Dev& d, int s) {
+  int cn = d.cur.slot_ccount[s];
+  if (cn <= 0) return;
+  int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+  BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
+  SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
+  int c0 = d.cur.slot_cstart[s];
+  for (int k = 0; k < cn; k++) {
+    const RowRec& r = d.cur.rows[c0 + k];
+    if (r.lamN == 0) continue;                      // Solver.elm:41
+    apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
   }
-  int remaining = d.iterations[w], rem;
-  for (;;) {
-    double p1 = 0, p2;
-    for (int gi = 0; gi < gn; gi++) p1 = sweep_nonfriction(d, d.isl_groups[g0 + gi], p1);
-    // solve2Body keeps ONE running sum through both phases (Solver.elm:473-489); step adds two sums (345-358)
-    p2 = (gn == 1) ? p1 : 0;
-    for (int gi = 0; gi < gn; gi++) p2 = sweep_friction(d, d.isl_groups[g0 + gi], p2);
-    double deltaTot = (gn == 1) ? p2 : p1 + p2;
-    if (remaining == 1) { rem = 0; break; }
-    if (deltaTot - kSolverTolerance < 0) { rem = remaining - 1; break; }
-    remaining--;
-  }
-  atomicMin(&d.world_min_rem[w], rem);
+  if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
+  if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
 }
-
-// islands of size classes [bin_lo, bin_hi], largest class first
+// islands of size classes [bin_lo, bin_hi], largest class first: the sorted work list holds the classes contiguously in descending order
+__device__ __forceinline__ int class_start(const Dev& d, int bin) {
+  int at = 0;
+  for (int b = kBins - 1; b > bin; b--) at += d.cur.counters[CNT_BIN0 + b];
+  return at;
+}
 __device__ __forceinline__ int island_from_worklist(const Dev& d, int t, int bin_lo, int bin_hi) {
-  int at = t, bin = bin_hi;
-  while (bin >= bin_lo && at >= d.cur.counters[CNT_BIN0 + bin]) { at -= d.cur.counters[CNT_BIN0 + bin]; bin--; }
-  return bin < bin_lo ? -1 : d.bin_items[(size_t)bin * d.n_bodies + at];
+  return d.isl_sorted[class_start(d, bin_hi) + t];
 }
-__global__ void __launch_bounds__(128) k_solve(Dev d, int bin_lo, int bin_hi) {
-  int total = 0;
-  for (int b = bin_lo; b <= bin_hi; b++) total += d.cur.counters[CNT_BIN0 + b];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    int isl = island_from_worklist(d, t, bin_lo, bin_hi);
-    if (isl >= 0) solve_island_global(d, isl);
-  }
-}
-
 // ---- k_integrate : one thread per body (SolverBody.elm:97-225) ---------------------------------------------
 __global__ void k_integrate(Dev d) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < d.n_bodies; r += gridDim.x * blockDim.x) {

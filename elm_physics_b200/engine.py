@@ -50,7 +50,6 @@ class Engine:
         if rc != 0:
             raise EngineError(f"ep_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
         self._keep = []
-        self.path = "auto"          # 'auto' | 'general' | 'fused' (ep_configure EP_OPT_PATH), applied at upload
 
     def close(self):
         if self.ctx:
@@ -67,10 +66,8 @@ class Engine:
         if rc != 0:
             raise EngineError(f"{what} failed with {rc}: {self.lib.ep_last_error(self.ctx).decode()}")
 
-    def configure(self, path=None, contact_cap=None, raw_cap=None):
-        """ep_configure: path 'auto' | 'general' | 'fused'; capacities in contacts."""
-        if path is not None:
-            self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_PATH, C.c_int64({"auto": 0, "general": 1, "fused": 2}[path])), "ep_configure")
+    def configure(self, contact_cap=None, raw_cap=None):
+        """ep_configure: capacities in contacts."""
         if contact_cap is not None:
             self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_CONTACT_CAP, C.c_int64(contact_cap)), "ep_configure")
         if raw_cap is not None:
@@ -80,7 +77,6 @@ class Engine:
         self._ck(self.lib.ep_upload_shapes(self.ctx, C.byref(shapes.c)), "ep_upload_shapes")
 
     def upload_worlds(self, bodies, params, warm=None):
-        self.configure(path=self.path)
         self._ck(self.lib.ep_upload_worlds(self.ctx, C.byref(bodies.c), C.byref(params.c),
                                            C.byref(warm.c) if warm is not None else None), "ep_upload_worlds")
 
@@ -97,7 +93,6 @@ class Engine:
         self._ck(self.lib.ep_download_contacts(self.ctx, C.byref(contacts.c)), "ep_download_contacts")
 
     def step(self, bodies, params, warm=None, out=None, n_steps=1):
-        self.configure(path=self.path)
         self._ck(self.lib.ep_step(self.ctx, C.byref(bodies.c), C.byref(params.c),
                                   C.byref(warm.c) if warm is not None else None,
                                   C.byref(out.c) if out is not None else None, C.c_int32(n_steps)), "ep_step")

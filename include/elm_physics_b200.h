@@ -167,12 +167,10 @@ int ep_create(ep_ctx** out, int device);
 void ep_destroy(ep_ctx* ctx);
 const char* ep_last_error(const ep_ctx* ctx);
 
-/* Tuning knobs, read by the next ep_upload_worlds.  EP_OPT_PATH: 0 = auto (batches of small worlds take the fused
- * one-CTA-per-world front end, everything else the general multi-kernel path), 1 = general, 2 = fused.
- * EP_OPT_CONTACT_CAP: device contact pool size (default max(16384, 16 x bodies)).  EP_OPT_RAW_CAP: per-world raw
- * contact pool of the fused path (default max(128, 12 x bodies per world)).  EP_OPT_ITEM_CAP: narrowphase work items
- * (shape pairs of candidate body pairs) per step, general path (default max(65536, 8 x shape instances)).  Exceeding a capacity is reported as
- * EP_ECAPACITY by ep_sync / the downloads, never silently. */
+/* Tuning knobs, read by the next ep_upload_worlds.  EP_OPT_PATH: reserved (one device path).
+ * EP_OPT_CONTACT_CAP: device contact pool size (default max(16384, 16 x bodies)).  EP_OPT_RAW_CAP: reserved.
+ * EP_OPT_ITEM_CAP: narrowphase work items (shape pairs of candidate body pairs) per step (default max(65536, 8 x shape
+ * instances)).  Exceeding a capacity is reported as EP_ECAPACITY by ep_sync / the downloads, never silently. */
 enum { EP_OPT_PATH = 0, EP_OPT_CONTACT_CAP = 1, EP_OPT_RAW_CAP = 2, EP_OPT_ITEM_CAP = 3, EP_OPT_COUNT = 4 };
 int ep_configure(ep_ctx* ctx, int32_t option, int64_t value);
 
@@ -208,7 +206,10 @@ enum { EP_STAT_KERNEL_LAUNCHES = 0, EP_STAT_CANDIDATE_PAIRS = 1, EP_STAT_GROUPS 
  * CUDA events on the context's stream and resets the accumulators; ep_kernel_times synchronises and returns
  * the accumulated milliseconds and launch counts per kernel kind (EP_K_*).  Launch counts are always kept. */
 enum { EP_K_PLACE = 0, EP_K_SORT = 1, EP_K_BROADPHASE = 2, EP_K_NARROWPHASE = 3, EP_K_EQUATIONS = 4, EP_K_ISLANDS = 5,
-       EP_K_SOLVE = 6, EP_K_INTEGRATE = 7, EP_K_WORLD_FRONT = 8, EP_K_COUNT = 9 };
+       EP_K_SOLVE = 6, EP_K_INTEGRATE = 7, EP_K_TILE_BUILD = 8,
+       /* the solver's concurrent launches by island size class (they overlap; EP_K_SOLVE brackets all of them) */
+       EP_K_SOLVE_LANES_SMEM0 = 9, EP_K_SOLVE_LANES_SMEM1 = 10, EP_K_SOLVE_LANES_SMEM2 = 11, EP_K_SOLVE_LANES_ROWS_L2 = 12,
+       EP_K_SOLVE_LANES_INPLACE = 13, EP_K_SOLVE_TEAM_WARP = 14, EP_K_SOLVE_TEAM_CTA = 15, EP_K_COUNT = 16 };
 int ep_profile(ep_ctx* ctx, int enable);
 int ep_kernel_times(ep_ctx* ctx, double* ms_out, int64_t* launches_out, int32_t n);
 const char* ep_kernel_name(int32_t kernel);

@@ -22,13 +22,11 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-9   # north_star per-step relative tolerance; the tests below assert the stronger bit-exact bar
 
 
-@pytest.fixture(scope="module", params=["general", "fused"])
+@pytest.fixture(scope="module")
 def engine(request):
-    """Both device paths: 'general' (the default multi-kernel path, class-binned narrowphase work items) and 'fused'
-    (one CTA per small world, everything in shared memory; skipped for worlds that do not fit)."""
+    """One context on cuda:0 for the whole module (the library has one device path and no CPU fallback)."""
     from elm_physics_b200 import engine as eng
     e = eng.Engine(0)
-    e.path = request.param
     yield e
     e.close()
 
@@ -65,8 +63,6 @@ def test_stack_of_five_lockstep(engine, oracle):
 
 def test_boxes_scene_resident(engine, oracle):
     """C2: 100 boxes (pyramid + stack), 40 resident GPU steps (contacts fed back on device) == 40 oracle steps."""
-    if engine.path == "fused":
-        pytest.skip("101 bodies do not fit the fused path's shared memory")
     shapes, bodies, params = _packed(scenes.boxes_scene())
     _, bg, oo, og = H.resident_vs_oracle(oracle, engine, shapes, bodies, params, 40, what="boxes")
     assert og.n_contacts > 500
@@ -228,8 +224,6 @@ def test_full_size_c3_properties(engine):
     """BASELINE config 3 at full size (8192 worlds x 32 bodies): size-independent properties —
     (1) worlds [0,16) of the full batch are bit-identical to the same worlds stepped as their own batch,
     (2) no capacity overflow, every world reports 1 <= iterations <= 20, state finite."""
-    if engine.path != "general":
-        pytest.skip("full size runs once, on the default path")
     steps = 30
     shapes, bodies, params = scenes.mixed_worlds(8192)
     engine.upload_shapes(shapes)

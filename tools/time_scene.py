@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Device-time a resident scene step by step (per-kernel CUDA-event breakdown).  Usage:
+    python tools/time_scene.py boxes|mixed:<worlds>|pile:<bodies> [--steps K] [--preroll P]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("scene")
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--preroll", type=int, default=60)
+    a = ap.parse_args()
+    from elm_physics_b200 import engine as eng, pack, scenes
+    name, _, arg = a.scene.partition(":")
+    if name == "boxes":
+        shapes, bodies, params = pack.pack_worlds(scenes.boxes_scene())
+    elif name == "mixed":
+        shapes, bodies, params = scenes.mixed_worlds(int(arg or 1024))
+    elif name == "pile":
+        shapes, bodies, params = pack.pack_worlds(scenes.pile_scene(int(arg or 2000)))
+    else:
+        raise SystemExit("unknown scene")
+    e = eng.Engine(0)
+    e.upload_shapes(shapes)
+    e.upload_worlds(bodies, params, None)
+    e.step_resident(a.preroll)
+    e.sync()
+    e.profile(True)
+    e.step_resident(a.steps)
+    e.sync()
+    kt = e.kernel_times()
+    e.profile(False)
+    st = e.stats()
+    import helpers as H
+    out = H.contacts_for(bodies)
+    e.download_contacts(out)
+    st = e.stats()
+    main_k = {k: v for k, v in kt.items() if not k.startswith("k_solve_")}
+    tot = sum(v[0] for v in main_k.values())
+    print(json.dumps({"scene": a.scene, "bodies": bodies.n_bodies, "ms_per_step": tot / a.steps,
+                      "kernels_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in kt.items() if v[1]},
+                      "contacts": st["contacts"], "groups": st["groups"], "islands": st["islands"], "candidate_pairs": st["candidate_pairs"]}))
+    e.close()
+
+
+if __name__ == "__main__":
+    main()
