@@ -289,24 +289,36 @@ def main():
     value = body_steps_all / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call, one frame per call --------------------------------------
-    eb = end_bodies.copy()
-    eo = H.contacts_for(eb)
-    warm = end_contacts
+    # ep_step_frame = what a `simulate` loop does per frame: H2D of every per-body array from pinned host memory, one
+    # step warm-started by the previous frame's (resident) contacts, D2H of the integrated state + the frame's contacts.
+    pool = eng.PinnedPool()
+    eb = end_bodies.copy(alloc=pool.empty)
+    cap = H.contacts_for(eb)
+    eo = abi.Contacts(eb.n_worlds, cap.group_cap, cap.contact_cap, alloc=pool.empty)
+    del cap
     h2d = d2h = 0
     barrier()
-    e.step(eb, params, warm, eo, 1)       # untimed warm-up of the host path
-    warm = eo
+    e.step_frame(eb, eo)                  # untimed warm-up of the host path
     t_e2e = 0.0
     for _ in range(args.e2e_steps):
-        eo2 = H.contacts_for(eb)
         barrier()
         t0 = time.perf_counter()
-        e.step(eb, params, warm, eo2, 1)
+        e.step_frame(eb, eo)
         t_e2e += max_over_ranks(time.perf_counter() - t0)
-        h2d = eb.nbytes_in() + warm.n_contacts * 56 + warm.n_groups * 12
-        d2h = eb.nbytes_out() + eo2.n_contacts * 160 + eo2.n_groups * 80
-        warm = eo2
+        h2d = sum(getattr(eb, n).nbytes for n, _ in abi.BODY_F64_FIELDS)
+        d2h = eb.nbytes_out() + eo.n_contacts * 132 + eo.n_groups * 80 + eb.n_worlds * 12
     e2e_value = n_dyn * args.e2e_steps * world_size / t_e2e
+    e2e_parity = None
+    if world_size == 1 and not args.no_cpu_baseline:
+        # the frames above continue the timed run: check the host-buffer path against the oracle over the same frames
+        sample = min(W, 32)
+        ob = end_bodies.slice_worlds(0, sample)
+        owarm = pack.contacts_from_world_dicts([pack.contacts_world_dict(end_contacts, k) for k in range(sample)])
+        oout = H.contacts_for(ob)
+        from oracle import binding as oracle_binding
+        oracle_binding.step(shapes, ob, abi.slice_params(params, 0, sample), owarm, oout, args.e2e_steps + 1)
+        r1 = int(bodies.world_body_off[sample])
+        e2e_parity = all(getattr(eb, n)[:r1].tobytes() == getattr(ob, n).tobytes() for n in abi.BODY_INOUT)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
@@ -317,7 +329,9 @@ def main():
                    "sharding": "contiguous world-index range per rank, no data-path collective",
                    "l2": "resident state (bodies + contacts + rows) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": args.e2e_steps, "call": "ep_step(host buffers, n_steps=1), contacts fed back from the host"},
+                "steps": args.e2e_steps,
+                "call": "ep_step_frame(pinned host buffers): state H2D, one step warm-started by the resident previous frame, "
+                        "state + contacts D2H", "bit_exact_vs_oracle_32_worlds": e2e_parity},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -367,6 +381,7 @@ def main():
                     exact = exact and getattr(end_bodies, name)[r0:r1].tobytes() == getattr(ch[0], name).tobytes()
             line["parity"] = {"worlds": sample, "steps": args.steps, "bit_exact_vs_oracle": bool(exact)}
         print(json.dumps(line), flush=True)
+    pool.close()
     e.close()
     if world_size > 1:
         dist.destroy_process_group()

@@ -86,12 +86,19 @@ BODY_INOUT = ("pos", "quat", "vel", "angvel", "force", "torque", "inv_inertia_wo
 class Bodies:
     """Packed body state (ep_bodies).  Arrays are attributes: pos (n,3), quat (n,4) ..."""
 
-    def __init__(self, world_body_off, body_id, kind, inst_off, inst_shape, inst_friction, inst_bounciness, **f):
+    def __init__(self, world_body_off, body_id, kind, inst_off, inst_shape, inst_friction, inst_bounciness, alloc=None, **f):
+        """`alloc(shape, dtype)` places the per-body f64 arrays (default numpy; engine.PinnedPool.empty for pinned)."""
         self.world_body_off, self.body_id, self.kind = _i32(world_body_off), _i32(body_id), _i32(kind)
         self.n_worlds, self.n_bodies = len(self.world_body_off) - 1, len(self.body_id)
         n = self.n_bodies
         for name, w in BODY_F64_FIELDS:
-            setattr(self, name, _f64(f[name], (n, w) if w > 1 else (n,)).copy())
+            src = _f64(f[name], (n, w) if w > 1 else (n,))
+            if alloc is None:
+                setattr(self, name, src.copy())
+            else:
+                a = alloc(src.shape, np.float64)
+                a[...] = src
+                setattr(self, name, a)
         self.inst_off, self.inst_shape = _i32(inst_off), _i32(inst_shape)
         self.inst_friction, self.inst_bounciness = _f64(inst_friction), _f64(inst_bounciness)
         self.n_insts = len(self.inst_shape)
@@ -104,9 +111,9 @@ class Bodies:
                           _ptr(self.inst_off, _pi32), self.n_insts, _ptr(self.inst_shape, _pi32),
                           _ptr(self.inst_friction, _pf64), _ptr(self.inst_bounciness, _pf64))
 
-    def copy(self):
+    def copy(self, alloc=None):
         return Bodies(self.world_body_off, self.body_id, self.kind, self.inst_off, self.inst_shape,
-                      self.inst_friction, self.inst_bounciness,
+                      self.inst_friction, self.inst_bounciness, alloc=alloc,
                       **{name: getattr(self, name) for name, _ in BODY_F64_FIELDS})
 
     def slice_worlds(self, w0, w1):
@@ -162,21 +169,28 @@ def slice_params(p, w0, w1):
 class Contacts:
     """Pair groups + contacts (ep_contacts) with caller-chosen capacities."""
 
-    def __init__(self, n_worlds, group_cap, contact_cap):
+    def __init__(self, n_worlds, group_cap, contact_cap, alloc=None):
         self.n_worlds, self.group_cap, self.contact_cap = n_worlds, group_cap, contact_cap
         g, c = max(group_cap, 1), max(contact_cap, 1)
-        self.world_group_off = np.zeros(n_worlds + 1, np.int32)
-        self.group_id1 = np.zeros(g, np.int32)
-        self.group_id2 = np.zeros(g, np.int32)
-        self.group_n_constraints = np.zeros(g, np.int32)
-        self.group_contact_off = np.zeros(g + 1, np.int32)
-        self.group_pre_pos1 = np.zeros((g, 3))
-        self.group_pre_quat1 = np.zeros((g, 4))
+        if alloc is None:
+            zeros = np.zeros
+        else:
+            def zeros(shape, dtype=np.float64):
+                a = alloc(shape, dtype)
+                a[...] = 0
+                return a
+        self.world_group_off = zeros(n_worlds + 1, np.int32)
+        self.group_id1 = zeros(g, np.int32)
+        self.group_id2 = zeros(g, np.int32)
+        self.group_n_constraints = zeros(g, np.int32)
+        self.group_contact_off = zeros(g + 1, np.int32)
+        self.group_pre_pos1 = zeros((g, 3))
+        self.group_pre_quat1 = zeros((g, 4))
         for name, dt, w in CONTACT_FIELDS:
-            setattr(self, name, np.zeros((c, w) if w > 1 else (c,), dt))
-        self.iterations = np.zeros(max(n_worlds, 1), np.int32)
-        self.world_n_islands = np.zeros(max(n_worlds, 1), np.int32)
-        self.group_island = np.zeros(g, np.int32)
+            setattr(self, name, zeros((c, w) if w > 1 else (c,), dt))
+        self.iterations = zeros(max(n_worlds, 1), np.int32)
+        self.world_n_islands = zeros(max(n_worlds, 1), np.int32)
+        self.group_island = zeros(g, np.int32)
         self.c = EpContacts(
             n_worlds, group_cap, contact_cap, _ptr(self.world_group_off, _pi32), _ptr(self.group_id1, _pi32),
             _ptr(self.group_id2, _pi32), _ptr(self.group_n_constraints, _pi32), _ptr(self.group_contact_off, _pi32),

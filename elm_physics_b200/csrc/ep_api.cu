@@ -14,6 +14,7 @@
 
 #include "ep_kernels.cuh"
 #include "ep_solve.cuh"
+#include "ep_output.cuh"
 
 namespace ep {
 __global__ void k_export_lambda(const RowRec* rows, int n, double* lam, double* t1) {
@@ -54,7 +55,8 @@ struct ep_ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   struct Pending { int kernel; cudaEvent_t a, b; };
-  std::vector<Pending> ev_pending;
+  std::vector<Pending> ev_pending, np_pending;
+  double np_ms[kClasses] = {0};
   double k_ms[EP_K_COUNT] = {0};
   int64_t k_launches[EP_K_COUNT] = {0};
   int64_t stats[EP_STAT_COUNT] = {0};
@@ -223,6 +225,7 @@ static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
   TRY(dev_alloc(ctx, pool, &f.slot_cstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_ccount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_jstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_jcount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_ncon, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_root, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &f.slot_group, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_item0, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_nitems, d.slot_cap));
   const size_t hn = (size_t)d.hash_mask + 1;
   TRY(dev_alloc(ctx, pool, &f.hkeys, hn)); TRY(dev_alloc(ctx, pool, &f.hvals, hn));
@@ -405,6 +408,20 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   CK(cudaMemsetAsync(d.flags, 0, FLAG_COUNT * sizeof(int32_t), ctx->stream));
   TRY(alloc_frame(ctx, d.cur, d));
   TRY(alloc_frame(ctx, d.prev, d));
+  {   // device image of ep_contacts (ep_output.cuh)
+    OutBuf& o = d.out;
+    o.group_cap = (int32_t)std::min<int64_t>(d.slot_cap, (1ll << 31) - 2); o.contact_cap = d.contact_cap;
+    const size_t g = (size_t)o.group_cap + 1, c = (size_t)o.contact_cap;
+    TRY(dev_alloc(ctx, pool, &o.world_group_off, (size_t)nw + 1)); TRY(dev_alloc(ctx, pool, &o.group_id1, g)); TRY(dev_alloc(ctx, pool, &o.group_id2, g));
+    TRY(dev_alloc(ctx, pool, &o.group_ncon, g)); TRY(dev_alloc(ctx, pool, &o.group_contact_off, g)); TRY(dev_alloc(ctx, pool, &o.group_island, g));
+    TRY(dev_alloc(ctx, pool, &o.iterations, nw)); TRY(dev_alloc(ctx, pool, &o.world_n_islands, nw));
+    TRY(dev_alloc(ctx, pool, &o.group_pre_pos1, 3 * g)); TRY(dev_alloc(ctx, pool, &o.group_pre_quat1, 4 * g));
+    TRY(dev_alloc(ctx, pool, &o.shape_key, c)); TRY(dev_alloc(ctx, pool, &o.feature_key, c));
+    TRY(dev_alloc(ctx, pool, &o.ni, 3 * c)); TRY(dev_alloc(ctx, pool, &o.pi, 3 * c)); TRY(dev_alloc(ctx, pool, &o.pj, 3 * c));
+    TRY(dev_alloc(ctx, pool, &o.friction, c)); TRY(dev_alloc(ctx, pool, &o.bounciness, c)); TRY(dev_alloc(ctx, pool, &o.lambda, c)); TRY(dev_alloc(ctx, pool, &o.t1, 3 * c));
+    TRY(dev_alloc(ctx, pool, &o.wg_cnt, nw)); TRY(dev_alloc(ctx, pool, &o.wc_cnt, nw)); TRY(dev_alloc(ctx, pool, &o.wc_off, nw));
+    TRY(dev_alloc(ctx, pool, &o.totals, 2));
+  }
   // previous frame's contacts = warm-start cache (Physics.elm:528-529, Equation.elm:50-58)
   if (warm && warm->world_group_off && warm->world_group_off[nw] > 0) {
     int ng = warm->world_group_off[nw];
@@ -484,6 +501,15 @@ static void resolve_events(ep_ctx* ctx) {     // stream must be idle
     if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->k_ms[p.kernel] += ms;
   }
   ctx->ev_pending.clear();
+  for (auto& p : ctx->np_pending) { float ms = 0; if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->np_ms[p.kernel] += ms; }
+  if (!ctx->np_pending.empty()) {
+    int32_t cnt[CNT_COUNT];
+    cudaMemcpy(cnt, ctx->d.prev.counters, sizeof cnt, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ep] narrowphase per class (lo*6+hi; 0 box 1 convex 2 plane 3 sphere 4 capsule 5 particle): total ms over the profiled steps, items in the last step\n");
+    for (int c = 0; c < kClasses; c++) if (ctx->np_ms[c] > 0.0005 * ctx->np_pending.size() / kClasses || cnt[CNT_CLASS0 + c]) fprintf(stderr, "[ep]   class %2d (%d,%d): %9.3f ms  %8d items\n", c, c / 6, c % 6, ctx->np_ms[c], cnt[CNT_CLASS0 + c]);
+    for (int c = 0; c < kClasses; c++) ctx->np_ms[c] = 0;
+  }
+  ctx->np_pending.clear();
   ctx->ev_used = 0;
 }
 
@@ -528,7 +554,17 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
       { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }
-      { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d); }
+      static const bool np_serial = getenv("EP_NP_SERIAL") != nullptr;    // profiling aid: one launch per work-item class
+      if (np_serial && ctx->profiling) {
+        for (int c = 0; c < kClasses; c++) {
+          cudaEvent_t a = next_event(ctx), b = next_event(ctx);
+          cudaEventRecord(a, st);
+          k_narrowphase<<<gwide, 128, 0, st>>>(d, c);
+          cudaEventRecord(b, st);
+          ctx->np_pending.push_back({c, a, b});
+        }
+      } else
+      { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d, -1); }
       { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d);
         k_island_sort<<<grid_for(ctx, d.n_bodies / 2 + 1, 256, 4), 256, 0, st>>>(d); ctx->launches++; }
@@ -605,80 +641,87 @@ extern "C" int ep_download_bodies(ep_ctx* ctx, ep_bodies* B) {
   return check_flags(ctx);
 }
 
+// Compact the last computed frame on the device and copy it into the caller's ep_contacts (one D2H per array).
+static int download_contacts_async(ep_ctx* ctx, ep_contacts* out) {
+  const Dev& d = ctx->d;
+  const FrameBuf& f = d.prev;     // last computed frame
+  cudaStream_t st = ctx->stream;
+  const int nw = d.n_worlds;
+  k_out_count<<<grid_for(ctx, (int64_t)nw * 32, 128, 16), 128, 0, st>>>(d, f);
+  k_out_scan<<<1, 1024, 0, st>>>(d);
+  k_out_groups<<<grid_for(ctx, (int64_t)nw * 32, 128, 16), 128, 0, st>>>(d, f);
+  k_out_contacts<<<grid_for(ctx, d.contact_cap, 256, 8), 256, 0, st>>>(d, f);
+  CK(cudaGetLastError());
+  int32_t tot[2], cnt[CNT_COUNT];
+  CK(cudaMemcpyAsync(tot, d.out.totals, sizeof tot, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const size_t ng = (size_t)tot[0], nc = (size_t)tot[1];
+  if ((int64_t)ng > d.out.group_cap || (int64_t)nc > d.out.contact_cap) { ctx->err = "device contact image overflow"; return EP_ECAPACITY; }
+  if ((int64_t)ng > out->group_cap || (int64_t)nc > out->contact_cap) { ctx->err = "ep_contacts capacity too small"; return EP_ECAPACITY; }
+  cudaError_t e = cudaSuccess;
+  auto D2H = [&](void* dst, const void* src, size_t bytes) { if (dst && bytes && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); };
+  const OutBuf& o = d.out;
+  out->n_worlds = nw;
+  D2H(out->world_group_off, o.world_group_off, ((size_t)nw + 1) * 4);
+  D2H(out->group_id1, o.group_id1, ng * 4); D2H(out->group_id2, o.group_id2, ng * 4);
+  D2H(out->group_n_constraints, o.group_ncon, ng * 4); D2H(out->group_contact_off, o.group_contact_off, (ng + 1) * 4);
+  D2H(out->group_pre_pos1, o.group_pre_pos1, ng * 24); D2H(out->group_pre_quat1, o.group_pre_quat1, ng * 32);
+  D2H(out->shape_key, o.shape_key, nc * 4); D2H(out->feature_key, o.feature_key, nc * 8);
+  D2H(out->ni, o.ni, nc * 24); D2H(out->pi, o.pi, nc * 24); D2H(out->pj, o.pj, nc * 24);
+  D2H(out->friction, o.friction, nc * 8); D2H(out->bounciness, o.bounciness, nc * 8);
+  D2H(out->lambda, o.lambda, nc * 8); D2H(out->t1, o.t1, nc * 24);
+  D2H(out->iterations, o.iterations, (size_t)nw * 4); D2H(out->world_n_islands, o.world_n_islands, (size_t)nw * 4);
+  D2H(out->group_island, o.group_island, ng * 4);
+  if (e != cudaSuccess) { ctx->err = std::string("download: ") + cudaGetErrorString(e); return EP_ECUDA; }
+  ctx->stats[EP_STAT_CANDIDATE_PAIRS] = cnt[CNT_CAND]; ctx->stats[EP_STAT_GROUPS] = (int64_t)ng; ctx->stats[EP_STAT_CONTACTS] = (int64_t)nc;
+  ctx->stats[EP_STAT_ISLANDS] = cnt[CNT_ISLANDS];
+  ctx->launches += 4;
+  return EP_OK;
+}
+
 extern "C" int ep_download_contacts(ep_ctx* ctx, ep_contacts* out) {
   if (!ctx || !out) return EP_EINVAL;
   if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
   CK(cudaSetDevice(ctx->device));
   TRY(check_flags(ctx));
-  const Dev& d = ctx->d;
-  const FrameBuf& f = d.prev;     // last computed frame
-  cudaStream_t st = ctx->stream;
-  const int nw = d.n_worlds;
-  int32_t cnt[CNT_COUNT];
-  CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  const int ns = cnt[CNT_CAND], nc = cnt[CNT_CONTACTS];
-  std::vector<int32_t> base(nw), num(nw), row1(ns), row2(ns), cstart(ns), ccount(ns), jcount(ns), ncon(ns), root(ns), minrem(nw), nisl(nw);
-  std::vector<ContactRec> crec(std::max(nc, 1));
-  std::vector<double> lam(std::max(nc, 1)), t1(3 * (size_t)std::max(nc, 1)), prepos(3 * (size_t)d.n_bodies), prequat(4 * (size_t)d.n_bodies);
-  double *d_lam = nullptr, *d_t1 = nullptr;
-  CK(cudaMalloc(&d_lam, std::max(nc, 1) * sizeof(double)));
-  CK(cudaMalloc(&d_t1, 3 * (size_t)std::max(nc, 1) * sizeof(double)));
-  if (nc > 0) k_export_lambda<<<grid_for(ctx, nc, 256, 16), 256, 0, st>>>(f.rows, nc, d_lam, d_t1);
-  auto D2H = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
-  cudaError_t e = cudaSuccess;
-  auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  acc(D2H(base.data(), f.cand_base, nw * 4)); acc(D2H(num.data(), f.cand_n, nw * 4));
-  acc(D2H(row1.data(), f.slot_row1, ns * 4)); acc(D2H(row2.data(), f.slot_row2, ns * 4));
-  acc(D2H(cstart.data(), f.slot_cstart, ns * 4)); acc(D2H(ccount.data(), f.slot_ccount, ns * 4));
-  acc(D2H(jcount.data(), f.slot_jcount, ns * 4)); acc(D2H(ncon.data(), f.slot_ncon, ns * 4)); acc(D2H(root.data(), f.slot_root, ns * 4));
-  acc(D2H(minrem.data(), d.world_min_rem, nw * 4)); acc(D2H(nisl.data(), d.world_n_islands, nw * 4));
-  acc(D2H(crec.data(), f.contacts, (size_t)nc * sizeof(ContactRec)));
-  acc(D2H(lam.data(), d_lam, (size_t)nc * 8)); acc(D2H(t1.data(), d_t1, 3 * (size_t)nc * 8));
-  acc(D2H(prepos.data(), d.pre_pos, prepos.size() * 8)); acc(D2H(prequat.data(), d.pre_quat, prequat.size() * 8));
-  acc(cudaStreamSynchronize(st));
-  cudaFree(d_lam); cudaFree(d_t1);
-  if (e != cudaSuccess) { ctx->err = std::string("download: ") + cudaGetErrorString(e); return EP_ECUDA; }
-  // compact the valid pair slots world by world, enumeration order; contacts stay in solver order
-  int64_t ng = 0, nco = 0;
-  for (int w = 0; w < nw; w++)
-    for (int s = base[w]; s < base[w] + num[w]; s++)
-      if (ccount[s] > 0 || jcount[s] > 0) { ng++; nco += std::max(ccount[s], 0); }
-  if (ng > out->group_cap || nco > out->contact_cap) { ctx->err = "ep_contacts capacity too small"; return EP_ECAPACITY; }
-  int g = 0, c = 0;
-  out->n_worlds = nw;
-  for (int w = 0; w < nw; w++) {
-    out->world_group_off[w] = g;
-    int nbw = ctx->h_world_body_off[w + 1] - ctx->h_world_body_off[w];
-    int used = ctx->h_iterations[w] - minrem[w];
-    out->iterations[w] = nbw == 0 ? 0 : (1 - used > 0 ? 1 : used);      // Solver.elm:225-231, 275-276
-    if (out->world_n_islands) out->world_n_islands[w] = nisl[w];
-    for (int s = base[w]; s < base[w] + num[w]; s++) {
-      if (!(ccount[s] > 0 || jcount[s] > 0)) continue;
-      out->group_id1[g] = ctx->h_body_id[row1[s]]; out->group_id2[g] = ctx->h_body_id[row2[s]];
-      if (out->group_n_constraints) out->group_n_constraints[g] = ncon[s] < 0 ? -ncon[s] : ncon[s];
-      if (out->group_island) out->group_island[g] = root[s] >= 0 ? ctx->h_body_id[root[s]] : -1;
-      if (out->group_pre_pos1) {
-        memcpy(out->group_pre_pos1 + 3 * g, prepos.data() + 3 * (size_t)row1[s], 24);
-        memcpy(out->group_pre_quat1 + 4 * g, prequat.data() + 4 * (size_t)row1[s], 32);
-      }
-      out->group_contact_off[g] = c;
-      for (int k = 0; k < std::max(ccount[s], 0); k++, c++) {
-        const ContactRec& r = crec[cstart[s] + k];
-        out->shape_key[c] = r.sk; out->feature_key[c] = r.fk;
-        memcpy(out->ni + 3 * c, r.ni, 24); memcpy(out->pi + 3 * c, r.pi, 24); memcpy(out->pj + 3 * c, r.pj, 24);
-        out->friction[c] = r.friction; out->bounciness[c] = r.bounciness;
-        out->lambda[c] = lam[cstart[s] + k];
-        memcpy(out->t1 + 3 * c, t1.data() + 3 * (size_t)(cstart[s] + k), 24);
-      }
-      g++;
-    }
-  }
-  out->world_group_off[nw] = g;
-  out->group_contact_off[g] = c;
-  ctx->stats[EP_STAT_CANDIDATE_PAIRS] = cnt[CNT_CAND]; ctx->stats[EP_STAT_GROUPS] = g; ctx->stats[EP_STAT_CONTACTS] = c;
-  ctx->stats[EP_STAT_ISLANDS] = cnt[CNT_ISLANDS];
+  TRY(download_contacts_async(ctx, out));
+  CK(cudaStreamSynchronize(ctx->stream));
   return EP_OK;
+}
+
+extern "C" void* ep_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+extern "C" void ep_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
+  if (!ctx || !B) return EP_EINVAL;
+  if (!ctx->have_worlds) { ctx->err = "no resident worlds (ep_upload_worlds first)"; return EP_ESTATE; }
+  Dev& d = ctx->d;
+  if (B->n_bodies != d.n_bodies || B->n_worlds != d.n_worlds || B->n_insts != d.n_insts) { ctx->err = "ep_step_frame: topology differs from the resident batch"; return EP_ESTATE; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nb = d.n_bodies;
+  if (nb == 0) return EP_OK;
+  auto H2D = [&](const double* dst, const double* src, size_t n) { return cudaMemcpyAsync((void*)dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st); };
+  CK(H2D(d.pos, B->pos, 3 * nb)); CK(H2D(d.quat, B->quat, 4 * nb)); CK(H2D(d.vel, B->vel, 3 * nb)); CK(H2D(d.angvel, B->angvel, 3 * nb));
+  CK(H2D(d.force, B->force, 3 * nb)); CK(H2D(d.torque, B->torque, 3 * nb)); CK(H2D(d.iiw, B->inv_inertia_world, 9 * nb));
+  CK(H2D(d.inv_mass, B->inv_mass, nb)); CK(H2D(d.inv_inertia, B->inv_inertia, 3 * nb)); CK(H2D(d.ldp, B->lin_damp_pow, nb)); CK(H2D(d.adp, B->ang_damp_pow, nb));
+  CK(H2D(d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(d.ang_lock, B->ang_lock, 3 * nb)); CK(H2D(d.radius, B->bounding_radius, nb));
+  // static bodies may have been moved by the caller between frames: place every shape, not only the moving ones
+  if (d.n_pl_all > d.n_pl_moving) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
+  TRY(ep_step_resident(ctx, 1));
+  CK(cudaMemcpyAsync(B->pos, d.pos, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->quat, d.quat, 4 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->vel, d.vel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->angvel, d.angvel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->force, d.force, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->torque, d.torque, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(B->inv_inertia_world, d.iiw, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out) TRY(download_contacts_async(ctx, out));
+  return check_flags(ctx);
 }
 
 extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_contacts* warm_in, ep_contacts* out, int32_t n_steps) {

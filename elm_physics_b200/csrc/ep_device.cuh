@@ -36,6 +36,16 @@ enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_
        CNT_BIN0 = 8, CNT_CLASS0 = CNT_BIN0 + kBins, CNT_COUNT = CNT_CLASS0 + kClasses };
 enum { FLAG_POOL_OVERFLOW = 0, FLAG_PAIR_OVERFLOW = 1, FLAG_POLY_OVERFLOW = 2, FLAG_JOINT_OVERFLOW = 3, FLAG_COUNT = 4 };
 
+// The last frame's contacts in the layout of ep_contacts, compacted on the device (ep_output.cuh)
+struct OutBuf {
+  int32_t group_cap, contact_cap;
+  int32_t *world_group_off, *group_id1, *group_id2, *group_ncon, *group_contact_off, *group_island, *iterations, *world_n_islands;
+  double *group_pre_pos1, *group_pre_quat1;
+  int32_t* shape_key; int64_t* feature_key; double *ni, *pi, *pj, *friction, *bounciness, *lambda, *t1;
+  int32_t *wg_cnt, *wc_cnt, *wc_off;   // [n_worlds] valid groups / contacts of each world, first contact of each world
+  int32_t* totals;                     // [2] groups, contacts of the frame
+};
+
 struct FrameBuf {        // double-buffered: the previous frame is the warm-start cache
   ContactRec* contacts;
   RowRec* rows;
@@ -47,6 +57,7 @@ struct FrameBuf {        // double-buffered: the previous frame is the warm-star
   int32_t* slot_jcount;
   int32_t* slot_ncon;    // user constraints carried by the pair
   int32_t* slot_root;    // island root body row (-1 when the slot is not a pair group)
+  int32_t* slot_group;   // index of the slot's pair group in the compacted output (ep_output.cuh), -1 when it is none
   int32_t* slot_item0;   // first narrowphase work item (shape pair) of the slot; items are numbered shape1-major
   int32_t* slot_nitems;  // shapes1 x shapes2 when the pair passed the bounding-sphere test, else 0
   int64_t* hkeys;        // open-addressing table (world << 36 | bodyKey) -> slot
@@ -115,6 +126,7 @@ struct Dev {
   const int32_t* sh_pl_off;   // [n_shapes+1] placement program of each shape template
   const int32_t* sh_pl_code;  // rel offset * 2 + isDirection
   FrameBuf cur, prev;
+  OutBuf out;
 };
 
 }  // namespace ep

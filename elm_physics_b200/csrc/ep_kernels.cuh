@@ -224,7 +224,7 @@ __device__ __forceinline__ ShapeRef shape_ref(const Dev& d, int inst) {
   return s;
 }
 
-__global__ void __launch_bounds__(128) k_narrowphase(Dev d) {
+__global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls) {
   TagPt pa[kMaxPoly], pb[kMaxPoly];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d) {
     }
     if (cls_i >= kClasses) break;
     int idx = (chunk - first) * 32 + lane;
-    if (idx >= cnt) continue;
+    if (idx >= cnt || (only_cls >= 0 && cls != only_cls)) continue;
     int4 it = d.items[(size_t)cls * d.item_cap + idx];
     ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
     bool polyOvf = false;

@@ -16,7 +16,8 @@ _LIB = None
 
 EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
            "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream",
-           "ep_profile", "ep_kernel_times", "ep_kernel_name", "ep_configure")
+           "ep_profile", "ep_kernel_times", "ep_kernel_name", "ep_configure", "ep_step_frame", "ep_host_alloc",
+           "ep_host_free")
 
 
 class EngineError(RuntimeError):
@@ -34,10 +35,38 @@ def load_library():
         lib.ep_stream.restype = C.c_void_p
         lib.ep_kernel_name.restype = C.c_char_p
         lib.ep_destroy.restype = None
+        lib.ep_host_alloc.restype = C.c_void_p
+        lib.ep_host_alloc.argtypes = [C.c_size_t]
+        lib.ep_host_free.restype = None
+        lib.ep_host_free.argtypes = [C.c_void_p]
         for name in EXPORTS:
             getattr(lib, name)
         _LIB = lib
     return _LIB
+
+
+class PinnedPool:
+    """numpy arrays on page-locked host memory (ep_host_alloc); pass `pool.empty` as the `alloc` argument of
+    abi.Bodies / abi.Contacts so that ep_step_frame copies at full PCIe rate."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self._ptrs = []
+
+    def empty(self, shape, dtype):
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        p = self.lib.ep_host_alloc(max(nbytes, 1))
+        if not p:
+            raise EngineError(f"ep_host_alloc({nbytes}) failed")
+        self._ptrs.append(p)
+        buf = (C.c_char * max(nbytes, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+    def close(self):
+        for p in self._ptrs:
+            self.lib.ep_host_free(p)
+        self._ptrs = []
 
 
 class Engine:
@@ -96,6 +125,11 @@ class Engine:
         self._ck(self.lib.ep_step(self.ctx, C.byref(bodies.c), C.byref(params.c),
                                   C.byref(warm.c) if warm is not None else None,
                                   C.byref(out.c) if out is not None else None, C.c_int32(n_steps)), "ep_step")
+
+    def step_frame(self, bodies, out=None):
+        """ep_step_frame: one frame of the resident batch through host buffers (state in, state + contacts out)."""
+        self._ck(self.lib.ep_step_frame(self.ctx, C.byref(bodies.c), C.byref(out.c) if out is not None else None),
+                 "ep_step_frame")
 
     def stats(self):
         out = np.zeros(abi.EP_STAT_COUNT, np.int64)

@@ -17,6 +17,7 @@
 #ifndef ELM_PHYSICS_B200_H
 #define ELM_PHYSICS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -197,6 +198,19 @@ int ep_download_contacts(ep_ctx* ctx, ep_contacts* contacts);
 /* One-call form = getPairs + solve for every world: upload, n_steps, download. */
 int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_contacts* warm_in,
             ep_contacts* out, int32_t n_steps);
+
+/* One frame of the RESIDENT batch through host buffers = one `simulate` call of a loop that feeds the returned contacts
+ * back (README.md:21-28): H2D of every per-body f64 array of `bodies` (the caller may have applied forces / impulses /
+ * moved bodies between frames, src/Physics.elm:857-1017), one step with the resident contacts of the previous frame as
+ * the warm start, D2H of the integrated state and (if `out` is not NULL) of the frame's contacts.  The topology (worlds,
+ * body ids and kinds, shape instances, params, constraints) must be the one of the last ep_upload_worlds; use ep_step
+ * when it changes or when the warm start is not the previous frame. */
+int ep_step_frame(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out);
+
+/* Page-locked host memory for the buffers of ep_bodies / ep_contacts (any host memory works; pinned buffers copy at
+ * full PCIe rate and let the copies run asynchronously).  NULL when the allocation fails. */
+void* ep_host_alloc(size_t bytes);
+void ep_host_free(void* p);
 
 /* Introspection used by bench.py / tests. */
 int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n);   /* see EP_STAT_* */

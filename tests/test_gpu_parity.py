@@ -206,6 +206,36 @@ def test_warm_start_roundtrip_through_host(engine, oracle):
     H.assert_contacts_equal(oa, wb, "resident vs host round trip")
 
 
+def test_step_frame_host_buffers_lockstep(engine, oracle):
+    """ep_step_frame (host buffers in / out, resident contacts as the warm start, pinned memory) == the oracle fed its own
+    previous contacts, 60 frames, with forces applied on the host between frames (src/Physics.elm:857-1017)."""
+    from elm_physics_b200.engine import PinnedPool
+    shapes, bodies, params = scenes.mixed_worlds(6)
+    pool = PinnedPool()
+    try:
+        bo, bg = bodies.copy(), bodies.copy(alloc=pool.empty)
+        engine.upload_shapes(shapes)
+        engine.upload_worlds(bg, params, None)
+        og = abi.Contacts(bodies.n_worlds, H.contacts_for(bodies).group_cap, H.contacts_for(bodies).contact_cap, alloc=pool.empty)
+        wo = None
+        rng = np.random.RandomState(5)
+        for s in range(60):
+            if s % 7 == 3:
+                rows = rng.randint(0, bodies.n_bodies, 9)
+                push = rng.uniform(-300, 300, (9, 3))
+                for b in (bo, bg):
+                    b.force[rows] += push
+                    b.torque[rows] += 0.1 * push
+            oo = H.contacts_for(bodies)
+            oracle.step(shapes, bo, params, wo, oo, 1)
+            engine.step_frame(bg, og)
+            H.assert_contacts_equal(oo, og, f"step_frame {s}")
+            H.assert_bodies_equal(bo, bg, f"step_frame {s}")
+            wo = oo
+    finally:
+        pool.close()
+
+
 def test_python_simulate_mirror(engine):
     """The host-side mirror of Physics.simulate (physics.simulate) steps the README scene like the reference's
     own doc example: contacts fed back, ball ends on the floor; contactPoints reports the touching point."""
