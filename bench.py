@@ -215,7 +215,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from elm_physics_b200 import abi, engine as eng, pack, scenes
+    from elm_physics_b200 import abi, engine as eng, pack, scenes, sharding
     import helpers as H
 
     if not torch.cuda.is_available():
@@ -243,7 +243,8 @@ def main():
         return float(t.item())
 
     W = args.worlds
-    shapes, bodies, params = scenes.mixed_worlds(W, first_world=rank * W)     # shard = contiguous world-index range
+    w0, w1 = sharding.shard_range(W * world_size, rank, world_size)          # shard = contiguous world-index range
+    shapes, bodies, params = scenes.mixed_worlds(w1 - w0, first_world=w0)
     e = eng.Engine(local_rank)
     e.upload_shapes(shapes)
     e.upload_worlds(bodies, params, None)
@@ -283,6 +284,17 @@ def main():
     end_contacts = H.contacts_for(bodies)
     e.download_contacts(end_contacts)
     counts = e.stats()
+
+    # the only collective of the path: the final gather of the integrated state (untimed, reported)
+    gather_ms = None
+    if world_size > 1:
+        barrier()
+        t0 = time.perf_counter()
+        full = sharding.gather_body_state(end_bodies, W * world_size, device="cuda")
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * max_over_ranks(time.perf_counter() - t0)
+        assert full["pos"].shape[0] == bodies.n_bodies * world_size
+        del full
 
     n_dyn = W * BODIES_PER_WORLD
     body_steps_all = n_dyn * args.steps * world_size
@@ -334,6 +346,7 @@ def main():
                         "state + contacts D2H", "bit_exact_vs_oracle_32_worlds": e2e_parity},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "final_state_gather_ms": gather_ms,
     }
     if rank == 0:
         # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region) ------------
