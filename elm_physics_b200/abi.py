@@ -14,7 +14,7 @@ EP_STATIC, EP_DYNAMIC, EP_KINEMATIC = 1, 2, 3
 EP_POINT_TO_POINT, EP_HINGE, EP_LOCK, EP_DISTANCE = 0, 1, 2, 3
 EP_CONVEX_F64_HEADER, EP_CONVEX_I32_HEADER, EP_GROUP_F64, EP_GROUP_I32, EP_EDGE_I32 = 15, 4, 8, 5, 2
 EP_STAT_COUNT = 8
-EP_K_COUNT = 16
+EP_K_COUNT = 18
 EP_OPT_PATH, EP_OPT_CONTACT_CAP, EP_OPT_RAW_CAP = 0, 1, 2
 
 _pi32 = C.POINTER(C.c_int32)

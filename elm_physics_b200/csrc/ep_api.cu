@@ -48,7 +48,7 @@ struct ep_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
   int tile_grid[kTileBins] = {0, 0, 0, 0};
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
-  int full_grid[3] = {0, 0, 0}, head_grid[6] = {0, 0, 0, 0, 0, 0};
+  int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
   int lanes_grid = 0, build_grid = 0;
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
@@ -121,20 +121,15 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   // Shared memory of the lane-solver launches, sized for the typical tile of each class: classes 0..2 stage the whole image
   // (stand-in + 2 dynamic bodies, 2^class rows); classes 3..5 stage bodies + descriptors only (2^(class-1)+1 dynamic bodies,
   // 2^class rows) and stream the rows.  Tiles that need more fall to the next residency mode (k_tile_build).
-  for (int i = 0; i < 3; i++) { TileDims t; t.maxB = 3; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_words(t) * 8); }
-  for (int i = 3; i < 6; i++) { TileDims t; t.maxB = (1 << (i - 1)) + 2; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_head_words(t) * 8); }
+  for (int i = 0; i < 3; i++) { TileDims t; t.maxB = 3; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_words(t, 32) * 8); }
+  for (int i = 3; i < 6; i++) { TileDims t; t.maxB = (1 << (i - 1)) + 2; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_head_words(t, 32) * 8); }
   ok = ok && cudaFuncSetAttribute(k_solve_lanes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->tile_smem[2]) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_solve_lanes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->tile_smem[5]) == cudaSuccess;
   for (int i = 0; i < 6 && ok; i++) {
     int per_sm = 0;
-    if (i < 3) {
-      ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<2>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
-      ctx->full_grid[i] = per_sm * ctx->sm_count;
-    }
-    if (i >= 3) {
-      ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<1>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
-      ctx->head_grid[i] = per_sm * ctx->sm_count;
-    }
+    if (i < 3) ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<2>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
+    else ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<1>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
+    ctx->head_grid[i] = per_sm * ctx->sm_count;
   }
   if (ok) {
     int per_sm = 0;
@@ -402,7 +397,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   CK(cudaMemsetAsync(d.world_n_islands, 0, std::max(nw, 1) * sizeof(int32_t), ctx->stream));
   TRY(dev_alloc(ctx, pool, &d.jrows, d.jrow_cap));
   // tile images: 37 doubles per contact + 16 per dynamic body, with slack for the max-over-lanes padding of a tile
-  d.tile_arena_cap = (int64_t)d.contact_cap * 48 + (int64_t)d.jrow_cap * 16 + (int64_t)nb * 40 + 4096;
+  d.tile_arena_cap = (int64_t)d.contact_cap * 72 + (int64_t)d.jrow_cap * 24 + (int64_t)nb * 24 + 4096;
   TRY(dev_alloc(ctx, pool, &d.tile_arena, (size_t)d.tile_arena_cap));
   TRY(dev_alloc(ctx, pool, &d.flags, FLAG_COUNT));
   CK(cudaMemsetAsync(d.flags, 0, FLAG_COUNT * sizeof(int32_t), ctx->stream));
@@ -532,7 +527,7 @@ extern "C" int ep_kernel_times(ep_ctx* ctx, double* ms, int64_t* launches, int32
 }
 extern "C" const char* ep_kernel_name(int32_t k) {
   static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate", "k_tile_build",
-                                          "k_solve_lanes_smem_b0", "k_solve_lanes_smem_b1", "k_solve_lanes_smem_b2", "k_solve_lanes_rows_l2", "k_solve_lanes_inplace", "k_solve_team_warp", "k_solve_team_cta"};
+                                          "k_solve_lanes_b0", "k_solve_lanes_b1", "k_solve_lanes_b2", "k_solve_lanes_b3", "k_solve_lanes_b4", "k_solve_lanes_b5", "k_solve_lanes_inplace", "k_solve_team_warp", "k_solve_team_cta"};
   return (k >= 0 && k < EP_K_COUNT) ? names[k] : "";
 }
 
@@ -584,17 +579,15 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         ax++;
         return EP_OK;
       };
-      const int tiles_cap = (d.n_bodies + 31) / 32 + 1;
+      const int tiles_cap = d.n_bodies / 32 + 2;
       // longest first: CTA-per-island teams, warp-per-island teams, then the lane classes from the largest down
       TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256><<<ctx->sm_count * 2, 256, 0, sx>>>(d, 8, kBins - 1); }));
       TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32><<<ctx->sm_count * 16, 32, 0, sx>>>(d, kLaneBinMax + 1, 7); }));
-      TRY(side(EP_K_SOLVE_LANES_ROWS_L2, [&](cudaStream_t sx) {
-        k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5);
-        k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4);
-        k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3);
-        ctx->launches += 2; }));
+      TRY(side(EP_K_SOLVE_LANES_B5, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5); }));
+      TRY(side(EP_K_SOLVE_LANES_B4, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4); }));
+      TRY(side(EP_K_SOLVE_LANES_B3, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3); }));
       for (int i = 2; i >= 0; i--)
-        TRY(side(EP_K_SOLVE_LANES_SMEM0 + i, [&](cudaStream_t sx) { k_solve_lanes<2><<<std::min(ctx->full_grid[i], tiles_cap), 32, ctx->tile_smem[i], sx>>>(d, i, i); }));
+        TRY(side(EP_K_SOLVE_LANES_B0 + i, [&](cudaStream_t sx) { k_solve_lanes<2><<<std::min(ctx->head_grid[i], tiles_cap), 32, ctx->tile_smem[i], sx>>>(d, i, i); }));
       { Timed tt(ctx, EP_K_SOLVE_LANES_INPLACE, st); k_solve_lanes<0><<<std::min(ctx->lanes_grid, tiles_cap / 4 + 1), 128, 0, st>>>(d, 0, kLaneBinMax); }
       for (int i = 0; i < ax; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }

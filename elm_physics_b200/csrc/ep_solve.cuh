@@ -10,9 +10,9 @@
 //       the same rows for about the same number of iterations.  k_tile_build gathers each tile ONCE into a lane-transposed
 //       image (word k of lane l at [k][l]: every access of the warp is one coalesced 256 B request / conflict-free LDS.64):
 //       Jacobian rows, Spook scalars, lambdas, the islands' dynamic bodies (constants + solver-body delta velocities) and
-//       per-row descriptors (which two bodies a row couples).  k_solve_lanes<2> stages the whole image in shared memory
-//       (small classes), k_solve_lanes<1> stages bodies + descriptors and streams the rows from L2 one row ahead of their
-//       use; HBM sees each row once per step instead of once per iteration.
+//       per-row descriptors (which two bodies a row couples).  k_solve_lanes<L> stages the image in shared memory and iterates
+//       there; HBM sees each row once per step instead of once per iteration.  Large classes put fewer islands in a tile
+//       (class_lanes) so that it still fits.
 //   classes above           one CTA per island, the pair groups of one dependency level in parallel (k_solve_team).
 #pragma once
 #include "ep_kernels.cuh"
@@ -21,42 +21,75 @@ namespace ep {
 
 constexpr int kLaneBinMax = 5;   // islands of up to 32 contacts (96 rows) run lane-per-island
 // Tile image of 32 islands, every array lane-transposed ([k][lane]); in this order:
-//   bodies  [maxB][16] f64   invMass, I (m11 m21 m31 m12 ...), solver-body delta v/w.  Local body 0 is the shared stand-in of
-//                            every non-dynamic body: their solver bodies are zero and never modified (Solver.elm:507,531,796,815)
+//   bodies  [maxB][8] f64    invMass, solver-body delta v/w (6), pad.  Local body 0 is the shared stand-in of every non-dynamic
+//                            body: invMass 0, deltas 0 (their solver bodies are never modified, Solver.elm:507,531,796,815)
 //   ints    [maxB] body row | [maxR] sweep-1 descriptors | [maxC] sweep-2 descriptors | [maxC] global contact index
-//   nrows   [maxR][12] f64   sweep-1 rows in solver order (per group: joint rows, then contact normals): J[9], B, invC, lambda
-//   frows   [maxC][25] f64   sweep-2 rows: f1J[9], f2J[9], f1B, f1InvC, f2B, f2InvC, mu, lambdaF1, lambdaF2
+//   nrows   [maxR][18] f64   sweep-1 rows in solver order (per group: joint rows, then contact normals):
+//                            J[9], I1.wA (3), I2.wB (3), B, invC, lambda
+//   frows   [maxC][37] f64   sweep-2 rows: f1J[9], I1.wA, I2.wB, f2J[9], I1.wA, I2.wB, f1B, f1InvC, f2B, f2InvC, mu, lambdaF1, lambdaF2
+// I.w = invInertiaWorld x the row's angular Jacobian: the reference evaluates (I.w) * deltaLambda on every row of every
+// iteration (Solver.elm:505-550); I and w are constant during the solve, so the product is formed ONCE here, with the same
+// operations in the same order, and the solver neither holds the 3x3 matrices in registers nor redoes the 15 flops.
+// For the stand-in body I = 0 and invMass = 0, so its update adds +-0 to +0: it stays +0 without any branch on the body kind.
 // descriptor = local body1 | local body2 << 8 | (sweep 1: joint flag << 16, first-row-of-group flag << 17)
 //                                              | (sweep 2: index of the contact's normal row << 16)
-constexpr int kBodyF64 = 16, kNRowF64 = 12, kFRowF64 = 25;
+constexpr int kBodyF64 = 8, kNRowF64 = 18, kFRowF64 = 37;
+enum { NR_IA = 9, NR_IB = 12, NR_B = 15, NR_INVC = 16, NR_LAM = 17 };
+enum { FR_E1 = 0, FR_E1IA = 9, FR_E1IB = 12, FR_E2 = 15, FR_E2IA = 24, FR_E2IB = 27, FR_F1B = 30, FR_F1INVC = 31, FR_F2B = 32, FR_F2INVC = 33,
+       FR_MU = 34, FR_L1 = 35, FR_L2 = 36 };
 enum { DESC_JOINT = 1 << 16, DESC_GROUP_START = 1 << 17 };
+// Islands per tile (= active lanes of its warp) by size class.  Measured on B200: putting fewer islands of the large
+// classes in a tile so that the whole image fits shared memory does NOT pay (the tile's latency is the FP64 dependency
+// chain, ~1900 cycles per contact-iteration wherever the rows live, and 8x more tiles then queue for the same SM slots),
+// so every class uses full warps and the large classes stream their rows from L2 one row ahead.
+__host__ __device__ constexpr int class_lanes(int bin) { return 32; }
 struct TileDims { int maxB, maxR, maxC; };
-__host__ __device__ inline int64_t tile_head_words(TileDims t) { return 32 * (int64_t)(kBodyF64 * t.maxB) + 16 * (int64_t)(t.maxB + t.maxR + 2 * t.maxC); }
-__host__ __device__ inline int64_t tile_words(TileDims t) { return tile_head_words(t) + 32 * (int64_t)(kNRowF64 * t.maxR + kFRowF64 * t.maxC); }   // 8-byte words
+__host__ __device__ inline int64_t tile_head_words(TileDims t, int L) { return L * (int64_t)(kBodyF64 * t.maxB) + (L / 2) * (int64_t)(t.maxB + t.maxR + 2 * t.maxC); }
+__host__ __device__ inline int64_t tile_words(TileDims t, int L) { return tile_head_words(t, L) + L * (int64_t)(kNRowF64 * t.maxR + kFRowF64 * t.maxC); }   // 8-byte words
 
-struct Tile {
-  double* bd; int* ti; double* rd; int lane; TileDims t;     // bodies, ints, rows (each may live in shared or global memory)
-  __device__ __forceinline__ double& body(int b, int f) const { return bd[(b * kBodyF64 + f) * 32 + lane]; }
-  __device__ __forceinline__ int& body_row(int b) const { return ti[b * 32 + lane]; }
-  __device__ __forceinline__ int& desc1(int r) const { return ti[(t.maxB + r) * 32 + lane]; }
-  __device__ __forceinline__ int& desc2(int c) const { return ti[(t.maxB + t.maxR + c) * 32 + lane]; }
-  __device__ __forceinline__ int& contact_index(int c) const { return ti[(t.maxB + t.maxR + t.maxC + c) * 32 + lane]; }
-  __device__ __forceinline__ double& nrow(int r, int f) const { return rd[(r * kNRowF64 + f) * 32 + lane]; }
-  __device__ __forceinline__ double& frow(int c, int f) const { return rd[(t.maxR * kNRowF64 + c * kFRowF64 + f) * 32 + lane]; }
+// LT > 0: compile-time lane stride (the staged kernels); LT == 0: run-time stride (the in-place fallback)
+template <int LT>
+struct TileT {
+  double* bd; int* ti; double* rd; int lane; int Lrt; TileDims t;     // bodies, ints, rows
+  __device__ __forceinline__ int L() const { return LT ? LT : Lrt; }
+  __device__ __forceinline__ double& body(int b, int f) const { return bd[(b * kBodyF64 + f) * L() + lane]; }
+  __device__ __forceinline__ int& body_row(int b) const { return ti[b * L() + lane]; }
+  __device__ __forceinline__ int& desc1(int r) const { return ti[(t.maxB + r) * L() + lane]; }
+  __device__ __forceinline__ int& desc2(int c) const { return ti[(t.maxB + t.maxR + c) * L() + lane]; }
+  __device__ __forceinline__ int& contact_index(int c) const { return ti[(t.maxB + t.maxR + t.maxC + c) * L() + lane]; }
+  __device__ __forceinline__ double& nrow(int r, int f) const { return rd[(r * kNRowF64 + f) * L() + lane]; }
+  __device__ __forceinline__ double& frow(int c, int f) const { return rd[(t.maxR * kNRowF64 + c * kFRowF64 + f) * L() + lane]; }
+  // head = bodies + ints (may be staged in shared memory on its own), rows behind it in the image
+  __device__ __forceinline__ void bind(double* head, double* rows) {
+    bd = head; ti = (int*)(head + L() * (int64_t)(kBodyF64 * t.maxB)); rd = rows;
+  }
 };
-__device__ __forceinline__ void tile_bind(Tile& T, double* head, double* rows) {
-  T.bd = head; T.ti = (int*)(head + 32 * (int64_t)(kBodyF64 * T.t.maxB)); T.rd = rows;
+// I.w of both bodies of a row, written behind its Jacobian (same expression as applyVelocityBody1/2, Solver.elm:505-550)
+template <class TT>
+__device__ __forceinline__ void tile_write_jac(const TT& T, bool frow, int idx, int f0, const double* J, const M33& I1, const M33& I2) {
+  double v[15];
+#pragma unroll
+  for (int k = 0; k < 9; k++) v[k] = J[k];
+  v[9] = I1.m11 * J[0] + I1.m12 * J[1] + I1.m13 * J[2];
+  v[10] = I1.m21 * J[0] + I1.m22 * J[1] + I1.m23 * J[2];
+  v[11] = I1.m31 * J[0] + I1.m32 * J[1] + I1.m33 * J[2];
+  v[12] = I2.m11 * J[6] + I2.m12 * J[7] + I2.m13 * J[8];
+  v[13] = I2.m21 * J[6] + I2.m22 * J[7] + I2.m23 * J[8];
+  v[14] = I2.m31 * J[6] + I2.m32 * J[7] + I2.m33 * J[8];
+#pragma unroll
+  for (int k = 0; k < 15; k++) { if (frow) T.frow(idx, f0 + k) = v[k]; else T.nrow(idx, f0 + k) = v[k]; }
 }
 
 // Tiles of the lane classes are numbered class kLaneBinMax first; tile t of class b holds sorted islands
-// [class_start(b) + 32 t, ...).  Returns false past the last tile of class 0.
-struct TileRef { int bin, first, count; };     // first sorted index, islands in the tile (1..32)
+// [class_start(b) + L_b t, ...).  Returns false past the last tile of class 0.
+struct TileRef { int bin, first, count; };     // first sorted index, islands in the tile (1..class_lanes(bin))
+__device__ __forceinline__ int class_tiles(const Dev& d, int b) { return (d.cur.counters[CNT_BIN0 + b] + class_lanes(b) - 1) / class_lanes(b); }
 __device__ __forceinline__ bool lane_tile(const Dev& d, int gtile, TileRef& r) {
   int base = 0;
   for (int b = kBins - 1; b > kLaneBinMax; b--) base += d.cur.counters[CNT_BIN0 + b];
   for (int b = kLaneBinMax; b >= 0; b--) {
-    int cnt = d.cur.counters[CNT_BIN0 + b], nt = (cnt + 31) >> 5;
-    if (gtile < nt) { r.bin = b; r.first = base + gtile * 32; r.count = min(32, cnt - gtile * 32); return true; }
+    const int cnt = d.cur.counters[CNT_BIN0 + b], L = class_lanes(b), nt = (cnt + L - 1) / L;
+    if (gtile < nt) { r.bin = b; r.first = base + gtile * L; r.count = min(L, cnt - gtile * L); return true; }
     gtile -= nt; base += cnt;
   }
   return false;
@@ -67,7 +100,7 @@ __device__ __forceinline__ int warp_max(int v) {
 }
 
 // ---- k_tile_build : one warp per tile, one lane per island ---------------------------------------------------------------
-// Residency mode of a tile, decided here from the dynamic shared memory of the launches (Dev::tile_smem): 2 = whole image
+// Residency of a tile, decided here from the dynamic shared memory of the class's launch (Dev::tile_smem): 2 = whole image
 // staged in shared memory, 1 = bodies + descriptors staged and the rows streamed from L2 one row ahead, 0 = in place.
 __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
   const int lane = threadIdx.x & 31;
@@ -75,6 +108,7 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
   for (int gtile = warp;; gtile += nwarps) {
     TileRef tr;
     if (!lane_tile(d, gtile, tr)) break;
+    const int L = class_lanes(tr.bin);
     const int isl = lane < tr.count ? d.isl_sorted[tr.first + lane] : -1;
     const int g0 = isl >= 0 ? d.isl_off[isl] : 0, gn = isl >= 0 ? d.isl_cnt[isl] : 0;
     const int nc = isl >= 0 ? d.isl_nc[isl] : 0, nj = isl >= 0 ? d.isl_nj[isl] : 0;
@@ -82,12 +116,9 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
     td.maxB = warp_max(isl >= 0 ? d.isl_nb[isl] : 0) + 1;
     td.maxR = warp_max(nc + nj);
     td.maxC = warp_max(nc);
-    const int64_t words = tile_words(td), head = tile_head_words(td);
-    int mode = 0;
-    if (td.maxB < 256 && td.maxR < 256) {
-      if (tr.bin <= 2) mode = words * 8 <= d.tile_smem[tr.bin] ? 2 : (head * 8 <= d.tile_smem[3] ? 1 : 0);
-      else mode = head * 8 <= d.tile_smem[tr.bin] ? 1 : 0;
-    } else td.maxC = -1;                      // cannot happen for classes <= kLaneBinMax (rows <= 96); refuse rather than corrupt
+    const int64_t words = tile_words(td, L), head = tile_head_words(td, L);
+    int mode = tr.bin <= 2 ? (words * 8 <= d.tile_smem[tr.bin] ? 2 : (head * 8 <= d.tile_smem[3] ? 1 : 0)) : (head * 8 <= d.tile_smem[tr.bin] ? 1 : 0);
+    if (td.maxB >= 256 || td.maxR >= 256) td.maxC = -1;     // cannot happen for classes <= kLaneBinMax (rows <= 96); refuse rather than corrupt
     unsigned long long off = 0;
     if (lane == 0) {
       off = atomicAdd(d.tile_top, (unsigned long long)words);
@@ -97,8 +128,8 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
     off = __shfl_sync(0xffffffffu, off, 0);
     td.maxC = __shfl_sync(0xffffffffu, td.maxC, 0);
     if (isl < 0 || td.maxC < 0) continue;
-    Tile T; T.t = td; T.lane = lane;
-    tile_bind(T, d.tile_arena + off, d.tile_arena + off + head);
+    TileT<0> T; T.t = td; T.lane = lane; T.Lrt = L;
+    T.bind(d.tile_arena + off, d.tile_arena + off + head);
     // local body table: 0 = the non-dynamic stand-in, dynamic bodies 1.. in order of first appearance
     T.body_row(0) = -1;
 #pragma unroll
@@ -107,22 +138,24 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
     for (int gi = 0; gi < gn; gi++) {
       const int s = d.isl_groups[g0 + gi];
       const int rr[2] = {d.cur.slot_row1[s], d.cur.slot_row2[s]};
-      int lb[2];
+      int lb[2]; M33 I[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int br = rr[e];
         int m = 0;
+        I[e].m11 = I[e].m21 = I[e].m31 = I[e].m12 = I[e].m22 = I[e].m32 = I[e].m13 = I[e].m23 = I[e].m33 = 0;
         if (d.kind[br] == 2) {
+          const double* im = d.iiw + 9 * (size_t)br;
+          I[e].m11 = im[0]; I[e].m21 = im[1]; I[e].m31 = im[2]; I[e].m12 = im[3]; I[e].m22 = im[4]; I[e].m32 = im[5];
+          I[e].m13 = im[6]; I[e].m23 = im[7]; I[e].m33 = im[8];
           m = d.body_mark[br];
           if (m == 0) {
             m = nB++; d.body_mark[br] = m; T.body_row(m) = br;
             T.body(m, 0) = d.inv_mass[br];
-            const double* im = d.iiw + 9 * (size_t)br;
-#pragma unroll
-            for (int k = 0; k < 9; k++) T.body(m, 1 + k) = im[k];
             const double* sb = d.sbv + 6 * (size_t)br;
 #pragma unroll
-            for (int k = 0; k < 6; k++) T.body(m, 10 + k) = sb[k];
+            for (int k = 0; k < 6; k++) T.body(m, 1 + k) = sb[k];
+            T.body(m, 7) = 0.0;
           }
         }
         lb[e] = m;
@@ -132,23 +165,19 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
       const int j0 = d.cur.slot_jstart[s], jn = d.cur.slot_jcount[s];
       for (int k = 0; k < jn; k++, r++) {
         const JointRow& jr = d.jrows[j0 + k];
-#pragma unroll
-        for (int f = 0; f < 9; f++) T.nrow(r, f) = jr.J[f];
-        T.nrow(r, 9) = jr.B; T.nrow(r, 10) = jr.invC; T.nrow(r, 11) = jr.lam;
+        tile_write_jac(T, false, r, 0, jr.J, I[0], I[1]);
+        T.nrow(r, NR_B) = jr.B; T.nrow(r, NR_INVC) = jr.invC; T.nrow(r, NR_LAM) = jr.lam;
         T.desc1(r) = pair | DESC_JOINT | first; first = 0;
       }
       const int c0 = d.cur.slot_cstart[s], cn = max(d.cur.slot_ccount[s], 0);
       for (int k = 0; k < cn; k++, r++, c++) {
-        const double2* src = (const double2*)(d.cur.rows + c0 + k);     // RowRec is 64 B aligned
-        double2 v[18];
-#pragma unroll
-        for (int f = 0; f < 18; f++) v[f] = src[f];
-        const double last = ((const double*)src)[36];
-#pragma unroll
-        for (int f = 0; f < 6; f++) { T.nrow(r, 2 * f) = v[f].x; T.nrow(r, 2 * f + 1) = v[f].y; }
-#pragma unroll
-        for (int f = 6; f < 18; f++) { T.frow(c, 2 * f - 12) = v[f].x; T.frow(c, 2 * f - 11) = v[f].y; }
-        T.frow(c, 24) = last;
+        const RowRec& src = d.cur.rows[c0 + k];
+        tile_write_jac(T, false, r, 0, src.nJ, I[0], I[1]);
+        T.nrow(r, NR_B) = src.nB; T.nrow(r, NR_INVC) = src.nInvC; T.nrow(r, NR_LAM) = src.lamN;
+        tile_write_jac(T, true, c, FR_E1, src.f1J, I[0], I[1]);
+        tile_write_jac(T, true, c, FR_E2, src.f2J, I[0], I[1]);
+        T.frow(c, FR_F1B) = src.f1B; T.frow(c, FR_F1INVC) = src.f1InvC; T.frow(c, FR_F2B) = src.f2B; T.frow(c, FR_F2INVC) = src.f2InvC;
+        T.frow(c, FR_MU) = src.mu; T.frow(c, FR_L1) = src.lamF1; T.frow(c, FR_L2) = src.lamF2;
         T.desc1(r) = pair | first; first = 0;
         T.desc2(c) = pair | (r << 16);
         T.contact_index(c) = c0 + k;
@@ -157,58 +186,87 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
   }
 }
 
-// Rows of the tile column of this lane, loaded into registers one row AHEAD of their use so that the (shared-memory or
-// L2) latency of row c+1 hides behind the dependent FP64 chain of row c.
-struct RowN { double J[9], B, invC, lam; int desc; };
-struct RowF { double e1[9], e2[9], f1B, f1InvC, f2B, f2InvC, mu, l1, l2; int desc; };
-__device__ __forceinline__ void load_row_n(const Tile& T, int r, RowN& o) {
+// Rows of the tile column of this lane, loaded into registers one row AHEAD of their use so that the load latency of
+// row c+1 hides behind the dependent FP64 chain of row c.
+struct RowN { double J[9], ia[3], ib[3], B, invC, lam; int desc; };
+struct RowF { double e1[9], e1a[3], e1b[3], e2[9], e2a[3], e2b[3], f1B, f1InvC, f2B, f2InvC, mu, l1, l2, nl; int desc; };
+// one address computation per row, then constant offsets
+template <class TT>
+__device__ __forceinline__ void load_row_n(const TT& T, int r, RowN& o) {
+  const int L = T.L();
+  const double* p = T.rd + ((size_t)r * kNRowF64 * L + T.lane);
 #pragma unroll
-  for (int k = 0; k < 9; k++) o.J[k] = T.nrow(r, k);
-  o.B = T.nrow(r, 9); o.invC = T.nrow(r, 10); o.lam = T.nrow(r, 11); o.desc = T.desc1(r);
-}
-__device__ __forceinline__ void load_row_f(const Tile& T, int c, RowF& o) {
+  for (int k = 0; k < 9; k++) o.J[k] = p[k * L];
 #pragma unroll
-  for (int k = 0; k < 9; k++) { o.e1[k] = T.frow(c, k); o.e2[k] = T.frow(c, 9 + k); }
-  o.f1B = T.frow(c, 18); o.f1InvC = T.frow(c, 19); o.f2B = T.frow(c, 20); o.f2InvC = T.frow(c, 21);
-  o.mu = T.frow(c, 22); o.l1 = T.frow(c, 23); o.l2 = T.frow(c, 24); o.desc = T.desc2(c);
+  for (int k = 0; k < 3; k++) { o.ia[k] = p[(NR_IA + k) * L]; o.ib[k] = p[(NR_IB + k) * L]; }
+  o.B = p[NR_B * L]; o.invC = p[NR_INVC * L]; o.lam = p[NR_LAM * L]; o.desc = T.desc1(r);
 }
-// The two solver bodies of the current row, held in registers across consecutive rows that share them (pairs are
-// enumerated body1-major, so body1 usually stays).  Local body 0 never touches memory.
-struct Pair { int b1, b2; BodyK k1, k2; SB s1, s2; };
-__device__ __forceinline__ void tile_store_sb(const Tile& T, int b, const SB& s) {
-  T.body(b, 10) = s.vX; T.body(b, 11) = s.vY; T.body(b, 12) = s.vZ; T.body(b, 13) = s.wX; T.body(b, 14) = s.wY; T.body(b, 15) = s.wZ;
+template <class TT>
+__device__ __forceinline__ void load_row_f(const TT& T, int c, RowF& o) {
+  const int L = T.L();
+  const double* p = T.rd + (((size_t)T.t.maxR * kNRowF64 + (size_t)c * kFRowF64) * L + T.lane);
+#pragma unroll
+  for (int k = 0; k < 9; k++) { o.e1[k] = p[(FR_E1 + k) * L]; o.e2[k] = p[(FR_E2 + k) * L]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    o.e1a[k] = p[(FR_E1IA + k) * L]; o.e1b[k] = p[(FR_E1IB + k) * L]; o.e2a[k] = p[(FR_E2IA + k) * L]; o.e2b[k] = p[(FR_E2IB + k) * L];
+  }
+  o.f1B = p[FR_F1B * L]; o.f1InvC = p[FR_F1INVC * L]; o.f2B = p[FR_F2B * L]; o.f2InvC = p[FR_F2INVC * L];
+  o.mu = p[FR_MU * L]; o.l1 = p[FR_L1 * L]; o.l2 = p[FR_L2 * L]; o.desc = T.desc2(c);
+  o.nl = T.nrow((o.desc >> 16) & 0xff, NR_LAM);     // the normal lambda of this contact: sweep 1 is complete when sweep 2 loads
 }
-__device__ __forceinline__ void pair_load_body(const Tile& T, int b, BodyK& k, SB& s) {
-  if (b == 0) {
-    k.kind = 1; k.invMass = 0; k.I.m11 = k.I.m21 = k.I.m31 = k.I.m12 = k.I.m22 = k.I.m32 = k.I.m13 = k.I.m23 = k.I.m33 = 0;
-    s.vX = s.vY = s.vZ = s.wX = s.wY = s.wZ = 0;
-  } else {
-    k.kind = 2; k.invMass = T.body(b, 0);
-    k.I.m11 = T.body(b, 1); k.I.m21 = T.body(b, 2); k.I.m31 = T.body(b, 3); k.I.m12 = T.body(b, 4); k.I.m22 = T.body(b, 5);
-    k.I.m32 = T.body(b, 6); k.I.m13 = T.body(b, 7); k.I.m23 = T.body(b, 8); k.I.m33 = T.body(b, 9);
-    s.vX = T.body(b, 10); s.vY = T.body(b, 11); s.vZ = T.body(b, 12); s.wX = T.body(b, 13); s.wY = T.body(b, 14); s.wZ = T.body(b, 15);
+// The two solver bodies of the current row (inverse mass + delta v/w), held in registers across consecutive rows that
+// share them (pairs are enumerated body1-major, so body1 usually stays).  Local body 0 never touches memory.
+struct Pair { int b1, b2; double im1, im2; SB s1, s2; };
+template <class TT>
+__device__ __forceinline__ void tile_store_sb(const TT& T, int b, const SB& s) {
+  const int L = T.L();
+  double* p = T.bd + ((size_t)b * kBodyF64 * L + T.lane);
+  p[L] = s.vX; p[2 * L] = s.vY; p[3 * L] = s.vZ; p[4 * L] = s.wX; p[5 * L] = s.wY; p[6 * L] = s.wZ;
+}
+template <class TT>
+__device__ __forceinline__ void pair_load_body(const TT& T, int b, double& im, SB& s) {
+  if (b == 0) { im = 0; s.vX = s.vY = s.vZ = s.wX = s.wY = s.wZ = 0; }
+  else {
+    const int L = T.L();
+    const double* p = T.bd + ((size_t)b * kBodyF64 * L + T.lane);
+    im = p[0]; s.vX = p[L]; s.vY = p[2 * L]; s.vZ = p[3 * L]; s.wX = p[4 * L]; s.wY = p[5 * L]; s.wZ = p[6 * L];
   }
 }
-__device__ __forceinline__ void pair_enter(const Tile& T, Pair& P, int desc) {
+template <class TT>
+__device__ __forceinline__ void pair_enter(const TT& T, Pair& P, int desc) {
   const int nb1 = desc & 0xff, nb2 = (desc >> 8) & 0xff;
   if (nb1 == P.b1 && nb2 == P.b2) return;
   // a body that changes sides goes through the tile: stores first, loads after
   if (nb1 != P.b1 && P.b1 > 0) tile_store_sb(T, P.b1, P.s1);
   if (nb2 != P.b2 && P.b2 > 0) tile_store_sb(T, P.b2, P.s2);
-  if (nb1 != P.b1) { pair_load_body(T, nb1, P.k1, P.s1); P.b1 = nb1; }
-  if (nb2 != P.b2) { pair_load_body(T, nb2, P.k2, P.s2); P.b2 = nb2; }
+  if (nb1 != P.b1) { pair_load_body(T, nb1, P.im1, P.s1); P.b1 = nb1; }
+  if (nb2 != P.b2) { pair_load_body(T, nb2, P.im2, P.s2); P.b2 = nb2; }
 }
-__device__ __forceinline__ void pair_flush(const Tile& T, Pair& P) {
+template <class TT>
+__device__ __forceinline__ void pair_flush(const TT& T, Pair& P) {
   if (P.b1 > 0) tile_store_sb(T, P.b1, P.s1);
   if (P.b2 > 0) tile_store_sb(T, P.b2, P.s2);
   P.b1 = -1; P.b2 = -1;
 }
+// applyVelocityBody1/2 (Solver.elm:505-550) with the precomputed I.w; branch-free (see the stand-in note above)
+__device__ __forceinline__ void apply_pre(double dl, const double* J, const double* ia, const double* ib, Pair& P) {
+  const double k1 = dl * P.im1, k2 = dl * P.im2;
+  P.s1.vX = P.s1.vX - k1 * J[3]; P.s1.vY = P.s1.vY - k1 * J[4]; P.s1.vZ = P.s1.vZ - k1 * J[5];
+  P.s1.wX = P.s1.wX + ia[0] * dl; P.s1.wY = P.s1.wY + ia[1] * dl; P.s1.wZ = P.s1.wZ + ia[2] * dl;
+  P.s2.vX = P.s2.vX + k2 * J[3]; P.s2.vY = P.s2.vY + k2 * J[4]; P.s2.vZ = P.s2.vZ + k2 * J[5];
+  P.s2.wX = P.s2.wX + ib[0] * dl; P.s2.wY = P.s2.wY + ib[1] * dl; P.s2.wZ = P.s2.wZ + ib[2] * dl;
+}
 
 // The whole solve of the island of this lane on its tile column, then the scatter of the results.  Each sweep walks ONE
-// flat row sequence (the lanes of the warp stay in lock step on the row index whatever their group structure is);
-// changing the body pair is the only divergent section.
-__device__ __forceinline__ void solve_lane(const Dev& d, const Tile& T, int isl) {
-  const int gn = d.isl_cnt[isl], w = d.isl_world[isl], C = d.isl_nc[isl], R = C + d.isl_nj[isl];
+// flat row sequence: ALL 32 lanes of the warp run the same loops (to the largest row count / iteration count of the tile,
+// predicated off where a lane has fewer rows, has converged, or holds no island) and re-converge with __syncwarp after
+// every row, so changing the body pair is the only divergent section and it never outlives its row.
+template <class TT>
+__device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
+  const bool have = isl >= 0;
+  const int gn = have ? d.isl_cnt[isl] : 0, w = have ? d.isl_world[isl] : 0, C = have ? d.isl_nc[isl] : 0, R = have ? C + d.isl_nj[isl] : 0;
+  const int Rmax = warp_max(R), Cmax = warp_max(C);
   Pair P; P.b1 = -1; P.b2 = -1;
   // warm start (applyContactsWarmStart, Solver.elm:102-119): groups in REVERSE enumeration order (buildAndWarmStart walks
   // pairGroups, Solver.elm:122-208), the seeded normal impulses of a group in solver order
@@ -218,87 +276,108 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const Tile& T, int isl)
     for (int r = lo; r <= hi; r++) {
       const int desc = T.desc1(r);
       if (desc & DESC_JOINT) continue;
-      const double lam = T.nrow(r, 11);
+      const double lam = T.nrow(r, NR_LAM);
       if (lam == 0) continue;                        // Solver.elm:41
       pair_enter(T, P, desc);
-      double J[9];
+      double J[9], ia[3], ib[3];
 #pragma unroll
       for (int k = 0; k < 9; k++) J[k] = T.nrow(r, k);
-      apply_row(lam, J, P.k1, P.k2, P.s1, P.s2);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { ia[k] = T.nrow(r, NR_IA + k); ib[k] = T.nrow(r, NR_IB + k); }
+      apply_pre(lam, J, ia, ib, P);
     }
     hi = lo - 1;
   }
   pair_flush(T, P);
-  const int iterations = d.iterations[w];
-  int remaining = iterations, rem;
-  const double eps = spook(d.dt[w]).eps;
-  for (;;) {
+  __syncwarp();
+  const int iterations = have ? d.iterations[w] : 1;
+  int remaining = iterations, rem = 0;
+  bool done = !have;
+  const double eps = have ? spook(d.dt[w]).eps : 0.0;
+  while (__any_sync(0xffffffffu, !done)) {
     // sweep 1: velocityNonFrictionGroup (Solver.elm:850-864) group by group: joint rows (572-619), then contact normals (625-672)
     double p1 = 0;
     {
       RowN nxt;
-      if (R > 0) load_row_n(T, 0, nxt);
-      for (int r = 0; r < R; r++) {
-        RowN cur = nxt;
-        if (r + 1 < R) load_row_n(T, r + 1, nxt);
-        pair_enter(T, P, cur.desc);
-        const double lo = (cur.desc & DESC_JOINT) ? -kMaxImpulse : 0.0;
-        double dl = row_solve(cur.J, cur.B, cur.invC, eps, lo, kMaxImpulse, cur.lam, P.k1, P.k2, P.s1, P.s2);
-        T.nrow(r, 11) = cur.lam;
-        p1 = p1 + eabs(dl);
+      if (!done && R > 0) load_row_n(T, 0, nxt);
+      for (int r = 0; r < Rmax; r++) {
+        if (!done && r < R) {
+          RowN cur = nxt;
+          if (r + 1 < R) load_row_n(T, r + 1, nxt);
+          pair_enter(T, P, cur.desc);
+          const double lo = (cur.desc & DESC_JOINT) ? -kMaxImpulse : 0.0;
+          const double prev = cur.invC * (cur.B - gw_lambda(cur.J, P.s1, P.s2) - eps * cur.lam);
+          const double dl = (cur.lam + prev - lo < 0) ? lo - cur.lam : ((cur.lam + prev - kMaxImpulse > 0) ? kMaxImpulse - cur.lam : prev);
+          apply_pre(dl, cur.J, cur.ia, cur.ib, P);
+          T.nrow(r, NR_LAM) = cur.lam + dl;
+          p1 = p1 + eabs(dl);
+        }
+        __syncwarp();
       }
-      pair_flush(T, P);
+      if (!done) pair_flush(T, P);
+      __syncwarp();
     }
-    // sweep 2: velocityFrictionGroup (Solver.elm:869-880); solve2Body keeps ONE running sum through both phases
-    // (Solver.elm:473-489), step adds two sums (345-358)
+    // sweep 2: velocityFrictionGroup (Solver.elm:869-880, 678-844): friction1 then friction2, cone +-mu*lambda_n; solve2Body
+    // keeps ONE running sum through both phases (Solver.elm:473-489), step adds two sums (345-358)
     double p2 = (gn == 1) ? p1 : 0;
     {
       RowF nxt;
-      if (C > 0) load_row_f(T, 0, nxt);
-      for (int c = 0; c < C; c++) {
-        RowF cur = nxt;
-        if (c + 1 < C) load_row_f(T, c + 1, nxt);
-        const double lamN = T.nrow((cur.desc >> 16) & 0xff, 11);
-        pair_enter(T, P, cur.desc);
-        double a1, a2;
-        p2 = friction_pair(cur.e1, cur.e2, cur.f1B, cur.f1InvC, cur.f2B, cur.f2InvC, eps, cur.mu, lamN, cur.l1, cur.l2,
-                           P.k1, P.k2, P.s1, P.s2, p2, a1, a2);
-        T.frow(c, 23) = cur.l1; T.frow(c, 24) = cur.l2;
+      if (!done && C > 0) load_row_f(T, 0, nxt);
+      for (int c = 0; c < Cmax; c++) {
+        if (!done && c < C) {
+          RowF cur = nxt;
+          if (c + 1 < C) load_row_f(T, c + 1, nxt);
+          pair_enter(T, P, cur.desc);
+          const double cap = cur.mu * cur.nl;
+          const double dPrev1 = cur.f1InvC * (cur.f1B - gw_lambda(cur.e1, P.s1, P.s2) - eps * cur.l1);
+          const double d1 = (cur.l1 + dPrev1 + cap < 0) ? -cap - cur.l1 : ((cur.l1 + dPrev1 - cap > 0) ? cap - cur.l1 : dPrev1);
+          apply_pre(d1, cur.e1, cur.e1a, cur.e1b, P);
+          const double dPrev2 = cur.f2InvC * (cur.f2B - gw_lambda(cur.e2, P.s1, P.s2) - eps * cur.l2);
+          const double d2 = (cur.l2 + dPrev2 + cap < 0) ? -cap - cur.l2 : ((cur.l2 + dPrev2 - cap > 0) ? cap - cur.l2 : dPrev2);
+          apply_pre(d2, cur.e2, cur.e2a, cur.e2b, P);
+          T.frow(c, FR_L1) = cur.l1 + d1; T.frow(c, FR_L2) = cur.l2 + d2;
+          p2 = p2 + eabs(d1) + eabs(d2);
+        }
+        __syncwarp();
       }
-      pair_flush(T, P);
+      if (!done) pair_flush(T, P);
+      __syncwarp();
     }
-    double deltaTot = (gn == 1) ? p2 : p1 + p2;
-    if (remaining == 1) { rem = 0; break; }
-    if (deltaTot - kSolverTolerance < 0) { rem = remaining - 1; break; }
-    remaining--;
+    if (!done) {
+      const double deltaTot = (gn == 1) ? p2 : p1 + p2;
+      if (remaining == 1) { rem = 0; done = true; }
+      else if (deltaTot - kSolverTolerance < 0) { rem = remaining - 1; done = true; }
+      else remaining--;
+    }
   }
+  if (!have) return;
   atomicMin(&d.world_min_rem[w], rem);
   d.body_iters[d.isl_root[isl]] = iterations - rem;
   // scatter: lambdas back to the slot-order rows (next frame's warm start, Solver.elm:320-335), delta velocities to the bodies
   for (int c = 0; c < C; c++) {
     RowRec& o = d.cur.rows[T.contact_index(c)];
-    o.lamN = T.nrow((T.desc2(c) >> 16) & 0xff, 11); o.lamF1 = T.frow(c, 23); o.lamF2 = T.frow(c, 24);
+    o.lamN = T.nrow((T.desc2(c) >> 16) & 0xff, NR_LAM); o.lamF1 = T.frow(c, FR_L1); o.lamF2 = T.frow(c, FR_L2);
   }
   const int nB = d.isl_nb[isl] + 1;
   for (int b = 1; b < nB; b++) {
     double* sb = d.sbv + 6 * (size_t)T.body_row(b);
 #pragma unroll
-    for (int k = 0; k < 6; k++) sb[k] = T.body(b, 10 + k);
+    for (int k = 0; k < 6; k++) sb[k] = T.body(b, 1 + k);
   }
 }
 
 // One warp per tile.  MODE 2: whole image staged in dynamic shared memory; MODE 1: bodies + descriptors staged, rows read
-// from the image in place (L2) one row ahead; MODE 0: everything in place.  Processes the tiles of classes [bin_lo, bin_hi]
-// whose residency mode (k_tile_build) is MODE.
+// from the image in place (L2) one row ahead; MODE 0: everything in place, four warps per CTA.  Processes the tiles of
+// classes [bin_lo, bin_hi] whose residency (k_tile_build) is MODE.
 template <int MODE>
 __global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int bin_lo, int bin_hi) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   int t0 = 0;                     // first global tile of class bin_hi
-  for (int b = kLaneBinMax; b > bin_hi; b--) t0 += (d.cur.counters[CNT_BIN0 + b] + 31) >> 5;
+  for (int b = kLaneBinMax; b > bin_hi; b--) t0 += class_tiles(d, b);
   int nt = 0;
-  for (int b = bin_hi; b >= bin_lo; b--) nt += (d.cur.counters[CNT_BIN0 + b] + 31) >> 5;
+  for (int b = bin_hi; b >= bin_lo; b--) nt += class_tiles(d, b);
   for (int t = warp; t < nt; t += nwarps) {
     const int gtile = t0 + t;
     const int4 e = d.tile_dir[gtile];
@@ -306,20 +385,20 @@ __global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int
     int maxC = e.w & 0xfffffff; if (maxC & 0x8000000) maxC = -1;
     if (mode != MODE || maxC < 0) continue;
     TileRef tr; lane_tile(d, gtile, tr);
-    Tile T; T.lane = lane; T.t.maxB = e.z & 0xffff; T.t.maxR = (e.z >> 16) & 0xffff; T.t.maxC = maxC;
+    TileT<32> T; T.lane = lane; T.Lrt = 32; T.t.maxB = e.z & 0xffff; T.t.maxR = (e.z >> 16) & 0xffff; T.t.maxC = maxC;
     double* img = d.tile_arena + (((unsigned long long)(unsigned)e.y << 32) | (unsigned)e.x);
-    const int head = (int)tile_head_words(T.t);
+    const int head = (int)tile_head_words(T.t, 32);
     if (MODE == 0) {
-      tile_bind(T, img, img + head);
+      T.bind(img, img + head);
     } else {
       double* sm = (double*)tile_smem;
-      const int n = MODE == 2 ? (int)tile_words(T.t) : head;
+      const int n = MODE == 2 ? (int)tile_words(T.t, 32) : head;
       __syncwarp();
       for (int i = lane; i < n; i += 32) sm[i] = img[i];
       __syncwarp();
-      tile_bind(T, sm, MODE == 2 ? sm + head : img + head);
+      T.bind(sm, MODE == 2 ? sm + head : img + head);
     }
-    if (lane < tr.count) solve_lane(d, T, d.isl_sorted[tr.first + lane]);
+    solve_lane(d, T, lane < tr.count ? d.isl_sorted[tr.first + lane] : -1);
   }
 }
 

@@ -21,6 +21,8 @@ def main():
     name, _, arg = a.scene.partition(":")
     if name == "boxes":
         shapes, bodies, params = pack.pack_worlds(scenes.boxes_scene())
+    elif name == "stack":
+        shapes, bodies, params = pack.pack_worlds(scenes.stack_scene(int(arg or 5), 20))
     elif name == "mixed":
         shapes, bodies, params = scenes.mixed_worlds(int(arg or 1024))
     elif name == "pile":
