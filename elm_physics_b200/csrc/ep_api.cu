@@ -115,8 +115,12 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  // side streams in launch order of the solver (longest class first): earlier ones get the higher priority so that the
+  // long tiles are scheduled onto SMs before the short ones fill them
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; i < ep_ctx::kAux && ok; i++)
-    ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+    ok = cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, i < 4 ? prio_hi : prio_lo) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
   // Shared memory of the lane-solver launches, sized for the typical tile of each class: classes 0..2 stage the whole image
   // (stand-in + 2 dynamic bodies, 2^class rows); classes 3..5 stage bodies + descriptors only (2^(class-1)+1 dynamic bodies,
@@ -561,7 +565,12 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       } else
       { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d, -1); }
       { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
-      { Timed t(ctx, EP_K_ISLANDS); k_islands<<<grid_for(ctx, d.n_worlds, 64, 16), 64, 0, st>>>(d);
+      { Timed t(ctx, EP_K_ISLANDS);
+        // one CTA per world: a warp for small worlds, more for large ones; the union-find arrays sit in shared memory when they fit
+        const int it = d.nb_max <= 64 ? 32 : (d.nb_max <= 512 ? 128 : 256);
+        const size_t ism = 3 * (size_t)d.nb_max * sizeof(int);
+        const int use_smem = ism <= 40 * 1024;
+        k_islands<<<std::max(1, std::min(d.n_worlds, ctx->sm_count * 32)), it, use_smem ? ism : 0, st>>>(d, use_smem);
         k_island_sort<<<grid_for(ctx, d.n_bodies / 2 + 1, 256, 4), 256, 0, st>>>(d); ctx->launches++; }
       { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
     }

@@ -489,67 +489,142 @@ __device__ __forceinline__ int island_key(int bin, int pred_iters, int groups) {
   int gk = groups <= 1 ? 0 : (groups == 2 ? 1 : (groups <= 4 ? 2 : 3));
   return (bin * kIterKeys + it) * kGroupKeys + gk;
 }
-__global__ void k_islands(Dev d) {
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < d.n_worlds; w += gridDim.x * blockDim.x) {
-    int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
-    int* parent = d.uf_parent + r0; int* count = d.uf_count + r0; int* fill = d.uf_fill + r0;
-    for (int l = 0; l < n; l++) { parent[l] = l; count[l] = 0; d.body_mark[r0 + l] = 0; }
-    int s0 = d.cur.cand_base[w], sn = d.cur.cand_n[w];
-    int valid = 0;
-    for (int s = s0 + sn - 1; s >= s0; s--) {           // Islands.connect inside buildAndWarmStart (Solver.elm:201-206)
+// One CTA per world (one warp for small worlds).  Union-find with lock-free hooking: the root of a set is always its
+// member with the LOWEST body id (Islands.elm:39-46 "lower root wins"), so the final roots do not depend on the order of
+// the unions and the parallel version yields exactly the reference's roots.  Islands of a world are numbered by ascending
+// body row of the root; the groups of an island stay in pair-enumeration order (Islands.elm:51-119).
+__device__ __forceinline__ int uf_root(volatile int* parent, int x) {
+  for (;;) { int p = parent[x]; if (p == x) return x; x = p; }
+}
+__global__ void k_islands(Dev d, int use_smem) {
+  extern __shared__ int s_isl[];           // [3][nb_max] parent / count / fill when the largest world fits
+  __shared__ int s_scan[33];
+  __shared__ int s_nisl, s_valid, s_ibase, s_gbase;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarps = nt >> 5;
+  for (int w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
+    const int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    int* parent = use_smem ? s_isl : d.uf_parent + r0;
+    int* count = use_smem ? s_isl + d.nb_max : d.uf_count + r0;
+    int* fill = use_smem ? s_isl + 2 * d.nb_max : d.uf_fill + r0;
+    const int s0 = d.cur.cand_base[w], sn = d.cur.cand_n[w];
+    for (int l = tid; l < n; l += nt) { parent[l] = l; count[l] = 0; fill[l] = 0; d.body_mark[r0 + l] = 0; }
+    if (tid == 0) { s_nisl = 0; s_valid = 0; }
+    __syncthreads();
+    // Islands.connect for every dynamic-dynamic pair group (Solver.elm:201-206)
+    for (int s = s0 + tid; s < s0 + sn; s += nt) {
       if (d.cur.slot_ccount[s] <= 0 && d.cur.slot_jcount[s] <= 0) continue;
-      valid++;
-      int ra = d.cur.slot_row1[s], rb = d.cur.slot_row2[s];
-      if (d.kind[ra] == 2 && d.kind[rb] == 2) {
-        int a = uf_find(parent, ra - r0), b = uf_find(parent, rb - r0);
-        int ia = d.body_id[r0 + a], ib = d.body_id[r0 + b];   // lower id becomes root (Islands.elm:39-46)
-        if (ia - ib < 0) parent[b] = a; else if (ia - ib > 0) parent[a] = b;
+      const int ra = d.cur.slot_row1[s], rb = d.cur.slot_row2[s];
+      if (d.kind[ra] != 2 || d.kind[rb] != 2) continue;
+      int a = ra - r0, b = rb - r0;
+      for (;;) {
+        a = uf_root(parent, a); b = uf_root(parent, b);
+        if (a == b) break;
+        const int ia = d.body_id[r0 + a], ib = d.body_id[r0 + b];
+        const int win = (ia - ib < 0) ? a : b, lose = (ia - ib < 0) ? b : a;
+        if (atomicCAS(&parent[lose], lose, win) == lose) break;
       }
     }
-    for (int s = s0; s < s0 + sn; s++) {                // annotate (Islands.elm:68-89)
+    __syncthreads();
+    for (int l = tid; l < n; l += nt) parent[l] = uf_root(parent, l);      // flatten (reads may see already-flattened entries: still roots)
+    __syncthreads();
+    // annotate (Islands.elm:68-89): island of a group = root of its dynamic body; groups / rows / contacts / joint rows per root
+    int valid = 0;
+    for (int s = s0 + tid; s < s0 + sn; s += nt) {
       if (d.cur.slot_ccount[s] <= 0 && d.cur.slot_jcount[s] <= 0) { d.cur.slot_root[s] = -1; continue; }
-      int ra = d.cur.slot_row1[s], rb = d.cur.slot_row2[s];
-      int root = uf_find(parent, (d.kind[ra] == 2 ? ra : rb) - r0);
+      const int ra = d.cur.slot_row1[s], rb = d.cur.slot_row2[s];
+      const int root = parent[(d.kind[ra] == 2 ? ra : rb) - r0];
       d.cur.slot_root[s] = r0 + root;
-      count[root]++;
+      atomicAdd(&count[root], 1);
+      valid++;
     }
-    int nisl = 0;
-    for (int l = 0; l < n; l++) nisl += count[l] > 0;
-    d.world_n_islands[w] = nisl;
-    if (nisl == 0) continue;
-    int ibase = atomicAdd(&d.cur.counters[CNT_ISLANDS], nisl);
-    int gbase = atomicAdd(&d.cur.counters[CNT_ISL_GROUPS], valid);
-    // per island: rows (size class), contacts, dynamic bodies
-    for (int l = 0; l < n; l++) fill[l] = 0;
-    for (int s = s0; s < s0 + sn; s++) {
-      int root = d.cur.slot_root[s];
-      if (root >= 0) fill[root - r0] += 3 * max(d.cur.slot_ccount[s], 0) + d.cur.slot_jcount[s];
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if (lane == 0 && valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    // number the islands by ascending root row: block-wide exclusive scan of (count > 0)
+    int run = 0;
+    for (int base = 0; base < n; base += nt) {
+      const int l = base + tid;
+      const int flag = (l < n && count[l] > 0) ? 1 : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0) s_scan[wid] = __popc(bal);
+      __syncthreads();
+      int before = run;
+      for (int k = 0; k < wid; k++) before += s_scan[k];
+      int total = 0;
+      for (int k = 0; k < nwarps; k++) total += s_scan[k];
+      if (flag) fill[l] = before + __popc(bal & ((1u << lane) - 1u));       // island number inside the world (for now)
+      run += total;
+      __syncthreads();
     }
-    int k = 0, goff = gbase;
-    for (int l = 0; l < n; l++) if (count[l] > 0) {
-      int isl = ibase + k;
-      d.isl_off[isl] = goff; d.isl_cnt[isl] = count[l]; d.isl_world[isl] = w; d.isl_root[isl] = r0 + l;
-      int bin = island_bin(fill[l]);
-      int key = island_key(bin, d.body_iters[r0 + l], count[l]);
+    if (tid == 0) {
+      s_nisl = run;
+      d.world_n_islands[w] = run;
+      s_ibase = run ? atomicAdd(&d.cur.counters[CNT_ISLANDS], run) : 0;
+      s_gbase = run ? atomicAdd(&d.cur.counters[CNT_ISL_GROUPS], s_valid) : 0;
+    }
+    __syncthreads();
+    if (s_nisl == 0) { __syncthreads(); continue; }
+    const int ibase = s_ibase, gbase = s_gbase;
+    // group offsets of the islands: exclusive scan of count[] over the roots in island order.  Islands are few per
+    // world in the batched configs and the scan is over bodies, so a single warp does it.
+    if (wid == 0) {
+      int goff = gbase;
+      for (int base = 0; base < n; base += 32) {
+        const int l = base + lane;
+        const int c = (l < n) ? count[l] : 0;
+        int sc = c;
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += v; }
+        if (c > 0) {
+          const int isl = ibase + fill[l];
+          d.isl_off[isl] = goff + sc - c; d.isl_cnt[isl] = c; d.isl_world[isl] = w; d.isl_root[isl] = r0 + l;
+          d.isl_nc[isl] = 0; d.isl_nj[isl] = 0; d.isl_nb[isl] = 0;
+          count[l] = isl + 1;                       // root -> island index + 1 from here on
+          fill[l] = goff + sc - c;                  // next free group slot of the island
+        }
+        goff += __shfl_sync(0xffffffffu, sc, 31);
+      }
+    }
+    __syncthreads();
+    // groups of an island in enumeration order: one warp walks the slots 32 at a time, lanes with the same root rank
+    // themselves with match_any; contacts / joint rows accumulate per island
+    if (wid == 0) {
+      for (int base = 0; base < sn; base += 32) {
+        const int s = s0 + base + lane;
+        const int root = (base + lane < sn) ? d.cur.slot_root[s] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, root);
+        if (root >= 0) {
+          const int l = root - r0;
+          const int rank = __popc(peers & ((1u << lane) - 1u));
+          const int leader = __ffs(peers) - 1;
+          const int at = fill[l] + rank;
+          d.isl_groups[at] = s;
+          const int isl = count[l] - 1;
+          atomicAdd(&d.isl_nc[isl], max(d.cur.slot_ccount[s], 0));
+          atomicAdd(&d.isl_nj[isl], max(d.cur.slot_jcount[s], 0));
+          __syncwarp(peers);
+          if (lane == leader) fill[l] += __popc(peers);
+        }
+        __syncwarp();
+      }
+    }
+    // dynamic bodies of an island = its union-find component
+    for (int l = tid; l < n; l += nt) {
+      if (d.kind[r0 + l] != 2) continue;
+      const int c = count[parent[l]];
+      if (c > 0) atomicAdd(&d.isl_nb[c - 1], 1);
+    }
+    __syncthreads();
+    // size class and sort key of each island (k_island_sort)
+    for (int l = tid; l < n; l += nt) {
+      if (parent[l] != l || count[l] <= 0) continue;
+      const int isl = count[l] - 1;
+      const int bin = island_bin(3 * d.isl_nc[isl] + d.isl_nj[isl]);
+      const int key = island_key(bin, d.body_iters[r0 + l], d.isl_cnt[isl]);
       d.isl_key[isl] = key;
       atomicAdd(&d.key_cnt[key], 1);
       atomicAdd(&d.cur.counters[CNT_BIN0 + bin], 1);
-      d.isl_nc[isl] = 0; d.isl_nb[isl] = 0; d.isl_nj[isl] = 0;
-      fill[l] = goff; goff += count[l]; k++;
-      count[l] = isl + 1;                               // root -> island index + 1 from here on (0 = no island)
     }
-    for (int s = s0; s < s0 + sn; s++) {                // groups of an island stay in enumeration order
-      int root = d.cur.slot_root[s];
-      if (root >= 0) {
-        d.isl_groups[fill[root - r0]++] = s;
-        d.isl_nc[count[root - r0] - 1] += max(d.cur.slot_ccount[s], 0); d.isl_nj[count[root - r0] - 1] += max(d.cur.slot_jcount[s], 0);
-      }
-    }
-    for (int l = 0; l < n; l++) {                       // dynamic bodies of an island = its union-find component
-      if (d.kind[r0 + l] != 2) continue;
-      int c = count[uf_find(parent, l)];
-      if (c > 0) d.isl_nb[c - 1]++;
-    }
+    __syncthreads();
   }
 }
 
