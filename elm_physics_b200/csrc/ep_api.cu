@@ -226,11 +226,10 @@ static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
   TRY(dev_alloc(ctx, pool, &f.slot_ncon, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_root, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_group, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_item0, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_nitems, d.slot_cap));
-  const size_t hn = (size_t)d.hash_mask + 1;
-  TRY(dev_alloc(ctx, pool, &f.hkeys, hn)); TRY(dev_alloc(ctx, pool, &f.hvals, hn));
+  TRY(dev_alloc(ctx, pool, &f.pair_slot, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.cand_base, d.n_worlds)); TRY(dev_alloc(ctx, pool, &f.cand_n, d.n_worlds));
   TRY(dev_alloc(ctx, pool, &f.counters, CNT_COUNT));
-  CK(cudaMemsetAsync(f.hkeys, 0xFF, hn * sizeof(int64_t), ctx->stream));
+  CK(cudaMemsetAsync(f.pair_slot, 0xFF, (size_t)d.slot_cap * sizeof(int32_t), ctx->stream));
   CK(cudaMemsetAsync(f.counters, 0, CNT_COUNT * sizeof(int32_t), ctx->stream));
   CK(cudaMemsetAsync(f.cand_base, 0, std::max(d.n_worlds, 1) * sizeof(int32_t), ctx->stream));
   CK(cudaMemsetAsync(f.cand_n, 0, std::max(d.n_worlds, 1) * sizeof(int32_t), ctx->stream));
@@ -264,10 +263,11 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_upload(ctx, pool, &d.world_body_off, B->world_body_off, nw + 1));
   TRY(dev_upload(ctx, pool, &d.body_id, B->body_id, nb));
   TRY(dev_upload(ctx, pool, &d.kind, B->kind, nb));
-  std::vector<int32_t> body_world(nb), inst_body(ni);
+  std::vector<int32_t> body_world(nb), inst_body(ni), pair_off(std::max(nw, 1), 0);
   int64_t slot_cap = 0;
   for (int w = 0; w < nw; w++) {
     int64_t n = B->world_body_off[w + 1] - B->world_body_off[w];
+    pair_off[w] = (int32_t)std::min<int64_t>(slot_cap, (1ll << 31) - 1);
     slot_cap += n * (n - 1) / 2;
     for (int r = B->world_body_off[w]; r < B->world_body_off[w + 1]; r++) body_world[r] = w;
   }
@@ -278,6 +278,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     if (B->inst_off[r + 1] - B->inst_off[r] > 255) { ctx->err = "more than 255 shapes on a body"; return EP_EINVAL; }
   }
   TRY(dev_upload(ctx, pool, &d.body_world, body_world.data(), nb));
+  TRY(dev_upload(ctx, pool, &d.world_pair_off, pair_off.data(), nw));
   TRY(dev_upload_rw(ctx, pool, &d.pos, B->pos, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.quat, B->quat, 4 * (size_t)nb));
   TRY(dev_upload_rw(ctx, pool, &d.vel, B->vel, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.angvel, B->angvel, 3 * (size_t)nb));
   TRY(dev_upload_rw(ctx, pool, &d.force, B->force, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.torque, B->torque, 3 * (size_t)nb));
@@ -368,8 +369,6 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   if (ctx->opt[EP_OPT_CONTACT_CAP] > 0) ccap = std::max<int64_t>(ctx->opt[EP_OPT_CONTACT_CAP], 64);
   if (warm && warm->world_group_off) ccap = std::max<int64_t>(ccap, warm->group_contact_off[warm->world_group_off[nw]]);
   d.contact_cap = (int32_t)std::min<int64_t>(ccap, (1ll << 31) - 64);
-  int64_t h = 1; while (h < 2 * (int64_t)d.contact_cap) h <<= 1;
-  d.hash_mask = (int32_t)(h - 1);
   d.jrow_cap = 6 * ncn + 8;
   // scratch
   TRY(dev_alloc(ctx, pool, &d.sorted, nb)); TRY(dev_alloc(ctx, pool, &d.sort_key, nb));
@@ -391,7 +390,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   {
     int64_t icap = std::max<int64_t>(1 << 16, 8 * (int64_t)ni);
     if (ctx->opt[EP_OPT_ITEM_CAP] > 0) icap = std::max<int64_t>(ctx->opt[EP_OPT_ITEM_CAP], 64);
-    d.item_cap = (int32_t)std::min<int64_t>(icap, (1ll << 28));
+    d.item_cap = (int32_t)std::min<int64_t>(icap, (1ll << 27));   // item * kRawStride stays below 2^31
     TRY(dev_alloc(ctx, pool, &d.items, (size_t)kClasses * d.item_cap));
     TRY(dev_alloc(ctx, pool, &d.raw, (size_t)d.item_cap * kRawStride));
     TRY(dev_alloc(ctx, pool, &d.raw_cnt, d.item_cap));
@@ -458,7 +457,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     CK(cudaMemcpyAsync(f.slot_ccount, ccount.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.contacts, crec.data(), nc * sizeof(ContactRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.rows, rrec.data(), nc * sizeof(RowRec), cudaMemcpyHostToDevice, ctx->stream));
-    k_hash_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng); CK(cudaGetLastError());
+    k_pair_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng); CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
   }
   // place every shape once (static bodies are never re-placed)
@@ -549,7 +548,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
     CK(cudaMemsetAsync(d.key_cnt, 0, 2 * kKeys * sizeof(int32_t), st));
     CK(cudaMemsetAsync(d.tile_top, 0, sizeof(unsigned long long), st));
     {
-      CK(cudaMemsetAsync(d.cur.hkeys, 0xFF, ((size_t)d.hash_mask + 1) * sizeof(int64_t), st));
+      CK(cudaMemsetAsync(d.cur.pair_slot, 0xFF, (size_t)d.slot_cap * sizeof(int32_t), st));
       if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
       { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
       { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }

@@ -60,8 +60,7 @@ struct FrameBuf {        // double-buffered: the previous frame is the warm-star
   int32_t* slot_group;   // index of the slot's pair group in the compacted output (ep_output.cuh), -1 when it is none
   int32_t* slot_item0;   // first narrowphase work item (shape pair) of the slot; items are numbered shape1-major
   int32_t* slot_nitems;  // shapes1 x shapes2 when the pair passed the bounding-sphere test, else 0
-  int64_t* hkeys;        // open-addressing table (world << 36 | bodyKey) -> slot
-  int32_t* hvals;
+  int32_t* pair_slot;    // [slot_cap] dense (world, i<j body pair) -> slot of this frame, -1 = no contacts (the warm-start cache index)
   int32_t* cand_base;    // [n_worlds] first slot of the world (enumeration order inside)
   int32_t* cand_n;       // [n_worlds]
   int32_t* counters;     // [CNT_COUNT]
@@ -72,6 +71,7 @@ struct Dev {
   const int32_t* sh_kind; const int32_t* sh_f64_off; const int32_t* sh_i32_off; const double* sh_f64; const int32_t* sh_i32;
   // bodies (ep_bodies)
   int32_t n_worlds, n_bodies, n_insts;
+  const int32_t* world_pair_off;   // [n_worlds] first entry of the world in the pair tables (sum of n(n-1)/2 of the worlds before)
   const int32_t* world_body_off; const int32_t* body_id; const int32_t* kind; const int32_t* body_world;
   double *pos, *quat, *vel, *angvel, *force, *torque, *iiw;
   const double *inv_mass, *inv_inertia, *ldp, *adp, *lin_lock, *ang_lock, *radius;
@@ -100,7 +100,7 @@ struct Dev {
   int32_t* world_n_islands;   // [n_worlds]
   JointRow* jrows;
   int32_t* flags;             // [FLAG_COUNT]
-  int64_t slot_cap; int32_t contact_cap; int32_t hash_mask; int32_t jrow_cap;
+  int64_t slot_cap; int32_t contact_cap; int32_t jrow_cap;
   // narrowphase work items, binned by class so that the lanes of a warp run the same Collision.* module
   int32_t item_cap;
   int4* items;                // [kClasses][item_cap] (slot, instance a, instance b, item id)

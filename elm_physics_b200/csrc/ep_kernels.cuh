@@ -14,37 +14,18 @@
 
 namespace ep {
 
-constexpr int64_t kHashEmpty = -1;
 constexpr double kMaxImpulse = 1000000.0;      // Equation.elm:459-461
 constexpr double kWarmStartFactor = 0.85;      // Equation.elm:467-469
 
-__device__ __forceinline__ uint32_t hash_mix(int64_t k) {
-  uint64_t x = (uint64_t)k;
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-  return (uint32_t)x;
-}
-// ContactId.elm:62-68 with the world index on top (ids < 2^18, worlds < 2^27)
-__device__ __forceinline__ int64_t pair_key(int world, int ida, int idb) {
-  int64_t a = ida, b = idb;
-  int64_t bk = (a - b <= 0) ? a * 262144 + b : b * 262144 + a;
-  return ((int64_t)world << 36) | bk;
-}
-__device__ void hash_insert(const FrameBuf& fb, int mask, int64_t key, int val) {
-  uint32_t h = hash_mix(key) & mask;
-  for (;;) {
-    unsigned long long old = atomicCAS((unsigned long long*)&fb.hkeys[h], (unsigned long long)kHashEmpty, (unsigned long long)key);
-    if (old == (unsigned long long)kHashEmpty || old == (unsigned long long)key) { fb.hvals[h] = val; return; }
-    h = (h + 1) & mask;
-  }
-}
-__device__ int hash_find(const FrameBuf& fb, int mask, int64_t key) {
-  uint32_t h = hash_mix(key) & mask;
-  for (;;) {
-    int64_t k = fb.hkeys[h];
-    if (k == key) return fb.hvals[h];
-    if (k == kHashEmpty) return -1;
-    h = (h + 1) & mask;
-  }
+// The warm-start cache is keyed by bodyKey(min id, max id) (ContactId.elm:62-68, ContactCache.elm).  Ids are unique inside
+// a world, so the key is equivalent to the unordered pair of body ROWS; every i<j pair of a world owns one entry of a dense
+// table (same size as the pair-slot pool), which makes insert and lookup a single L2-resident access instead of a probe
+// sequence through a hash table.
+__device__ __forceinline__ int64_t pair_index(const Dev& d, int w, int ra, int rb) {
+  const int r0 = d.world_body_off[w];
+  const int64_t n = d.world_body_off[w + 1] - r0;
+  const int64_t a = (ra < rb ? ra : rb) - r0, b = (ra < rb ? rb : ra) - r0;
+  return d.world_pair_off[w] + a * n - a * (a + 1) / 2 + (b - a - 1);
 }
 
 // ---- k_place ------------------------------------------------------------------------------------------
@@ -406,7 +387,7 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
   jstart = j0; jcount = E;
 }
 
-__global__ void __launch_bounds__(128) k_equations(Dev d) {
+__global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
   const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
     int ncon = d.cur.slot_ncon[s];
@@ -423,9 +404,10 @@ __global__ void __launch_bounds__(128) k_equations(Dev d) {
       int c0 = atomicAdd(&d.cur.counters[CNT_CONTACTS], nc);
       if (c0 + nc > d.contact_cap) { d.flags[FLAG_POOL_OVERFLOW] = 1; nc = 0; c0 = 0; }
       d.cur.slot_cstart[s] = c0; d.cur.slot_ccount[s] = nc;
-      if (nc > 0) hash_insert(d.cur, d.hash_mask, pair_key(w, d.body_id[r1], d.body_id[r2]), s);
+      const int64_t pidx = pair_index(d, w, r1, r2);
+      if (nc > 0) d.cur.pair_slot[pidx] = s;
       // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128
-      int ps = hash_find(d.prev, d.hash_mask, pair_key(w, d.body_id[r1], d.body_id[r2]));
+      int ps = d.prev.pair_slot[pidx];
       int pc0 = 0, pcn = 0;
       if (ps >= 0) { pc0 = d.prev.slot_cstart[ps]; pcn = d.prev.slot_ccount[ps]; }
       const int i1b = d.inst_off[r1], i2b = d.inst_off[r2], ns2 = d.inst_off[r2 + 1] - i2b;
@@ -865,12 +847,13 @@ __global__ void k_integrate(Dev d) {
   }
 }
 
-// warm-start upload helper: (re)build the hash of a frame from its slots
-__global__ void k_hash_slots(Dev d, FrameBuf fb, int n_slots) {
+// warm-start upload helper: (re)build the pair table of a frame from its slots
+__global__ void k_pair_slots(Dev d, FrameBuf fb, int n_slots) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
     if (fb.slot_ccount[s] <= 0) continue;
     int r1 = fb.slot_row1[s], r2 = fb.slot_row2[s];
-    hash_insert(fb, d.hash_mask, pair_key(d.body_world[r1], d.body_id[r1], d.body_id[r2]), s);
+    if (r1 == r2) continue;
+    fb.pair_slot[pair_index(d, d.body_world[r1], r1, r2)] = s;
   }
 }
 
