@@ -45,18 +45,30 @@ def kernel_bytes(name, c):
         "k_broadphase": nb * 36 + P * 32,
         # per candidate: 2 placed shape blocks read; per contact: ContactRec written (104 B)
         "k_narrowphase": P * 2 * 8 * c["placed_f64_per_body"] + K * 104,
-        # per group: 2 bodies x 41 doubles; per contact: ContactRec read (104) + warm-start read (56) + RowRec written (320)
-        "k_equations": G * 2 * 328 + K * (104 + 56 + 320),
+        # per group: 2 bodies x 41 doubles; per contact: raw contact read (88) + warm-start read (56) + ContactRec (104) and
+        # RowRec (320) written
+        "k_equations": G * 2 * 328 + K * (88 + 56 + 104 + 320),
         # per candidate slot: rows/kinds/counts (20 B) read, root written (4), island list (4)
         "k_islands": P * 28 + nb * 12,
-        # per contact: RowRec read once (320 B) + 3 lambdas written (24 B); per dynamic body: delta-v read+write (96 B)
-        "k_solve": K * 344 + nd * 96,
+        # per contact: image rows read once (440 B) + 3 lambdas written (24 B); per dynamic body: image body read (64 B),
+        # delta-v written (48 B)
+        "k_solve": K * 464 + nd * 112,
         # 512 B per body-step (336 read + 176 written)
         "k_integrate": nb * 512,
-        # tile images: RowRec read once (296 B) and written lane-transposed (296 B) per contact; 128 B per dynamic body
-        "k_tile_build": K * 592 + nd * 256,
+        # tile images: RowRec read once (296 B), lane-transposed rows written (55 doubles = 440 B) per contact; per dynamic
+        # body: inverse mass + inverse inertia + deltas read (128 B), 64 B written
+        "k_tile_build": K * 736 + nd * 192,
     }
     return table[name]
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), scaled to
+# this workload where the capture was taken on a 2048-world batch; None where no capture exists yet.
+TRAFFIC_NCU = {}
+try:
+    TRAFFIC_NCU = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic_per_launch.json")))["bytes_per_launch_8192_worlds"]
+except Exception:  # noqa: BLE001
+    pass
 
 
 class ClockSampler(threading.Thread):
@@ -259,6 +271,7 @@ def main():
     start_contacts = H.contacts_for(bodies)
     e.download_contacts(start_contacts)
     counts0 = e.stats()
+    work0 = (counts0["contact_iterations"], counts0["joint_row_iterations"])
 
     stream = torch.cuda.ExternalStream(e.stream_handle(), device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -368,8 +381,24 @@ def main():
         dur_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
         ach = kernel_bytes(dom, c) / (dur_ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                            "traffic": TRAFFIC_NCU.get(dom), "peak_source": "measured" if peaks else "fallback",
                             "avg_launch_ms": dur_ms, "share_of_step": ktimes[dom][0] / total_k if total_k else None}
+        # The solver is not an HBM kernel (each row crosses HBM once per step): its ceiling is the FP64 pipe without FMA
+        # (tools/fp64_peak.cu: profiles/r01_fp64_peak.json) and, in practice, the dependent-issue latency of the PGS chain.
+        # Algorithmic fp64 ops: 270 per contact-iteration, 90 per joint-row-iteration, counted on the device.
+        ci = counts["contact_iterations"] - work0[0]
+        ji = counts["joint_row_iterations"] - work0[1]
+        fp64_peak = 18.52
+        try:
+            fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))["dadd_tops"])
+        except Exception:  # noqa: BLE001
+            pass
+        if "k_solve" in ktimes and ktimes["k_solve"][0] > 0:
+            tops = (270.0 * ci + 90.0 * ji) / (ktimes["k_solve"][0] * 1e-3) / 1e12
+            line["roofline_fp64"] = {"kernel": "k_solve", "achieved": tops, "peak": fp64_peak, "unit": "T fp64 op/s (no FMA)",
+                                     "frac": tops / fp64_peak, "contact_iterations_per_step": ci / args.steps,
+                                     "mean_iterations_per_contact": ci / max(1.0, args.steps * c["contacts"]),
+                                     "peak_source": "tools/fp64_peak.cu measured on this pool's B200 (profiles/r01_fp64_peak.json)"}
         line["kernels"] = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1], "share": v[0] / total_k if total_k else None,
                                "algorithmic_GBps": kernel_bytes(k, c) / (max(v[0], 1e-9) / max(v[1], 1) * 1e-3) / 1e9}
                            for k, v in ktimes.items()}

@@ -402,6 +402,8 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   // tile images: 37 doubles per contact + 16 per dynamic body, with slack for the max-over-lanes padding of a tile
   d.tile_arena_cap = (int64_t)d.contact_cap * 72 + (int64_t)d.jrow_cap * 24 + (int64_t)nb * 24 + 4096;
   TRY(dev_alloc(ctx, pool, &d.tile_arena, (size_t)d.tile_arena_cap));
+  TRY(dev_alloc(ctx, pool, &d.work, 2));
+  CK(cudaMemsetAsync(d.work, 0, 2 * sizeof(unsigned long long), ctx->stream));
   TRY(dev_alloc(ctx, pool, &d.flags, FLAG_COUNT));
   CK(cudaMemsetAsync(d.flags, 0, FLAG_COUNT * sizeof(int32_t), ctx->stream));
   TRY(alloc_frame(ctx, d.cur, d));
@@ -736,6 +738,13 @@ extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, 
 extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
   if (!ctx || !out) return EP_EINVAL;
   ctx->stats[EP_STAT_KERNEL_LAUNCHES] = ctx->launches;
+  if (ctx->have_worlds) {
+    unsigned long long wk[2] = {0, 0};
+    cudaStreamSynchronize(ctx->stream);
+    if (cudaMemcpy(wk, ctx->d.work, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      ctx->stats[EP_STAT_CONTACT_ITERATIONS] = (int64_t)wk[0]; ctx->stats[EP_STAT_JOINT_ROW_ITERATIONS] = (int64_t)wk[1];
+    }
+  }
   for (int i = 0; i < n && i < EP_STAT_COUNT; i++) out[i] = ctx->stats[i];
   return EP_OK;
 }

@@ -262,7 +262,7 @@ __device__ __forceinline__ void apply_pre(double dl, const double* J, const doub
 // flat row sequence: ALL 32 lanes of the warp run the same loops (to the largest row count / iteration count of the tile,
 // predicated off where a lane has fewer rows, has converged, or holds no island) and re-converge with __syncwarp after
 // every row, so changing the body pair is the only divergent section and it never outlives its row.
-template <class TT>
+template <bool PREFETCH, class TT>
 __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   const bool have = isl >= 0;
   const int gn = have ? d.isl_cnt[isl] : 0, w = have ? d.isl_world[isl] : 0, C = have ? d.isl_nc[isl] : 0, R = have ? C + d.isl_nj[isl] : 0;
@@ -299,11 +299,12 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
     double p1 = 0;
     {
       RowN nxt;
-      if (!done && R > 0) load_row_n(T, 0, nxt);
+      if (PREFETCH && !done && R > 0) load_row_n(T, 0, nxt);
       for (int r = 0; r < Rmax; r++) {
         if (!done && r < R) {
-          RowN cur = nxt;
-          if (r + 1 < R) load_row_n(T, r + 1, nxt);
+          RowN cur;
+          if (PREFETCH) { cur = nxt; if (r + 1 < R) load_row_n(T, r + 1, nxt); }
+          else load_row_n(T, r, cur);
           pair_enter(T, P, cur.desc);
           const double lo = (cur.desc & DESC_JOINT) ? -kMaxImpulse : 0.0;
           const double prev = cur.invC * (cur.B - gw_lambda(cur.J, P.s1, P.s2) - eps * cur.lam);
@@ -322,11 +323,12 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
     double p2 = (gn == 1) ? p1 : 0;
     {
       RowF nxt;
-      if (!done && C > 0) load_row_f(T, 0, nxt);
+      if (PREFETCH && !done && C > 0) load_row_f(T, 0, nxt);
       for (int c = 0; c < Cmax; c++) {
         if (!done && c < C) {
-          RowF cur = nxt;
-          if (c + 1 < C) load_row_f(T, c + 1, nxt);
+          RowF cur;
+          if (PREFETCH) { cur = nxt; if (c + 1 < C) load_row_f(T, c + 1, nxt); }
+          else load_row_f(T, c, cur);
           pair_enter(T, P, cur.desc);
           const double cap = cur.mu * cur.nl;
           const double dPrev1 = cur.f1InvC * (cur.f1B - gw_lambda(cur.e1, P.s1, P.s2) - eps * cur.l1);
@@ -353,6 +355,8 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   if (!have) return;
   atomicMin(&d.world_min_rem[w], rem);
   d.body_iters[d.isl_root[isl]] = iterations - rem;
+  atomicAdd(&d.work[0], (unsigned long long)C * (iterations - rem));
+  if (R > C) atomicAdd(&d.work[1], (unsigned long long)(R - C) * (iterations - rem));
   // scatter: lambdas back to the slot-order rows (next frame's warm start, Solver.elm:320-335), delta velocities to the bodies
   for (int c = 0; c < C; c++) {
     RowRec& o = d.cur.rows[T.contact_index(c)];
@@ -366,6 +370,8 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   }
 }
 
+// Rows are prefetched one row ahead into registers only where they come from L2 (a staged tile's LDS latency hides behind
+// the FP64 chain by itself, and the registers saved double the warps per SM).
 // One warp per tile.  MODE 2: whole image staged in dynamic shared memory; MODE 1: bodies + descriptors staged, rows read
 // from the image in place (L2) one row ahead; MODE 0: everything in place, four warps per CTA.  Processes the tiles of
 // classes [bin_lo, bin_hi] whose residency (k_tile_build) is MODE.
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int
       __syncwarp();
       T.bind(sm, MODE == 2 ? sm + head : img + head);
     }
-    solve_lane(d, T, lane < tr.count ? d.isl_sorted[tr.first + lane] : -1);
+    solve_lane<MODE != 2>(d, T, lane < tr.count ? d.isl_sorted[tr.first + lane] : -1);
   }
 }
 
@@ -512,7 +518,11 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi)
       if (below) { rem = remaining - 1; break; }
       remaining--;
     }
-    if (tid == 0) { atomicMin(&d.world_min_rem[w], rem); d.body_iters[d.isl_root[isl]] = iterations - rem; }
+    if (tid == 0) {
+      atomicMin(&d.world_min_rem[w], rem); d.body_iters[d.isl_root[isl]] = iterations - rem;
+      atomicAdd(&d.work[0], (unsigned long long)d.isl_nc[isl] * (iterations - rem));
+      if (d.isl_nj[isl]) atomicAdd(&d.work[1], (unsigned long long)d.isl_nj[isl] * (iterations - rem));
+    }
     __syncthreads();
   }
 }
