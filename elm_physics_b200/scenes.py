@@ -231,3 +231,123 @@ def small_mixed_world(seed=1, n=12, with_extras=True):
         bodies.append(("rider", P.move_to((4.0, 0.0, 1.2), P.block((0.5, 0.5, 0.5), P.wood))))
     with_ids, _ = P.assign_ids(bodies)
     return [(P.on_earth(), with_ids)]
+
+
+# ---- C4: one large scene, convex polyhedra + compound bodies falling into a pit ---------------------------------
+def _octahedron(r):
+    v = [(r, 0, 0), (-r, 0, 0), (0, r, 0), (0, -r, 0), (0, 0, r), (0, 0, -r)]
+    f = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
+    return P.shape_unsafe_convex(f, v)
+
+
+def _square_pyramid(a, h):
+    v = [(-a, -a, 0), (a, -a, 0), (a, a, 0), (-a, a, 0), (0, 0, h)]
+    f = [(0, 3, 2), (0, 2, 1), (0, 1, 4), (1, 2, 4), (2, 3, 4), (3, 0, 4)]      # triangular mesh; coplanar faces are merged
+    return P.shape_unsafe_convex(f, v)
+
+
+def _pile_body(kind, mat):
+    if kind == 0:
+        return P.block((0.9, 0.7, 0.5), mat)
+    if kind == 1:
+        return P.cylinder(0.4, 0.9, mat)
+    if kind == 2:
+        return P.cone(0.45, 0.9, mat)
+    if kind == 3:
+        return P.dynamic([(_octahedron(0.5), mat)])
+    if kind == 4:
+        return P.dynamic([(_square_pyramid(0.45, 0.8), mat)])
+    if kind == 5:      # block + sphere compound
+        return P.dynamic([(P.shape_block((0.6, 0.6, 0.6), center=(-0.35, 0, 0)), mat), (P.shape_sphere(0.3, center=(0.35, 0, 0)), mat)])
+    if kind == 6:      # dumbbell of three cylinders (Physics/Shape.elm:257-269 style)
+        return P.dynamic([(P.shape_cylinder(12, 0.3, 0.25, center=(0, 0, -0.4)), mat), (P.shape_cylinder(12, 0.12, 0.6), mat),
+                          (P.shape_cylinder(12, 0.3, 0.25, center=(0, 0, 0.4)), mat)])
+    # hollow crate: five thin blocks (examples/src/RaycastCar.elm:150-172 style)
+    return P.dynamic([(P.shape_block((0.8, 0.8, 0.1), center=(0, 0, -0.35)), mat), (P.shape_block((0.1, 0.8, 0.6), center=(-0.35, 0, 0)), mat),
+                      (P.shape_block((0.1, 0.8, 0.6), center=(0.35, 0, 0)), mat), (P.shape_block((0.6, 0.1, 0.6), center=(0, -0.35, 0)), mat),
+                      (P.shape_block((0.6, 0.1, 0.6), center=(0, 0.35, 0)), mat)])
+
+
+def pile_scene(n_bodies=2000, iterations=20, seed=4, layers=None):
+    """C4: plane + 4 static walls forming a square pit + `n_bodies` dynamic bodies (80 % convex hulls: block, 12-gon
+    cylinder, 12-gon cone, octahedron, square pyramid; 20 % compounds: block+sphere, dumbbell, hollow crate) dropped from a
+    lattice (spacing 2 m, jitter +-0.2 m, random orientation)."""
+    side = max(2, int(math.ceil((n_bodies / float(layers or 20)) ** 0.5)))   # side x side x layers lattice, 20 layers at full size
+    half = side + 1.0                                             # half width of the pit
+    bodies = [("floor", P.plane(P.wood))]
+    wall_h = 4.0
+    for k, (cx, cy, sx, sy) in enumerate(((half + 0.5, 0, 1.0, 2 * half + 2), (-half - 0.5, 0, 1.0, 2 * half + 2),
+                                          (0, half + 0.5, 2 * half + 2, 1.0), (0, -half - 0.5, 2 * half + 2, 1.0))):
+        bodies.append((f"wall{k}", P.move_to((cx, cy, wall_h / 2), P.static([(P.shape_block((sx, sy, wall_h)), P.wood)]))))
+    u = uniforms(scene_seed(4, seed), (n_bodies, 7))
+    q = random_quaternions(u[:, 3:6])
+    for i in range(n_bodies):
+        r = i % 10
+        kind = r if r < 5 else (r - 5 if r < 8 else r - 3)        # 0..4 hulls twice as often as the 3 compounds 5..7
+        mat = MATERIALS[i % 5]
+        ix, iy, iz = i % side, (i // side) % side, i // (side * side)
+        pos = ((ix - (side - 1) / 2) * 2.0 + (u[i, 0] - 0.5) * 0.4, (iy - (side - 1) / 2) * 2.0 + (u[i, 1] - 0.5) * 0.4,
+               1.5 + 2.0 * iz + (u[i, 2] - 0.5) * 0.4)
+        bodies.append((f"b{i}", P.place_quaternion(pos, tuple(float(c) for c in q[i]), _pile_body(kind, mat))))
+    cfg = P.on_earth()
+    cfg.solver_iterations = iterations
+    with_ids, _ = P.assign_ids(bodies)
+    return [(cfg, with_ids)]
+
+
+# ---- C5: RaycastCar-style worlds with hinge / point-to-point constraints -------------------------------------------
+def car_world(seed=0, iterations=20):
+    """Plane + static ramp (10 x 16 x 0.5 block tilted pi/16, sandbox/src/Car.elm:264-275) + chassis (compound of two
+    blocks) + 4 wheel spheres hinged to it (sandbox/src/Car.elm:177-254) + 6 hollow crates + a point-to-point tether."""
+    u = uniforms(scene_seed(5, seed), (16, 3))
+    ramp = P.static([(P.shape_block((10.0, 16.0, 0.5)), P.wood)])
+    ramp = P.move_to((0.0, 12.0, 0.6), P.rotate_around((0, 0, 0), (1, 0, 0), math.pi / 16, ramp))
+    chassis = P.dynamic([(P.shape_block((2.0, 4.0, 0.6)), P.steel), (P.shape_block((1.6, 2.0, 0.5), center=(0, -0.3, 0.55)), P.plastic)])
+    chassis = P.scale_mass_to(10.0, chassis)
+    cx, cy, cz = (u[0, 0] - 0.5) * 0.4, (u[0, 1] - 0.5) * 0.4, 1.6
+    chassis = P.set_velocity_to((0.0, 2.0 + u[0, 2], 0.0), P.move_to((cx, cy, cz), chassis))
+    bodies = [("floor", P.plane(P.wood)), ("ramp", ramp), ("chassis", chassis)]
+    cons = {}
+    for k, (wx, wy) in enumerate(((-1.3, 1.4), (1.3, 1.4), (-1.3, -1.4), (1.3, -1.4))):
+        wheel = P.scale_mass_to(2.0, P.sphere(0.6, P.rubber))
+        wheel = P.move_to((cx + wx, cy + wy, cz - 0.5), wheel)
+        bodies.append((f"wheel{k}", wheel))
+        cons[("chassis", f"wheel{k}")] = [P.Hinge((wx, wy, -0.5), (1, 0, 0), (0, 0, 0), (1, 0, 0))]
+    for k in range(6):
+        crate = _pile_body(7, P.wood)
+        crate = P.move_to((-3.0 + 1.2 * k + (u[4 + k, 0] - 0.5) * 0.2, 6.0 + (u[4 + k, 1] - 0.5) * 0.2, 1.0 + 0.9 * (k % 2)), crate)
+        bodies.append((f"crate{k}", crate))
+    cons[("chassis", "crate0")] = [P.PointToPoint((0.0, 2.0, 0.0), (0.0, -0.4, 0.0))]       # tether
+    cfg = P.on_earth()
+    cfg.solver_iterations = iterations
+
+    def constrain(a):
+        tab = {b: v for (x, b), v in cons.items() if x == a}
+        return (lambda b: tab.get(b, [])) if tab else None
+    cfg.constrain = constrain
+    with_ids, _ = P.assign_ids(bodies)
+    return (cfg, with_ids)
+
+
+def car_worlds(n_worlds, first_world=0, iterations=20):
+    return [car_world(first_world + w, iterations) for w in range(n_worlds)]
+
+
+def replicate_worlds(shapes, bodies, params, times):
+    """Tile a packed batch `times` times (same shapes table): the cheap way to a large batch of structurally identical
+    worlds (C5 at full size) without building every world through the Python object layer."""
+    from . import abi
+    assert params.collide is None
+    nb, nw, ni = bodies.n_bodies, bodies.n_worlds, bodies.n_insts
+    wbo = np.concatenate([bodies.world_body_off[:-1] + k * nb for k in range(times)] + [[times * nb]]).astype(np.int32)
+    ioff = np.concatenate([bodies.inst_off[:-1] + k * ni for k in range(times)] + [[times * ni]]).astype(np.int32)
+    cols = {name: np.concatenate([getattr(bodies, name)] * times, axis=0) for name, _ in abi.BODY_F64_FIELDS}
+    b = abi.Bodies(wbo, np.tile(bodies.body_id, times), np.tile(bodies.kind, times), ioff, np.tile(bodies.inst_shape, times),
+                   np.tile(bodies.inst_friction, times), np.tile(bodies.inst_bounciness, times), **cols)
+    nc = params.n_constraints
+    p = abi.Params(np.tile(params.gravity, (times, 1)), np.tile(params.dt, times), np.tile(params.iterations, times),
+                   con_body_a=np.concatenate([params.con_body_a + k * nb for k in range(times)]) if nc else (),
+                   con_body_b=np.concatenate([params.con_body_b + k * nb for k in range(times)]) if nc else (),
+                   con_kind=np.tile(params.con_kind, times) if nc else (),
+                   con_data=np.tile(params.con_data, (times, 1)) if nc else ())
+    return shapes, b, p

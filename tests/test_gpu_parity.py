@@ -162,6 +162,26 @@ def test_joint_constraints_lockstep(engine, oracle, kind):
     assert np.isfinite(bg.pos).all()
 
 
+def test_convex_pile_resident(engine, oracle):
+    """C4 at test size: 150 convex hulls / compounds dropped into a walled pit (static block walls), 260 resident steps:
+    islands of every size class up to ~150 contacts (lane tiles and both team kernels), general convex SAT + clipping,
+    compound bodies."""
+    shapes, bodies, params = _packed(scenes.pile_scene(150, layers=10))
+    _, _, _, og = H.resident_vs_oracle(oracle, engine, shapes, bodies, params, 260, what="pile150")
+    assert og.n_contacts > 400
+    assert og.world_n_islands[0] < 80
+
+
+def test_car_worlds_resident(engine, oracle):
+    """C5 at test size: 24 car worlds (chassis compound + 4 hinged wheels + ramp + 6 hollow crates + tether),
+    120 resident steps: joint rows inside lane-per-island tiles and team islands, batched."""
+    shapes, bodies, params = _packed(scenes.car_worlds(24))
+    assert params.n_constraints == 24 * 5
+    _, bg, _, og = H.resident_vs_oracle(oracle, engine, shapes, bodies, params, 120, what="cars24")
+    assert int(og.group_n_constraints[:og.n_groups].sum()) == 24 * 5
+    assert np.isfinite(bg.pos).all()
+
+
 def test_collide_callback_mask(engine, oracle):
     """`collide` evaluated caller-side (BroadPhase.elm:189-215): boxes that ignore each other fall through."""
     worlds = scenes.stack_scene(3, 10)

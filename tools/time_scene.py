@@ -27,6 +27,9 @@ def main():
         shapes, bodies, params = scenes.mixed_worlds(int(arg or 1024))
     elif name == "pile":
         shapes, bodies, params = pack.pack_worlds(scenes.pile_scene(int(arg or 2000)))
+    elif name == "cars":
+        shapes, bodies, params = pack.pack_worlds(scenes.car_worlds(64))
+        shapes, bodies, params = scenes.replicate_worlds(shapes, bodies, params, max(1, int(arg or 4096) // 64))
     else:
         raise SystemExit("unknown scene")
     e = eng.Engine(0)
@@ -41,7 +44,9 @@ def main():
     e.profile(False)
     st = e.stats()
     import helpers as H
-    out = H.contacts_for(bodies)
+    from elm_physics_b200 import abi
+    nb = bodies.n_bodies
+    out = H.contacts_for(bodies) if nb < 5000 or bodies.n_worlds > 1 else abi.Contacts(bodies.n_worlds, 40 * nb, 160 * nb)
     e.download_contacts(out)
     st = e.stats()
     main_k = {k: v for k, v in kt.items() if not k.startswith("k_solve_")}
