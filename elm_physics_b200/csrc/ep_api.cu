@@ -279,6 +279,19 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   }
   TRY(dev_upload(ctx, pool, &d.body_world, body_world.data(), nb));
   TRY(dev_upload(ctx, pool, &d.world_pair_off, pair_off.data(), nw));
+  {   // broadphase chunk table
+    std::vector<int32_t> cw, cp, wco(nw + 1, 0);
+    for (int w = 0; w < nw; w++) {
+      int64_t n = B->world_body_off[w + 1] - B->world_body_off[w], P = n * (n - 1) / 2;
+      for (int64_t p0 = 0; p0 < P; p0 += kBpChunk) { cw.push_back(w); cp.push_back((int32_t)p0); }
+      wco[w + 1] = (int32_t)cw.size();
+    }
+    d.n_chunks = (int32_t)cw.size();
+    TRY(dev_upload(ctx, pool, &d.chunk_world, cw.data(), cw.size())); TRY(dev_upload(ctx, pool, &d.chunk_p0, cp.data(), cp.size()));
+    TRY(dev_upload(ctx, pool, &d.world_chunk_off, wco.data(), wco.size()));
+    TRY(dev_alloc(ctx, pool, &d.chunk_cnt, cw.size())); TRY(dev_alloc(ctx, pool, &d.chunk_icnt, cw.size()));
+    TRY(dev_alloc(ctx, pool, &d.chunk_base, cw.size())); TRY(dev_alloc(ctx, pool, &d.chunk_ibase, cw.size()));
+  }
   TRY(dev_upload_rw(ctx, pool, &d.pos, B->pos, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.quat, B->quat, 4 * (size_t)nb));
   TRY(dev_upload_rw(ctx, pool, &d.vel, B->vel, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.angvel, B->angvel, 3 * (size_t)nb));
   TRY(dev_upload_rw(ctx, pool, &d.force, B->force, 3 * (size_t)nb)); TRY(dev_upload_rw(ctx, pool, &d.torque, B->torque, 3 * (size_t)nb));
@@ -552,8 +565,13 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
     {
       CK(cudaMemsetAsync(d.cur.pair_slot, 0xFF, (size_t)d.slot_cap * sizeof(int32_t), st));
       if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
-      { Timed t(ctx, EP_K_SORT); k_sort<<<gw, 128, 0, st>>>(d); }
-      { Timed t(ctx, EP_K_BROADPHASE); k_broadphase<<<gw, 128, 0, st>>>(d); }
+      { Timed t(ctx, EP_K_SORT); k_sort<<<gw, d.nb_max <= 128 ? 128 : (d.nb_max <= 512 ? 256 : 1024), 0, st>>>(d); }
+      { Timed t(ctx, EP_K_BROADPHASE);
+        const int gc = std::max(1, std::min(d.n_chunks, ctx->sm_count * 16));
+        k_bp_count<<<gc, 128, 0, st>>>(d);
+        k_bp_scan<<<grid_for(ctx, (int64_t)d.n_worlds * 32, 128, 16), 128, 0, st>>>(d);
+        k_bp_emit<<<gc, 128, 0, st>>>(d);
+        ctx->launches += 2; }
       static const bool np_serial = getenv("EP_NP_SERIAL") != nullptr;    // profiling aid: one launch per work-item class
       if (np_serial && ctx->profiling) {
         for (int c = 0; c < kClasses; c++) {

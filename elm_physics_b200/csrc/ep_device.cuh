@@ -82,6 +82,9 @@ struct Dev {
   double *pre_pos, *pre_quat; // transform3d before the last integration (contactPoints, Physics.elm:1180-1186)
   // placement work items: (instance, rel offset*2 + isDirection)
   const int32_t* pl_inst; const int32_t* pl_code; int32_t n_pl_moving; int32_t n_pl_all;
+  // broadphase chunks: consecutive pair-index ranges of a world (ep_kernels.cuh k_bp_*)
+  int32_t n_chunks; const int32_t* chunk_world; const int32_t* chunk_p0; const int32_t* world_chunk_off;
+  int32_t *chunk_cnt, *chunk_icnt, *chunk_base, *chunk_ibase;
   // params (ep_params)
   const double* gravity; const double* dt; const int32_t* iterations;
   const uint8_t* collide; const int64_t* collide_off;

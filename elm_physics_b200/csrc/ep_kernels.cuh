@@ -2,7 +2,7 @@
 // simulate call, over ALL resident worlds:
 //   k_place       Shape.placeIn of every moving body's shapes            (src/Internal/Shape.elm:94-110)
 //   k_sort        stable gravity sort per world                          (src/Physics.elm:548-573)
-//   k_broadphase  i<j bounding-sphere test, ordered ballot compaction    (src/Internal/BroadPhase.elm:54-215)
+//   k_bp_*        i<j bounding-sphere test, ordered ballot compaction    (src/Internal/BroadPhase.elm:54-215)
 //   k_narrowphase shape matrix per candidate pair                        (src/Internal/NarrowPhase.elm, src/Collision/*)
 //   k_equations   Jacobian rows + Spook scalars + warm-start lookup      (src/Internal/Equation.elm:116-450)
 //   k_islands     union-find (min id root), per-island group lists       (src/Internal/Islands.elm)
@@ -107,16 +107,21 @@ __device__ __forceinline__ int item_class(int ka, int kb) { return ka < kb ? ka 
 // classes in descending expected cost: the work list starts the long items first
 __constant__ int kClassOrder[kClasses] = {7, 1, 10, 0, 4, 9, 8, 3, 2, 22, 28, 21, 16, 11, 5, 29, 17, 23, 35, 14, 15, 20, 6, 12, 13, 18, 19, 24, 25, 26, 27, 30, 31, 32, 33, 34};
 
-__global__ void k_broadphase(Dev d) {
-  __shared__ int s_warp[32], s_warp2[32];
-  __shared__ int s_base, s_ibase, s_dead;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
-    int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
-    int64_t P = (int64_t)n * (n - 1) / 2;
-    // pass A: count candidate pairs and their shape pairs (work items)
+// The i<j pairs of a world are cut into chunks of kBpChunk consecutive pair indices (host table, ep_upload_worlds), so a
+// world of any size spreads over many CTAs while the slots still come out in pair-enumeration order:
+//   k_bp_count  one CTA per chunk: candidate pairs and shape pairs (work items) of the chunk
+//   k_bp_scan   one warp per world: exclusive scan over the world's chunks, the world's slot / item ranges
+//   k_bp_emit   one CTA per chunk: ordered ballot compaction into the pair slots, work items scattered into class bins
+constexpr int kBpChunk = 4096;
+__global__ void __launch_bounds__(128) k_bp_count(Dev d) {
+  __shared__ int s_warp[4], s_warp2[4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int c = blockIdx.x; c < d.n_chunks; c += gridDim.x) {
+    const int w = d.chunk_world[c];
+    const int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    const int64_t P = (int64_t)n * (n - 1) / 2, p0 = d.chunk_p0[c], p1 = min(P, p0 + kBpChunk);
     int cnt = 0, icnt = 0;
-    for (int64_t p = threadIdx.x; p < P; p += blockDim.x) {
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
       int i, j; pair_from_index(p, n, i, j);
       int r1 = d.sorted[r0 + i], r2 = d.sorted[r0 + j];
       bool may = may_contact(d, w, r0, n, r1, r2);
@@ -127,26 +132,59 @@ __global__ void k_broadphase(Dev d) {
     if (lane == 0) { s_warp[wid] = cnt; s_warp2[wid] = icnt; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      int tot = 0, itot = 0;
-      for (int k = 0; k < nwarps; k++) { tot += s_warp[k]; itot += s_warp2[k]; }
-      int base = atomicAdd(&d.cur.counters[CNT_CAND], tot);
-      int ibase = atomicAdd(&d.cur.counters[CNT_ITEMS], itot);
-      bool dead = false;
-      if ((int64_t)base + tot > d.slot_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 1; dead = true; }
-      if ((int64_t)ibase + itot > d.item_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 5; dead = true; }
-      if (dead) { tot = 0; base = 0; ibase = 0; }
-      d.cur.cand_base[w] = base; d.cur.cand_n[w] = tot;
-      s_base = base; s_ibase = ibase; s_dead = dead || tot == 0;
-      d.world_min_rem[w] = d.iterations[w];
+      d.chunk_cnt[c] = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+      d.chunk_icnt[c] = s_warp2[0] + s_warp2[1] + s_warp2[2] + s_warp2[3];
     }
     __syncthreads();
-    const bool dead = s_dead != 0;
-    // pass B: ordered (enumeration order) ballot compaction of the slots; work items scattered into class bins
-    int running = s_base, irunning = s_ibase;
-    for (int64_t p0 = 0; p0 < P && !dead; p0 += blockDim.x) {
+  }
+}
+__global__ void __launch_bounds__(128) k_bp_scan(Dev d) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = warp; w < d.n_worlds; w += nwarps) {
+    const int c0 = d.world_chunk_off[w], c1 = d.world_chunk_off[w + 1];
+    int tot = 0, itot = 0;
+    for (int c = c0 + lane; c < c1; c += 32) { tot += d.chunk_cnt[c]; itot += d.chunk_icnt[c]; }
+    for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); itot += __shfl_xor_sync(0xffffffffu, itot, o); }
+    int base = 0, ibase = 0, dead = 0;
+    if (lane == 0) {
+      base = atomicAdd(&d.cur.counters[CNT_CAND], tot);
+      ibase = atomicAdd(&d.cur.counters[CNT_ITEMS], itot);
+      if ((int64_t)base + tot > d.slot_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 1; dead = 1; }
+      if ((int64_t)ibase + itot > d.item_cap) { d.flags[FLAG_PAIR_OVERFLOW] = 5; dead = 1; }
+      if (dead) { tot = 0; base = 0; ibase = 0; }
+      d.cur.cand_base[w] = base; d.cur.cand_n[w] = tot;
+      d.world_min_rem[w] = d.iterations[w];
+    }
+    base = __shfl_sync(0xffffffffu, base, 0); ibase = __shfl_sync(0xffffffffu, ibase, 0); dead = __shfl_sync(0xffffffffu, dead, 0);
+    // exclusive scan over the chunks of the world, 32 at a time
+    for (int cb = c0; cb < c1; cb += 32) {
+      const int c = cb + lane;
+      const int v = c < c1 ? d.chunk_cnt[c] : 0, iv = c < c1 ? d.chunk_icnt[c] : 0;
+      int sc = v, isc = iv;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, sc, o), it = __shfl_up_sync(0xffffffffu, isc, o);
+        if (lane >= o) { sc += t; isc += it; }
+      }
+      if (c < c1) { d.chunk_base[c] = dead ? -1 : base + sc - v; d.chunk_ibase[c] = dead ? -1 : ibase + isc - iv; }
+      base += __shfl_sync(0xffffffffu, sc, 31); ibase += __shfl_sync(0xffffffffu, isc, 31);
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_bp_emit(Dev d) {
+  __shared__ int s_warp[32], s_warp2[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = blockIdx.x; c < d.n_chunks; c += gridDim.x) {
+    const int w = d.chunk_world[c];
+    const int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    const int64_t P = (int64_t)n * (n - 1) / 2, pc0 = d.chunk_p0[c], pc1 = min(P, pc0 + kBpChunk);
+    int running = d.chunk_base[c], irunning = d.chunk_ibase[c];
+    const bool dead = running < 0 || d.chunk_cnt[c] == 0;
+    // ordered (enumeration order) ballot compaction of the slots; work items scattered into class bins
+    for (int64_t p0 = pc0; p0 < pc1 && !dead; p0 += blockDim.x) {
       int64_t p = p0 + threadIdx.x;
       bool flag = false; int r1 = 0, r2 = 0, ncon = 0, nit = 0, ns2 = 0; bool may = false;
-      if (p < P) {
+      if (p < pc1) {
         int i, j; pair_from_index(p, n, i, j);
         r1 = d.sorted[r0 + i]; r2 = d.sorted[r0 + j];
         may = may_contact(d, w, r0, n, r1, r2);
@@ -162,7 +200,7 @@ __global__ void k_broadphase(Dev d) {
       if (lane == 31) s_warp2[wid] = iscan;
       __syncthreads();
       int before = 0, total = 0, ibefore = 0, itotal = 0;
-      for (int k = 0; k < nwarps; k++) { int c = s_warp[k], ic = s_warp2[k]; if (k < wid) { before += c; ibefore += ic; } total += c; itotal += ic; }
+      for (int k = 0; k < nwarps; k++) { int cc = s_warp[k], ic = s_warp2[k]; if (k < wid) { before += cc; ibefore += ic; } total += cc; itotal += ic; }
       int s = running + before + __popc(bal & ((1u << lane) - 1u));
       int item0 = irunning + ibefore + iscan - nit;
       if (flag) {

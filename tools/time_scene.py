@@ -49,6 +49,22 @@ def main():
     out = H.contacts_for(bodies) if nb < 5000 or bodies.n_worlds > 1 else abi.Contacts(bodies.n_worlds, 40 * nb, 160 * nb)
     e.download_contacts(out)
     st = e.stats()
+    if bodies.n_worlds == 1:      # level schedule of the largest island (what bounds k_solve_team): levels, sum over levels of the longest group
+        import numpy as np
+        ng = out.n_groups
+        gi, id1, id2 = out.group_island[:ng], out.group_id1[:ng], out.group_id2[:ng]
+        cn = np.diff(out.group_contact_off[:ng + 1]) + out.group_n_constraints[:ng] * 3
+        kind = {int(i): int(k) for i, k in zip(bodies.body_id, bodies.kind)}
+        big = np.bincount(gi[gi >= 0]).argmax()
+        last, lv_max = {}, {}
+        for g in np.nonzero(gi == big)[0]:
+            lv = max(last.get(int(b), 0) for b in (id1[g], id2[g]) if kind[int(b)] == 2)
+            for b in (id1[g], id2[g]):
+                if kind[int(b)] == 2:
+                    last[int(b)] = lv + 1
+            lv_max[lv] = max(lv_max.get(lv, 0), int(cn[g]))
+        print(json.dumps({"largest_island_groups": int((gi == big).sum()), "levels": len(lv_max), "sum_over_levels_of_longest_group_rows": int(sum(lv_max.values())),
+                          "contacts_in_island": int(cn[gi == big].sum())}))
     main_k = {k: v for k, v in kt.items() if not k.startswith("k_solve_")}
     tot = sum(v[0] for v in main_k.values())
     print(json.dumps({"scene": a.scene, "bodies": bodies.n_bodies, "ms_per_step": tot / a.steps,
