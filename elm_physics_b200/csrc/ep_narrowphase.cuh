@@ -303,6 +303,7 @@ EPD void project_convex(V3 axis, const Cvx& c, double& mn, double& mx) {
     mn = cc - e; mx = cc + e;
   } else {
     mn = kMaxNumber; mx = -kMaxNumber;
+#pragma unroll 4
     for (int i = c.nv - 1; i >= 0; i--) {
       V3 v = c.vert(i);
       double val = v.x * axis.x + v.y * axis.y + v.z * axis.z;
