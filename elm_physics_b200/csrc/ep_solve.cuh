@@ -171,17 +171,37 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
       }
       const int c0 = d.cur.slot_cstart[s], cn = max(d.cur.slot_ccount[s], 0);
       for (int k = 0; k < cn; k++, r++, c++) {
-        const RowRec& src = d.cur.rows[c0 + k];
-        tile_write_jac(T, false, r, 0, src.nJ, I[0], I[1]);
-        T.nrow(r, NR_B) = src.nB; T.nrow(r, NR_INVC) = src.nInvC; T.nrow(r, NR_LAM) = src.lamN;
-        tile_write_jac(T, true, c, FR_E1, src.f1J, I[0], I[1]);
-        tile_write_jac(T, true, c, FR_E2, src.f2J, I[0], I[1]);
-        T.frow(c, FR_F1B) = src.f1B; T.frow(c, FR_F1INVC) = src.f1InvC; T.frow(c, FR_F2B) = src.f2B; T.frow(c, FR_F2INVC) = src.f2InvC;
-        T.frow(c, FR_MU) = src.mu; T.frow(c, FR_L1) = src.lamF1; T.frow(c, FR_L2) = src.lamF2;
         T.desc1(r) = pair | first; first = 0;
         T.desc2(c) = pair | (r << 16);
         T.contact_index(c) = c0 + k;
       }
+    }
+    // contact rows, all lanes in lock step on the contact index so that every store of the warp covers whole 128 B lines
+    // (a lane-by-lane copy in group order writes the same lines with partial masks: twice the DRAM traffic, measured)
+    int curPair = -1; M33 I1, I2;
+    for (int cc = 0; cc < td.maxC; cc++) {
+      if (cc >= nc) continue;
+      const int desc = T.desc2(cc), rowN = (desc >> 16) & 0xff, pr = desc & 0xffff;
+      if (pr != curPair) {
+        curPair = pr;
+        const int lb[2] = {pr & 0xff, pr >> 8};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          M33 I; I.m11 = I.m21 = I.m31 = I.m12 = I.m22 = I.m32 = I.m13 = I.m23 = I.m33 = 0;
+          if (lb[e] > 0) {
+            const double* im = d.iiw + 9 * (size_t)T.body_row(lb[e]);
+            I.m11 = im[0]; I.m21 = im[1]; I.m31 = im[2]; I.m12 = im[3]; I.m22 = im[4]; I.m32 = im[5]; I.m13 = im[6]; I.m23 = im[7]; I.m33 = im[8];
+          }
+          if (e == 0) I1 = I; else I2 = I;
+        }
+      }
+      const RowRec& src = d.cur.rows[T.contact_index(cc)];
+      tile_write_jac(T, false, rowN, 0, src.nJ, I1, I2);
+      T.nrow(rowN, NR_B) = src.nB; T.nrow(rowN, NR_INVC) = src.nInvC; T.nrow(rowN, NR_LAM) = src.lamN;
+      tile_write_jac(T, true, cc, FR_E1, src.f1J, I1, I2);
+      tile_write_jac(T, true, cc, FR_E2, src.f2J, I1, I2);
+      T.frow(cc, FR_F1B) = src.f1B; T.frow(cc, FR_F1INVC) = src.f1InvC; T.frow(cc, FR_F2B) = src.f2B; T.frow(cc, FR_F2INVC) = src.f2InvC;
+      T.frow(cc, FR_MU) = src.mu; T.frow(cc, FR_L1) = src.lamF1; T.frow(cc, FR_L2) = src.lamF2;
     }
   }
 }

@@ -26,7 +26,7 @@ def main():
     elif name == "mixed":
         shapes, bodies, params = scenes.mixed_worlds(int(arg or 1024))
     elif name == "pile":
-        shapes, bodies, params = pack.pack_worlds(scenes.pile_scene(int(arg or 2000)))
+        shapes, bodies, params = pack.pack_worlds(scenes.pile_scene(int(arg or 2000), iterations=int(os.environ.get('PILE_ITERS', 20))))
     elif name == "cars":
         shapes, bodies, params = pack.pack_worlds(scenes.car_worlds(64))
         shapes, bodies, params = scenes.replicate_worlds(shapes, bodies, params, max(1, int(arg or 4096) // 64))
