@@ -50,6 +50,7 @@ struct ep_ctx {
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
   int lanes_grid = 0, build_grid = 0;
+  size_t team_smem_set = 48 * 1024;
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -392,6 +393,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.isl_groups, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &d.sched, d.slot_cap)); TRY(dev_alloc(ctx, pool, &d.sched_lvl, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &d.lvl_off, d.slot_cap)); TRY(dev_alloc(ctx, pool, &d.lvl_cur, d.slot_cap));
+  TRY(dev_alloc(ctx, pool, &d.sched_rec, 2 * (size_t)d.slot_cap));
   TRY(dev_alloc(ctx, pool, &d.isl_key, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nc, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nb, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nj, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_root, nb)); TRY(dev_alloc(ctx, pool, &d.isl_sorted, nb));
   TRY(dev_alloc(ctx, pool, &d.key_cnt, 2 * kKeys));
@@ -609,8 +611,22 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       };
       const int tiles_cap = d.n_bodies / 32 + 2;
       // longest first: CTA-per-island teams, warp-per-island teams, then the lane classes from the largest down
-      TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256><<<ctx->sm_count * 2, 256, 0, sx>>>(d, 8, kBins - 1); }));
-      TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32><<<ctx->sm_count * 16, 32, 0, sx>>>(d, kLaneBinMax + 1, 7); }));
+      // team kernels: shared memory = level-walk chunk (3 x 8T ints) + per-body last level / inverse mass / deltas of the largest world
+      const size_t body_b = (size_t)((d.nb_max + 1) & ~1) * 4 + (size_t)d.nb_max * 56;
+      const bool smemb = body_b + 3 * 8 * 256 * 4 <= 200 * 1024;
+      const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
+      if (smemb) {
+        if (sm_cta > ctx->team_smem_set) {
+          CK(cudaFuncSetAttribute(k_solve_team<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cta));
+          CK(cudaFuncSetAttribute(k_solve_team<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cta));
+          ctx->team_smem_set = sm_cta;
+        }
+        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1); }));
+        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7); }));
+      } else {
+        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1); }));
+        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7); }));
+      }
       TRY(side(EP_K_SOLVE_LANES_B5, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5); }));
       TRY(side(EP_K_SOLVE_LANES_B4, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4); }));
       TRY(side(EP_K_SOLVE_LANES_B3, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3); }));

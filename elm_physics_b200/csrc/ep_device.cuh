@@ -18,14 +18,18 @@ struct ContactRec {
 // `ContactEquations` + `ContactData` (src/Internal/Equation.elm:63-93): three Jacobian rows (wA, vB, wB;
 // vA = -vB) and their Spook scalars; min/max normal impulse are the constants 0 / 1e6.
 // Spook eps is the same for every row of a world (it depends on dt only) and is recomputed where needed.
+// xIa / xIb = invInertiaWorld(body1) * wA and invInertiaWorld(body2) * wB of each row (zero for a non-dynamic body): the
+// reference forms them on every row of every iteration (Solver.elm:505-550); they are constant during the solve and
+// computed once, with the same operations in the same order, when the row is built.
 struct RowRec {
-  double nJ[9], nB, nInvC, lamN;                                        // sweep 1 reads these 12 doubles (96 B)
-  double f1J[9], f2J[9], f1B, f1InvC, f2B, f2InvC, mu, lamF1, lamF2;   // sweep 2 reads these 25 (+ lamN)
+  double nJ[9], nB, nInvC, lamN;                                        // sweep 1 reads these 12 doubles (+ nIa nIb)
+  double f1J[9], f2J[9], f1B, f1InvC, f2B, f2InvC, mu, lamF1, lamF2;   // sweep 2 reads these 25 (+ lamN, f*Ia f*Ib)
   double dN, dF1, dF2;   // |deltaLambda| of the last iteration, for the canonical-order sum of the team solver
-};                       // 40 doubles = 320 B: rows stay 64 B aligned
+  double nIa[3], nIb[3], f1Ia[3], f1Ib[3], f2Ia[3], f2Ib[3];
+};                       // 58 doubles = 464 B (16 B aligned)
 
 // `ConstraintEquation` (src/Internal/Equation.elm:503-511); bounds are the constants -1e6 / 1e6.
-struct JointRow { double J[9]; double B, invC, eps, lam; double dl; double pad[2]; };   // 16 doubles; dl = |deltaLambda| of the last iteration
+struct JointRow { double J[9]; double B, invC, eps, lam; double dl; double Ia[3], Ib[3]; double pad[4]; };   // 24 doubles; dl = |deltaLambda| of the last iteration
 
 constexpr int kIterKeys = 32, kGroupKeys = 4;
 constexpr int kBins = 10;    // island size classes for the solver's work list (ep_solve.cuh)
@@ -98,6 +102,7 @@ struct Dev {
   int32_t* uf_count;          // [n_bodies]
   int32_t* uf_fill;           // [n_bodies]
   int32_t* isl_off; int32_t* isl_cnt; int32_t* isl_world; int32_t* isl_groups;
+  int4* sched_rec;            // [2 * slot_cap] TeamRec of every group of a team island, schedule order (ep_solve.cuh)
   int32_t *sched, *sched_lvl, *lvl_off, *lvl_cur;   // [slot_cap] level schedule of each island's groups (k_solve_team), parallel to isl_groups
   int32_t* world_min_rem;     // [n_worlds] min over islands of remaining iterations
   int32_t* world_n_islands;   // [n_worlds]

@@ -328,6 +328,14 @@ __device__ __forceinline__ double compute_contact_b(double spookA, double spookB
               + (bi.w.x * J[0] + bi.w.y * J[1] + bi.w.z * J[2]);
   return -g * spookA - gW * spookB;
 }
+// invInertiaWorld * angular Jacobian of a row, as applyVelocityBody1/2 forms it (Solver.elm:505-550); zero for non-dynamic bodies
+__device__ __forceinline__ void inertia_times(const BodyK& k, const double* w, double* out) {
+  if (k.kind != 2) { out[0] = 0; out[1] = 0; out[2] = 0; return; }
+  const M33& I = k.I;
+  out[0] = I.m11 * w[0] + I.m12 * w[1] + I.m13 * w[2];
+  out[1] = I.m21 * w[0] + I.m22 * w[1] + I.m23 * w[2];
+  out[2] = I.m31 * w[0] + I.m32 * w[1] + I.m33 * w[2];
+}
 struct Spook { double a, b, eps; };
 __device__ __forceinline__ Spook spook(double dt) {      // Equation.elm:369-376, 494-501
   Spook s;
@@ -340,6 +348,7 @@ __device__ __forceinline__ void joint_row(JointRow& r, double dt, V3 gravity, co
   r.B = velocityB - (dt * compute_gimf(gravity, b1, b2, r.J));     // computeSolverB 520-522
   r.invC = 1 / (compute_gimgt(b1, b2, r.J) + eps);                 // computeSolverInvC 527-529
   r.eps = eps; r.lam = 0;
+  inertia_times(b1.k, r.J, r.Ia); inertia_times(b2.k, r.J + 6, r.Ib);
 }
 // point-to-point rows for basis x,y,z (Equation.elm:308-361); writes 3 rows in EMISSION order
 __device__ void p2p_rows(JointRow* out, double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2, V3 pivot1, V3 pivot2) {
@@ -376,6 +385,9 @@ __device__ __forceinline__ void contact_row(RowRec& r, V3 ni, V3 pi, V3 pj, doub
   r.f2InvC = 1 / (compute_gimgt(b1, b2, r.f2J) + sp.eps);
   r.mu = friction;
   r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.dN = 0; r.dF1 = 0; r.dF2 = 0;
+  inertia_times(b1.k, r.nJ, r.nIa); inertia_times(b2.k, r.nJ + 6, r.nIb);
+  inertia_times(b1.k, r.f1J, r.f1Ia); inertia_times(b2.k, r.f1J + 6, r.f1Ib);
+  inertia_times(b1.k, r.f2J, r.f2Ia); inertia_times(b2.k, r.f2J + 6, r.f2Ib);
 }
 // addConstraintEquations (Equation.elm:157-361) for the pair (r1, r2) (global body rows; ncon < 0 == flipped registration):
 // rows are emitted per constraint in list order and consed, so the solver order is the reverse of emission:
@@ -420,7 +432,7 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
         rot_row(tmp[5], dt, gravity, sp, b1, b2, z1, x2);
       }
     }
-    for (int k = 0; k < nr; k++, e++) { tmp[k].dl = 0; tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
+    for (int k = 0; k < nr; k++, e++) { tmp[k].dl = 0; tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; tmp[k].pad[3] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
   }
   jstart = j0; jcount = E;
 }

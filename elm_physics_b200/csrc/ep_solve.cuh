@@ -64,20 +64,16 @@ struct TileT {
     bd = head; ti = (int*)(head + L() * (int64_t)(kBodyF64 * t.maxB)); rd = rows;
   }
 };
-// I.w of both bodies of a row, written behind its Jacobian (same expression as applyVelocityBody1/2, Solver.elm:505-550)
+// a row's Jacobian followed by its two I.w triples (computed with the row, k_equations)
 template <class TT>
-__device__ __forceinline__ void tile_write_jac(const TT& T, bool frow, int idx, int f0, const double* J, const M33& I1, const M33& I2) {
-  double v[15];
+__device__ __forceinline__ void tile_write_jac(const TT& T, bool frow, int idx, int f0, const double* J, const double* Ia, const double* Ib) {
 #pragma unroll
-  for (int k = 0; k < 9; k++) v[k] = J[k];
-  v[9] = I1.m11 * J[0] + I1.m12 * J[1] + I1.m13 * J[2];
-  v[10] = I1.m21 * J[0] + I1.m22 * J[1] + I1.m23 * J[2];
-  v[11] = I1.m31 * J[0] + I1.m32 * J[1] + I1.m33 * J[2];
-  v[12] = I2.m11 * J[6] + I2.m12 * J[7] + I2.m13 * J[8];
-  v[13] = I2.m21 * J[6] + I2.m22 * J[7] + I2.m23 * J[8];
-  v[14] = I2.m31 * J[6] + I2.m32 * J[7] + I2.m33 * J[8];
+  for (int k = 0; k < 9; k++) { if (frow) T.frow(idx, f0 + k) = J[k]; else T.nrow(idx, f0 + k) = J[k]; }
 #pragma unroll
-  for (int k = 0; k < 15; k++) { if (frow) T.frow(idx, f0 + k) = v[k]; else T.nrow(idx, f0 + k) = v[k]; }
+  for (int k = 0; k < 3; k++) {
+    if (frow) { T.frow(idx, f0 + 9 + k) = Ia[k]; T.frow(idx, f0 + 12 + k) = Ib[k]; }
+    else { T.nrow(idx, f0 + 9 + k) = Ia[k]; T.nrow(idx, f0 + 12 + k) = Ib[k]; }
+  }
 }
 
 // Tiles of the lane classes are numbered class kLaneBinMax first; tile t of class b holds sorted islands
@@ -138,16 +134,12 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
     for (int gi = 0; gi < gn; gi++) {
       const int s = d.isl_groups[g0 + gi];
       const int rr[2] = {d.cur.slot_row1[s], d.cur.slot_row2[s]};
-      int lb[2]; M33 I[2];
+      int lb[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int br = rr[e];
         int m = 0;
-        I[e].m11 = I[e].m21 = I[e].m31 = I[e].m12 = I[e].m22 = I[e].m32 = I[e].m13 = I[e].m23 = I[e].m33 = 0;
         if (d.kind[br] == 2) {
-          const double* im = d.iiw + 9 * (size_t)br;
-          I[e].m11 = im[0]; I[e].m21 = im[1]; I[e].m31 = im[2]; I[e].m12 = im[3]; I[e].m22 = im[4]; I[e].m32 = im[5];
-          I[e].m13 = im[6]; I[e].m23 = im[7]; I[e].m33 = im[8];
           m = d.body_mark[br];
           if (m == 0) {
             m = nB++; d.body_mark[br] = m; T.body_row(m) = br;
@@ -165,7 +157,7 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
       const int j0 = d.cur.slot_jstart[s], jn = d.cur.slot_jcount[s];
       for (int k = 0; k < jn; k++, r++) {
         const JointRow& jr = d.jrows[j0 + k];
-        tile_write_jac(T, false, r, 0, jr.J, I[0], I[1]);
+        tile_write_jac(T, false, r, 0, jr.J, jr.Ia, jr.Ib);
         T.nrow(r, NR_B) = jr.B; T.nrow(r, NR_INVC) = jr.invC; T.nrow(r, NR_LAM) = jr.lam;
         T.desc1(r) = pair | DESC_JOINT | first; first = 0;
       }
@@ -178,30 +170,23 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
     }
     // contact rows, all lanes in lock step on the contact index so that every store of the warp covers whole 128 B lines
     // (a lane-by-lane copy in group order writes the same lines with partial masks: twice the DRAM traffic, measured)
-    int curPair = -1; M33 I1, I2;
     for (int cc = 0; cc < td.maxC; cc++) {
       if (cc >= nc) continue;
-      const int desc = T.desc2(cc), rowN = (desc >> 16) & 0xff, pr = desc & 0xffff;
-      if (pr != curPair) {
-        curPair = pr;
-        const int lb[2] = {pr & 0xff, pr >> 8};
+      const int rowN = (T.desc2(cc) >> 16) & 0xff;
+      // all 58 doubles of the row into registers first (29 independent 16 B loads in flight), then the transposed stores
+      const double2* sp = (const double2*)(d.cur.rows + T.contact_index(cc));
+      double2 v[29];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          M33 I; I.m11 = I.m21 = I.m31 = I.m12 = I.m22 = I.m32 = I.m13 = I.m23 = I.m33 = 0;
-          if (lb[e] > 0) {
-            const double* im = d.iiw + 9 * (size_t)T.body_row(lb[e]);
-            I.m11 = im[0]; I.m21 = im[1]; I.m31 = im[2]; I.m12 = im[3]; I.m22 = im[4]; I.m32 = im[5]; I.m13 = im[6]; I.m23 = im[7]; I.m33 = im[8];
-          }
-          if (e == 0) I1 = I; else I2 = I;
-        }
-      }
-      const RowRec& src = d.cur.rows[T.contact_index(cc)];
-      tile_write_jac(T, false, rowN, 0, src.nJ, I1, I2);
-      T.nrow(rowN, NR_B) = src.nB; T.nrow(rowN, NR_INVC) = src.nInvC; T.nrow(rowN, NR_LAM) = src.lamN;
-      tile_write_jac(T, true, cc, FR_E1, src.f1J, I1, I2);
-      tile_write_jac(T, true, cc, FR_E2, src.f2J, I1, I2);
-      T.frow(cc, FR_F1B) = src.f1B; T.frow(cc, FR_F1INVC) = src.f1InvC; T.frow(cc, FR_F2B) = src.f2B; T.frow(cc, FR_F2INVC) = src.f2InvC;
-      T.frow(cc, FR_MU) = src.mu; T.frow(cc, FR_L1) = src.lamF1; T.frow(cc, FR_L2) = src.lamF2;
+      for (int f = 0; f < 29; f++) v[f] = sp[f];
+      const double* src = (const double*)v;       // RowRec field offsets in doubles: nJ 0, nB 9, nInvC 10, lamN 11, f1J 12, f2J 21,
+                                                  // f1B 30, f1InvC 31, f2B 32, f2InvC 33, mu 34, lamF1 35, lamF2 36, d* 37-39, nIa 40, nIb 43,
+                                                  // f1Ia 46, f1Ib 49, f2Ia 52, f2Ib 55
+      tile_write_jac(T, false, rowN, 0, src + 0, src + 40, src + 43);
+      T.nrow(rowN, NR_B) = src[9]; T.nrow(rowN, NR_INVC) = src[10]; T.nrow(rowN, NR_LAM) = src[11];
+      tile_write_jac(T, true, cc, FR_E1, src + 12, src + 46, src + 49);
+      tile_write_jac(T, true, cc, FR_E2, src + 21, src + 52, src + 55);
+      T.frow(cc, FR_F1B) = src[30]; T.frow(cc, FR_F1INVC) = src[31]; T.frow(cc, FR_F2B) = src[32]; T.frow(cc, FR_F2INVC) = src[33];
+      T.frow(cc, FR_MU) = src[34]; T.frow(cc, FR_L1) = src[35]; T.frow(cc, FR_L2) = src[36];
     }
   }
 }
@@ -438,56 +423,123 @@ __global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int
 // sum|dlambda| decides the early exit (Solver.elm:360-367).  All terms are >= 0, so ANY summation order is within
 // (rows+2)*2^-53 relative of the reference's left-to-right sum; the team reduces in parallel and only when that sum lands
 // within 1e-9 relative of the tolerance does thread 0 redo it in the reference's association from the per-row |dlambda|.
-template <int T>
+// Data: the solver-body deltas and inverse masses of the island's world sit in shared memory (SMEMB; else in place in
+// global memory), the level walk runs on shared-memory copies of the groups' body pairs, every group's record
+// (bodies, row ranges) is laid out in schedule order, and a group's rows are read one row ahead of their use.
+struct TeamRec { int b1, b2, c0, cn, j0, jn, pad0, pad1; };      // world-local dynamic body index or -1; contact / joint row ranges
+
+template <int T, bool SMEMB>
 __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi) {
-  __shared__ int s_nlev, s_decide;
+  constexpr int CH = 8 * T;                 // groups per pass of the level walk
+  extern __shared__ __align__(16) unsigned char team_smem[];
+  __shared__ int s_nlev, s_decide, s_lev0;
   __shared__ double s_part[T / 32];
   const int tid = threadIdx.x;
+  int* s_a = (int*)team_smem; int* s_b = s_a + CH; int* s_lv = s_b + CH;         // chunk of the level walk
+  int* s_last = s_lv + CH;                                                        // [nb_max]
+  double* s_im = (double*)(s_last + ((d.nb_max + 1) & ~1));                       // [nb_max]
+  double* s_sb = s_im + d.nb_max;                                                 // [nb_max][6]
   int total = 0;
   for (int b = bin_lo; b <= bin_hi; b++) total += d.cur.counters[CNT_BIN0 + b];
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int isl = island_from_worklist(d, item, bin_lo, bin_hi);
     const int g0 = d.isl_off[isl], gn = d.isl_cnt[isl], w = d.isl_world[isl];
-    const int r0 = d.world_body_off[w];
-    int* last = d.uf_fill + r0;            // per-body scratch; islands of a world own disjoint dynamic bodies
+    const int r0 = d.world_body_off[w], nbw = d.world_body_off[w + 1] - r0;
+    int* last = SMEMB ? s_last : d.uf_fill + r0;
     int* lvl = d.sched_lvl + g0; int* sched = d.sched + g0; int* loff = d.lvl_off + g0; int* lcur = d.lvl_cur + g0;
-    for (int gi = tid; gi < gn; gi += T) {
-      int s = d.isl_groups[g0 + gi];
-      int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-      if (d.kind[r1] == 2) last[r1 - r0] = 0;
-      if (d.kind[r2] == 2) last[r2 - r0] = 0;
-      loff[gi] = 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int nlev = 0;
-      for (int gi = 0; gi < gn; gi++) {
-        int s = d.isl_groups[g0 + gi];
-        int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-        bool d1 = d.kind[r1] == 2, d2 = d.kind[r2] == 2;
-        int l = 0;
-        if (d1) l = last[r1 - r0];
-        if (d2) l = max(l, last[r2 - r0]);
-        lvl[gi] = l;
-        l++;
-        if (d1) last[r1 - r0] = l;
-        if (d2) last[r2 - r0] = l;
-        nlev = max(nlev, l);
+    TeamRec* recs = (TeamRec*)d.sched_rec + g0;
+    auto sbp = [&](int l) -> double* { return SMEMB ? s_sb + 6 * l : d.sbv + 6 * (size_t)(r0 + l); };
+    auto imass = [&](int l) -> double { return SMEMB ? s_im[l] : d.inv_mass[r0 + l]; };
+    if (SMEMB) {
+      // the whole world's bodies are copied (entries of other islands are never used nor written back)
+      for (int l = tid; l < nbw; l += T) {
+        last[l] = 0;
+        s_im[l] = d.inv_mass[r0 + l];
+        const double* sb = d.sbv + 6 * (size_t)(r0 + l);
+#pragma unroll
+        for (int k = 0; k < 6; k++) s_sb[6 * l + k] = sb[k];
       }
-      s_nlev = nlev;
     }
+    for (int gi = tid; gi < gn; gi += T) {
+      loff[gi] = 0;
+      if (!SMEMB) {      // global scratch is shared with the other islands of the world: touch this island's bodies only
+        const int s = d.isl_groups[g0 + gi];
+        const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+        if (d.kind[r1] == 2) last[r1 - r0] = 0;
+        if (d.kind[r2] == 2) last[r2 - r0] = 0;
+      }
+    }
+    if (tid == 0) s_nlev = 0;
     __syncthreads();
+    // dependency levels: a serial walk in enumeration order, on shared-memory copies of the body pairs, CH groups per pass
+    for (int base = 0; base < gn; base += CH) {
+      const int m = min(CH, gn - base);
+      for (int i = tid; i < m; i += T) {
+        const int s = d.isl_groups[g0 + base + i];
+        const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+        s_a[i] = d.kind[r1] == 2 ? r1 - r0 : -1; s_b[i] = d.kind[r2] == 2 ? r2 - r0 : -1;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int nlev = s_nlev;
+        for (int i = 0; i < m; i++) {
+          const int a = s_a[i], b = s_b[i];
+          int l = 0;
+          if (a >= 0) l = last[a];
+          if (b >= 0) l = max(l, last[b]);
+          s_lv[i] = l;
+          l++;
+          if (a >= 0) last[a] = l;
+          if (b >= 0) last[b] = l;
+          nlev = max(nlev, l);
+        }
+        s_nlev = nlev;
+      }
+      __syncthreads();
+      for (int i = tid; i < m; i += T) { lvl[base + i] = s_lv[i]; atomicAdd(&loff[s_lv[i]], 1); }
+      __syncthreads();
+    }
     const int nlev = s_nlev;
-    for (int gi = tid; gi < gn; gi += T) atomicAdd(&loff[lvl[gi]], 1);
-    __syncthreads();
     if (tid == 0) { int run = 0; for (int l = 0; l < nlev; l++) { int c = loff[l]; loff[l] = run; lcur[l] = run; run += c; } }
     __syncthreads();
-    for (int gi = tid; gi < gn; gi += T) sched[atomicAdd(&lcur[lvl[gi]], 1)] = d.isl_groups[g0 + gi];
+    for (int gi = tid; gi < gn; gi += T) {
+      const int s = d.isl_groups[g0 + gi];
+      const int at = atomicAdd(&lcur[lvl[gi]], 1);
+      sched[at] = s;
+      const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+      TeamRec rc;
+      rc.b1 = d.kind[r1] == 2 ? r1 - r0 : -1; rc.b2 = d.kind[r2] == 2 ? r2 - r0 : -1;
+      rc.c0 = d.cur.slot_cstart[s]; rc.cn = max(d.cur.slot_ccount[s], 0); rc.j0 = d.cur.slot_jstart[s]; rc.jn = max(d.cur.slot_jcount[s], 0);
+      rc.pad0 = 0; rc.pad1 = 0;
+      recs[at] = rc;
+    }
     __syncthreads();
-    // warm start, levels descending
+    // one pair group of a level: load its bodies, run `rows`, store the dynamic bodies back
+    auto load_pair = [&](const TeamRec& rc, Pair& P) {
+      P.b1 = rc.b1; P.b2 = rc.b2;
+      if (rc.b1 >= 0) { const double* p = sbp(rc.b1); P.im1 = imass(rc.b1); P.s1.vX = p[0]; P.s1.vY = p[1]; P.s1.vZ = p[2]; P.s1.wX = p[3]; P.s1.wY = p[4]; P.s1.wZ = p[5]; }
+      else { P.im1 = 0; P.s1.vX = P.s1.vY = P.s1.vZ = P.s1.wX = P.s1.wY = P.s1.wZ = 0; }
+      if (rc.b2 >= 0) { const double* p = sbp(rc.b2); P.im2 = imass(rc.b2); P.s2.vX = p[0]; P.s2.vY = p[1]; P.s2.vZ = p[2]; P.s2.wX = p[3]; P.s2.wY = p[4]; P.s2.wZ = p[5]; }
+      else { P.im2 = 0; P.s2.vX = P.s2.vY = P.s2.vZ = P.s2.wX = P.s2.wY = P.s2.wZ = 0; }
+    };
+    auto store_pair = [&](const Pair& P) {
+      if (P.b1 >= 0) { double* p = sbp(P.b1); p[0] = P.s1.vX; p[1] = P.s1.vY; p[2] = P.s1.vZ; p[3] = P.s1.wX; p[4] = P.s1.wY; p[5] = P.s1.wZ; }
+      if (P.b2 >= 0) { double* p = sbp(P.b2); p[0] = P.s2.vX; p[1] = P.s2.vY; p[2] = P.s2.vZ; p[3] = P.s2.wX; p[4] = P.s2.wY; p[5] = P.s2.wZ; }
+    };
+    // warm start (applyContactsWarmStart, Solver.elm:102-119), levels descending
     for (int l = nlev - 1; l >= 0; l--) {
       const int b = loff[l], e = (l + 1 < nlev) ? loff[l + 1] : gn;
-      for (int i = b + tid; i < e; i += T) warm_group(d, sched[i]);
+      for (int i = b + tid; i < e; i += T) {
+        const TeamRec rc = recs[i];
+        if (rc.cn <= 0) continue;
+        Pair P; load_pair(rc, P);
+        for (int k = 0; k < rc.cn; k++) {
+          const RowRec& r = d.cur.rows[rc.c0 + k];
+          if (r.lamN == 0) continue;                      // Solver.elm:41
+          apply_pre(r.lamN, r.nJ, r.nIa, r.nIb, P);
+        }
+        store_pair(P);
+      }
       __syncthreads();
     }
     const int iterations = d.iterations[w];
@@ -495,14 +547,78 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi)
     const double eps = spook(d.dt[w]).eps;
     for (;;) {
       double part = 0;
+      // sweep 1: joint rows (Solver.elm:572-619), then contact normals (625-672) of every group, level by level
       for (int l = 0; l < nlev; l++) {
         const int b = loff[l], e = (l + 1 < nlev) ? loff[l + 1] : gn;
-        for (int i = b + tid; i < e; i += T) part += sweep_nonfriction(d, sched[i], eps, 0.0);
+        for (int i = b + tid; i < e; i += T) {
+          const TeamRec rc = recs[i];
+          Pair P; load_pair(rc, P);
+          for (int k = 0; k < rc.jn; k++) {
+            JointRow& r = d.jrows[rc.j0 + k];
+            const double lam = r.lam;
+            const double prev = r.invC * (r.B - gw_lambda(r.J, P.s1, P.s2) - r.eps * lam);
+            const double dl = (lam + prev - (-kMaxImpulse) < 0) ? (-kMaxImpulse) - lam : ((lam + prev - kMaxImpulse > 0) ? kMaxImpulse - lam : prev);
+            apply_pre(dl, r.J, r.Ia, r.Ib, P);
+            r.lam = lam + dl; r.dl = eabs(dl);
+            part += eabs(dl);
+          }
+          if (rc.cn > 0) {
+            RowRec* rows = d.cur.rows + rc.c0;
+            double J[9], ia[3], ib[3], B, invC, lam;
+            auto ld = [&](const RowRec& r) {
+#pragma unroll
+              for (int q = 0; q < 9; q++) J[q] = r.nJ[q];
+#pragma unroll
+              for (int q = 0; q < 3; q++) { ia[q] = r.nIa[q]; ib[q] = r.nIb[q]; }
+              B = r.nB; invC = r.nInvC; lam = r.lamN;
+            };
+            ld(rows[0]);
+            for (int k = 0; k < rc.cn; k++) {
+              double cJ[9], cia[3], cib[3]; const double cB = B, cInvC = invC, cLam = lam;
+#pragma unroll
+              for (int q = 0; q < 9; q++) cJ[q] = J[q];
+#pragma unroll
+              for (int q = 0; q < 3; q++) { cia[q] = ia[q]; cib[q] = ib[q]; }
+              if (k + 1 < rc.cn) ld(rows[k + 1]);            // next row in flight while this one computes
+              const double prev = cInvC * (cB - gw_lambda(cJ, P.s1, P.s2) - eps * cLam);
+              const double dl = (cLam + prev - 0.0 < 0) ? 0.0 - cLam : ((cLam + prev - kMaxImpulse > 0) ? kMaxImpulse - cLam : prev);
+              apply_pre(dl, cJ, cia, cib, P);
+              rows[k].lamN = cLam + dl; rows[k].dN = eabs(dl);
+              part += eabs(dl);
+            }
+          }
+          store_pair(P);
+        }
         __syncthreads();
       }
+      // sweep 2: friction1 then friction2 of every contact (Solver.elm:678-844), level by level
       for (int l = 0; l < nlev; l++) {
         const int b = loff[l], e = (l + 1 < nlev) ? loff[l + 1] : gn;
-        for (int i = b + tid; i < e; i += T) part += sweep_friction(d, sched[i], eps, 0.0);
+        for (int i = b + tid; i < e; i += T) {
+          const TeamRec rc = recs[i];
+          if (rc.cn <= 0) continue;
+          Pair P; load_pair(rc, P);
+          RowRec* rows = d.cur.rows + rc.c0;
+          for (int k = 0; k < rc.cn; k++) {
+            RowRec& r = rows[k];
+            if (k + 1 < rc.cn) {        // next row towards L1 while this one computes (464 B = up to five 128 B lines)
+              const char* nx = (const char*)(rows + k + 1);
+#pragma unroll
+              for (int q = 0; q < 5; q++) asm volatile("prefetch.global.L1 [%0];" :: "l"(nx + (q < 4 ? 128 * q : 463)));
+            }
+            const double cap = r.mu * r.lamN;
+            const double l1 = r.lamF1, l2 = r.lamF2;
+            const double dPrev1 = r.f1InvC * (r.f1B - gw_lambda(r.f1J, P.s1, P.s2) - eps * l1);
+            const double d1 = (l1 + dPrev1 + cap < 0) ? -cap - l1 : ((l1 + dPrev1 - cap > 0) ? cap - l1 : dPrev1);
+            apply_pre(d1, r.f1J, r.f1Ia, r.f1Ib, P);
+            const double dPrev2 = r.f2InvC * (r.f2B - gw_lambda(r.f2J, P.s1, P.s2) - eps * l2);
+            const double d2 = (l2 + dPrev2 + cap < 0) ? -cap - l2 : ((l2 + dPrev2 - cap > 0) ? cap - l2 : dPrev2);
+            apply_pre(d2, r.f2J, r.f2Ia, r.f2Ib, P);
+            r.lamF1 = l1 + d1; r.lamF2 = l2 + d2; r.dF1 = eabs(d1); r.dF2 = eabs(d2);
+            part += eabs(d1) + eabs(d2);
+          }
+          store_pair(P);
+        }
         __syncthreads();
       }
       if (remaining == 1) { rem = 0; break; }
@@ -542,6 +658,18 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi)
       atomicMin(&d.world_min_rem[w], rem); d.body_iters[d.isl_root[isl]] = iterations - rem;
       atomicAdd(&d.work[0], (unsigned long long)d.isl_nc[isl] * (iterations - rem));
       if (d.isl_nj[isl]) atomicAdd(&d.work[1], (unsigned long long)d.isl_nj[isl] * (iterations - rem));
+    }
+    if (SMEMB) {     // the island's dynamic bodies back to the solver-body array (other islands of the world own other bodies)
+      for (int i = tid; i < gn; i += T) {
+        const TeamRec rc = recs[i];
+        for (int e2 = 0; e2 < 2; e2++) {
+          const int l = e2 ? rc.b2 : rc.b1;
+          if (l < 0) continue;
+          double* o = d.sbv + 6 * (size_t)(r0 + l);
+#pragma unroll
+          for (int k = 0; k < 6; k++) o[k] = s_sb[6 * l + k];
+        }
+      }
     }
     __syncthreads();
   }
