@@ -267,7 +267,13 @@ __device__ __forceinline__ void apply_pre(double dl, const double* J, const doub
 // flat row sequence: ALL 32 lanes of the warp run the same loops (to the largest row count / iteration count of the tile,
 // predicated off where a lane has fewer rows, has converged, or holds no island) and re-converge with __syncwarp after
 // every row, so changing the body pair is the only divergent section and it never outlives its row.
-template <bool PREFETCH, class TT>
+// the [first, first + bytes) block of the tile image towards L1, lines shared out over the lanes
+__device__ __forceinline__ void prefetch_block(const double* first, int bytes, int lane) {
+  const char* p = (const char*)first;
+  for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + o));
+}
+
+template <int PREFETCH, class TT>      // 0: rows read where they are used (staged tiles); 1: next row prefetched to L1 (rows in L2)
 __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   const bool have = isl >= 0;
   const int gn = have ? d.isl_cnt[isl] : 0, w = have ? d.isl_world[isl] : 0, C = have ? d.isl_nc[isl] : 0, R = have ? C + d.isl_nj[isl] : 0;
@@ -303,13 +309,12 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
     // sweep 1: velocityNonFrictionGroup (Solver.elm:850-864) group by group: joint rows (572-619), then contact normals (625-672)
     double p1 = 0;
     {
-      RowN nxt;
-      if (PREFETCH && !done && R > 0) load_row_n(T, 0, nxt);
+      if (PREFETCH) prefetch_block(T.rd, kNRowF64 * 32 * 8, T.lane);
       for (int r = 0; r < Rmax; r++) {
+        if (PREFETCH && r + 1 < Rmax) prefetch_block(T.rd + (size_t)(r + 1) * kNRowF64 * 32, kNRowF64 * 32 * 8, T.lane);
         if (!done && r < R) {
           RowN cur;
-          if (PREFETCH) { cur = nxt; if (r + 1 < R) load_row_n(T, r + 1, nxt); }
-          else load_row_n(T, r, cur);
+          load_row_n(T, r, cur);
           pair_enter(T, P, cur.desc);
           const double lo = (cur.desc & DESC_JOINT) ? -kMaxImpulse : 0.0;
           const double prev = cur.invC * (cur.B - gw_lambda(cur.J, P.s1, P.s2) - eps * cur.lam);
@@ -327,13 +332,13 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
     // keeps ONE running sum through both phases (Solver.elm:473-489), step adds two sums (345-358)
     double p2 = (gn == 1) ? p1 : 0;
     {
-      RowF nxt;
-      if (PREFETCH && !done && C > 0) load_row_f(T, 0, nxt);
+      const double* fbase = T.rd + (size_t)T.t.maxR * kNRowF64 * 32;
+      if (PREFETCH) prefetch_block(fbase, kFRowF64 * 32 * 8, T.lane);
       for (int c = 0; c < Cmax; c++) {
+        if (PREFETCH && c + 1 < Cmax) prefetch_block(fbase + (size_t)(c + 1) * kFRowF64 * 32, kFRowF64 * 32 * 8, T.lane);
         if (!done && c < C) {
           RowF cur;
-          if (PREFETCH) { cur = nxt; if (c + 1 < C) load_row_f(T, c + 1, nxt); }
-          else load_row_f(T, c, cur);
+          load_row_f(T, c, cur);
           pair_enter(T, P, cur.desc);
           const double cap = cur.mu * cur.nl;
           const double dPrev1 = cur.f1InvC * (cur.f1B - gw_lambda(cur.e1, P.s1, P.s2) - eps * cur.l1);
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int
       __syncwarp();
       T.bind(sm, MODE == 2 ? sm + head : img + head);
     }
-    solve_lane<MODE != 2>(d, T, lane < tr.count ? d.isl_sorted[tr.first + lane] : -1);
+    solve_lane<MODE == 1 ? 1 : 0>(d, T, lane < tr.count ? d.isl_sorted[tr.first + lane] : -1);
   }
 }
 
