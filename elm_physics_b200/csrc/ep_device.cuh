@@ -31,7 +31,7 @@ struct RowRec {
 // `ConstraintEquation` (src/Internal/Equation.elm:503-511); bounds are the constants -1e6 / 1e6.
 struct JointRow { double J[9]; double B, invC, eps, lam; double dl; double Ia[3], Ib[3]; double pad[4]; };   // 24 doubles; dl = |deltaLambda| of the last iteration
 
-constexpr int kIterKeys = 32, kGroupKeys = 4;
+constexpr int kIterKeys = 128, kGroupKeys = 4;     // (16 size sub-classes x 8 iteration classes) x 4 group-count classes per size class
 constexpr int kBins = 10;    // island size classes for the solver's work list (ep_solve.cuh)
 constexpr int kKeys = kBins * kIterKeys * kGroupKeys;
 constexpr int kClasses = 36; // narrowphase work-item classes: unordered pair of shape sub-kinds, lo * 6 + hi (ep_kernels.cuh)

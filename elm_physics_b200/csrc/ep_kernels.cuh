@@ -516,10 +516,15 @@ __device__ __forceinline__ int island_bin(int rows) {
   while (b < kBins - 1 && rows > (3 << b)) b++;
   return b;
 }
-__device__ __forceinline__ int island_key(int bin, int pred_iters, int groups) {
-  int it = min(max(pred_iters, 0), kIterKeys - 1);
-  int gk = groups <= 1 ? 0 : (groups == 2 ? 1 : (groups <= 4 ? 2 : 3));
-  return (bin * kIterKeys + it) * kGroupKeys + gk;
+// Sort key inside a size class, most significant first: row count (16 sub-classes of the class's range: the lanes of a tile
+// then run about the same number of rows), iterations the island used last frame (8 classes), group count (fewer body-pair
+// switches diverge).  Larger = runs longer = scheduled first.
+__device__ __forceinline__ int island_key(int bin, int rows, int pred_iters, int groups) {
+  const int lo = bin == 0 ? 0 : (3 << (bin - 1)), hi = 3 << bin;
+  const int sz = bin >= kBins - 1 ? 15 : min(15, max(0, (rows - lo - 1) * 16 / max(1, hi - lo)));
+  const int it = min(7, max(0, pred_iters) / 3);
+  const int gk = groups <= 1 ? 0 : (groups == 2 ? 1 : (groups <= 4 ? 2 : 3));
+  return ((bin * 16 + sz) * 8 + it) * kGroupKeys + gk;
 }
 // One CTA per world (one warp for small worlds).  Union-find with lock-free hooking: the root of a set is always its
 // member with the LOWEST body id (Islands.elm:39-46 "lower root wins"), so the final roots do not depend on the order of
@@ -650,8 +655,9 @@ __global__ void k_islands(Dev d, int use_smem) {
     for (int l = tid; l < n; l += nt) {
       if (parent[l] != l || count[l] <= 0) continue;
       const int isl = count[l] - 1;
-      const int bin = island_bin(3 * d.isl_nc[isl] + d.isl_nj[isl]);
-      const int key = island_key(bin, d.body_iters[r0 + l], d.isl_cnt[isl]);
+      const int rows = 3 * d.isl_nc[isl] + d.isl_nj[isl];
+      const int bin = island_bin(rows);
+      const int key = island_key(bin, rows, d.body_iters[r0 + l], d.isl_cnt[isl]);
       d.isl_key[isl] = key;
       atomicAdd(&d.key_cnt[key], 1);
       atomicAdd(&d.cur.counters[CNT_BIN0 + bin], 1);
