@@ -406,7 +406,9 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     int64_t icap = std::max<int64_t>(1 << 16, 8 * (int64_t)ni);
     if (ctx->opt[EP_OPT_ITEM_CAP] > 0) icap = std::max<int64_t>(ctx->opt[EP_OPT_ITEM_CAP], 64);
     d.item_cap = (int32_t)std::min<int64_t>(icap, (1ll << 27));   // item * kRawStride stays below 2^31
-    TRY(dev_alloc(ctx, pool, &d.items, (size_t)kClasses * d.item_cap));
+    TRY(dev_alloc(ctx, pool, &d.items, (size_t)d.item_cap + 32 * kClasses));
+    TRY(dev_alloc(ctx, pool, &d.cls_off, kClasses * 8)); TRY(dev_alloc(ctx, pool, &d.cls_cur, kClasses * 8));
+    TRY(dev_alloc(ctx, pool, &d.np_first, kClasses + 1)); TRY(dev_alloc(ctx, pool, &d.np_end, kClasses));
     TRY(dev_alloc(ctx, pool, &d.raw, (size_t)d.item_cap * kRawStride));
     TRY(dev_alloc(ctx, pool, &d.raw_cnt, d.item_cap));
   }
@@ -521,7 +523,10 @@ static void resolve_events(ep_ctx* ctx) {     // stream must be idle
     int32_t cnt[CNT_COUNT];
     cudaMemcpy(cnt, ctx->d.prev.counters, sizeof cnt, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[ep] narrowphase per class (lo*6+hi; 0 box 1 convex 2 plane 3 sphere 4 capsule 5 particle): total ms over the profiled steps, items in the last step\n");
-    for (int c = 0; c < kClasses; c++) if (ctx->np_ms[c] > 0.0005 * ctx->np_pending.size() / kClasses || cnt[CNT_CLASS0 + c]) fprintf(stderr, "[ep]   class %2d (%d,%d): %9.3f ms  %8d items\n", c, c / 6, c % 6, ctx->np_ms[c], cnt[CNT_CLASS0 + c]);
+    for (int c = 0; c < kClasses; c++) {
+      int n = 0; for (int b = 0; b < 8; b++) n += cnt[CNT_CLASS0 + c * 8 + b];
+      if (n) fprintf(stderr, "[ep]   class %2d (%d,%d): %9.3f ms  %8d items\n", c, c / 6, c % 6, ctx->np_ms[c], n);
+    }
     for (int c = 0; c < kClasses; c++) ctx->np_ms[c] = 0;
   }
   ctx->np_pending.clear();

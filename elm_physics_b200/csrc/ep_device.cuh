@@ -37,7 +37,7 @@ constexpr int kKeys = kBins * kIterKeys * kGroupKeys;
 constexpr int kClasses = 36; // narrowphase work-item classes: unordered pair of shape sub-kinds, lo * 6 + hi (ep_kernels.cuh)
 constexpr int kRawStride = 8;// raw contacts reserved per work item (plane-box emits up to 8)
 enum { CNT_CAND = 0, CNT_CONTACTS = 1, CNT_ISLANDS = 2, CNT_ISL_GROUPS = 3, CNT_JROWS = 4, CNT_GROUPS = 5, CNT_WORK = 6, CNT_ITEMS = 7,
-       CNT_BIN0 = 8, CNT_CLASS0 = CNT_BIN0 + kBins, CNT_COUNT = CNT_CLASS0 + kClasses };
+       CNT_BIN0 = 8, CNT_CLASS0 = CNT_BIN0 + kBins, CNT_COUNT = CNT_CLASS0 + kClasses * 8 /* x depth bins, ep_kernels.cuh */ };
 enum { FLAG_POOL_OVERFLOW = 0, FLAG_PAIR_OVERFLOW = 1, FLAG_POLY_OVERFLOW = 2, FLAG_JOINT_OVERFLOW = 3, FLAG_COUNT = 4 };
 
 // The last frame's contacts in the layout of ep_contacts, compacted on the device (ep_output.cuh)
@@ -112,7 +112,9 @@ struct Dev {
   int64_t slot_cap; int32_t contact_cap; int32_t jrow_cap;
   // narrowphase work items, binned by class so that the lanes of a warp run the same Collision.* module
   int32_t item_cap;
-  int4* items;                // [kClasses][item_cap] (slot, instance a, instance b, item id)
+  int4* items;                // [item_cap + 32 kClasses] (slot, instance a, instance b, item id), by class (32-aligned) and depth bin
+  int32_t *cls_off, *cls_cur; // [kClasses * 8] first item / fill cursor of every (class, depth bin)
+  int32_t *np_first, *np_end; // [kClasses + 1] / [kClasses] item range of every class in kClassOrder order
   struct RawContact* raw;     // [item_cap][kRawStride] contacts of each item, solver order
   int32_t* raw_cnt;           // [item_cap]
   // solver work list: islands sorted by (size class, predicted iterations, group count), largest / longest first, so that the

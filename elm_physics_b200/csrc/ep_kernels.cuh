@@ -97,6 +97,18 @@ __device__ __forceinline__ bool may_contact(const Dev& d, int w, int r0, int n, 
   return true;
 }
 
+// How deep the bounding spheres of a candidate pair overlap, 0 (just touching) .. kDepthBins-1: a proxy for the cost of its
+// narrowphase items (separated hulls leave the SAT at an early axis, interpenetrating ones run every axis and the
+// clipping).  Items are ordered by it inside a class so that the lanes of a warp do similar work.  Ordering only.
+constexpr int kDepthBins = 8;
+__device__ __forceinline__ int depth_bin(const Dev& d, int r1, int r2) {
+  double rr = d.radius[r1] + d.radius[r2];
+  double dx = d.pos[3 * r2] - d.pos[3 * r1], dy = d.pos[3 * r2 + 1] - d.pos[3 * r1 + 1], dz = d.pos[3 * r2 + 2] - d.pos[3 * r1 + 2];
+  double q = 1.0 - (dx * dx + dy * dy + dz * dz) / (rr * rr);
+  int b = (int)(q * kDepthBins);
+  return b < 0 ? 0 : (b > kDepthBins - 1 ? kDepthBins - 1 : b);
+}
+
 // Work-item classes: shape sub-kind = convex box 0, convex other 1, plane 2, sphere 3, capsule 4, particle 5;
 // class = lo * 6 + hi of the unordered pair, so every lane of a warp in k_narrowphase runs the same Collision.* module.
 __device__ __forceinline__ int shape_subkind(const Dev& d, int inst) {
@@ -115,7 +127,10 @@ __constant__ int kClassOrder[kClasses] = {7, 1, 10, 0, 4, 9, 8, 3, 2, 22, 28, 21
 constexpr int kBpChunk = 4096;
 __global__ void __launch_bounds__(128) k_bp_count(Dev d) {
   __shared__ int s_warp[4], s_warp2[4];
+  __shared__ int s_hist[kClasses * kDepthBins];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kClasses * kDepthBins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
   for (int c = blockIdx.x; c < d.n_chunks; c += gridDim.x) {
     const int w = d.chunk_world[c];
     const int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
@@ -126,7 +141,17 @@ __global__ void __launch_bounds__(128) k_bp_count(Dev d) {
       int r1 = d.sorted[r0 + i], r2 = d.sorted[r0 + j];
       bool may = may_contact(d, w, r0, n, r1, r2);
       cnt += (may || constraints_between(d, r1, r2) != 0) ? 1 : 0;
-      if (may) icnt += (d.inst_off[r1 + 1] - d.inst_off[r1]) * (d.inst_off[r2 + 1] - d.inst_off[r2]);
+      if (may) {
+        const int n1 = d.inst_off[r1 + 1] - d.inst_off[r1], n2 = d.inst_off[r2 + 1] - d.inst_off[r2];
+        icnt += n1 * n2;
+        const int db = depth_bin(d, r1, r2);
+        for (int a = 0; a < n1; a++)
+          for (int b = 0; b < n2; b++) {
+            const int ka = shape_subkind(d, d.inst_off[r1] + a), kb = shape_subkind(d, d.inst_off[r2] + b);
+            if ((ka == 2 && kb == 2) || (ka == 5 && kb == 5)) continue;          // NarrowPhase.elm:132-134, 235-237
+            atomicAdd(&s_hist[item_class(ka, kb) * kDepthBins + db], 1);
+          }
+      }
     }
     for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); icnt += __shfl_down_sync(0xffffffffu, icnt, o); }
     if (lane == 0) { s_warp[wid] = cnt; s_warp2[wid] = icnt; }
@@ -137,9 +162,27 @@ __global__ void __launch_bounds__(128) k_bp_count(Dev d) {
     }
     __syncthreads();
   }
+  for (int i = threadIdx.x; i < kClasses * kDepthBins; i += blockDim.x) if (s_hist[i]) atomicAdd(&d.cur.counters[CNT_CLASS0 + i], s_hist[i]);
 }
 __global__ void __launch_bounds__(128) k_bp_scan(Dev d) {
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // item array layout: classes in descending expected cost (kClassOrder), each starting at a multiple of 32 (warps are
+    // homogeneous in class), deepest overlaps first inside a class
+    int at = 0;
+    for (int ci = 0; ci < kClasses; ci++) {
+      const int cls = kClassOrder[ci];
+      d.np_first[ci] = at;
+      for (int db = kDepthBins - 1; db >= 0; db--) {
+        const int bin = cls * kDepthBins + db;
+        d.cls_off[bin] = at; d.cls_cur[bin] = 0;
+        at += d.cur.counters[CNT_CLASS0 + bin];
+      }
+      d.np_end[ci] = at;
+      at = (at + 31) & ~31;
+    }
+    d.np_first[kClasses] = at;
+  }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int w = warp; w < d.n_worlds; w += nwarps) {
     const int c0 = d.world_chunk_off[w], c1 = d.world_chunk_off[w + 1];
@@ -183,14 +226,14 @@ __global__ void __launch_bounds__(128) k_bp_emit(Dev d) {
     // ordered (enumeration order) ballot compaction of the slots; work items scattered into class bins
     for (int64_t p0 = pc0; p0 < pc1 && !dead; p0 += blockDim.x) {
       int64_t p = p0 + threadIdx.x;
-      bool flag = false; int r1 = 0, r2 = 0, ncon = 0, nit = 0, ns2 = 0; bool may = false;
+      bool flag = false; int r1 = 0, r2 = 0, ncon = 0, nit = 0, ns2 = 0, dbin = 0; bool may = false;
       if (p < pc1) {
         int i, j; pair_from_index(p, n, i, j);
         r1 = d.sorted[r0 + i]; r2 = d.sorted[r0 + j];
         may = may_contact(d, w, r0, n, r1, r2);
         ncon = constraints_between(d, r1, r2);
         flag = may || ncon != 0;
-        if (may) { ns2 = d.inst_off[r2 + 1] - d.inst_off[r2]; nit = (d.inst_off[r1 + 1] - d.inst_off[r1]) * ns2; }
+        if (may) { ns2 = d.inst_off[r2 + 1] - d.inst_off[r2]; nit = (d.inst_off[r1 + 1] - d.inst_off[r1]) * ns2; dbin = depth_bin(d, r1, r2); }
       }
       unsigned bal = __ballot_sync(0xffffffffu, flag);
       int iscan = nit;                                            // inclusive warp scan of the item counts
@@ -214,20 +257,20 @@ __global__ void __launch_bounds__(128) k_bp_emit(Dev d) {
       for (int o = 16; o > 0; o >>= 1) maxit = max(maxit, __shfl_xor_sync(0xffffffffu, maxit, o));
       for (int k = 0; k < maxit; k++) {
         bool act = k < nit;
-        int ia = 0, ib = 0, cls = kClasses;
+        int ia = 0, ib = 0, cls = kClasses * kDepthBins;
         if (act) {
           ia = d.inst_off[r1] + k / ns2; ib = d.inst_off[r2] + k % ns2;
           int ka = shape_subkind(d, ia), kb = shape_subkind(d, ib);
           if ((ka == 2 && kb == 2) || (ka == 5 && kb == 5)) { d.raw_cnt[item0 + k] = 0; act = false; }   // NarrowPhase.elm:132-134, 235-237
-          else cls = item_class(ka, kb);
+          else cls = item_class(ka, kb) * kDepthBins + dbin;
         }
         unsigned peers = __match_any_sync(0xffffffffu, cls);
         if (act) {
           int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
           int basec = 0;
-          if (lane == leader) basec = atomicAdd(&d.cur.counters[CNT_CLASS0 + cls], __popc(peers));
+          if (lane == leader) basec = d.cls_off[cls] + atomicAdd(&d.cls_cur[cls], __popc(peers));
           basec = __shfl_sync(peers, basec, leader);
-          d.items[(size_t)cls * d.item_cap + basec + rank] = make_int4(s, ia, ib, item0 + k);
+          d.items[basec + rank] = make_int4(s, ia, ib, item0 + k);
         }
       }
       running += total; irunning += itotal;
@@ -247,16 +290,15 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls) {
   TagPt pa[kMaxPoly], pb[kMaxPoly];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  int cls_i = 0, cls = kClassOrder[0], cnt = min(d.cur.counters[CNT_CLASS0 + cls], d.item_cap), first = 0;   // chunk range of the current class
-  for (int chunk = warp;; chunk += nwarps) {
-    while (cls_i < kClasses && chunk >= first + ((cnt + 31) >> 5)) {
-      first += (cnt + 31) >> 5; cls_i++;
-      if (cls_i < kClasses) { cls = kClassOrder[cls_i]; cnt = min(d.cur.counters[CNT_CLASS0 + cls], d.item_cap); }
-    }
-    if (cls_i >= kClasses) break;
-    int idx = (chunk - first) * 32 + lane;
-    if (idx >= cnt || (only_cls >= 0 && cls != only_cls)) continue;
-    int4 it = d.items[(size_t)cls * d.item_cap + idx];
+  if (d.flags[FLAG_PAIR_OVERFLOW]) return;      // a world's pairs / items did not fit: its items were counted but never emitted
+  int ci = 0;                     // position in kClassOrder of the class this warp's chunk belongs to
+  const int total = d.np_first[kClasses];
+  for (int chunk = warp; chunk * 32 < total; chunk += nwarps) {
+    while (ci + 1 < kClasses && chunk * 32 >= d.np_first[ci + 1]) ci++;
+    const int cls = kClassOrder[ci];
+    const int idx = chunk * 32 + lane;
+    if (idx >= d.np_end[ci] || (only_cls >= 0 && cls != only_cls)) continue;
+    int4 it = d.items[idx];
     ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
     bool polyOvf = false;
     shape_pair_contacts(shape_ref(d, it.y), shape_ref(d, it.z), sink, pa, pb, polyOvf);
