@@ -437,7 +437,7 @@ template <int T, bool SMEMB>
 __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi) {
   constexpr int CH = 8 * T;                 // groups per pass of the level walk
   extern __shared__ __align__(16) unsigned char team_smem[];
-  __shared__ int s_nlev, s_decide, s_lev0;
+  __shared__ int s_nlev, s_decide;
   __shared__ double s_part[T / 32];
   const int tid = threadIdx.x;
   int* s_a = (int*)team_smem; int* s_b = s_a + CH; int* s_lv = s_b + CH;         // chunk of the level walk
