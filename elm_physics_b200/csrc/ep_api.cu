@@ -15,6 +15,7 @@
 #include "ep_kernels.cuh"
 #include "ep_solve.cuh"
 #include "ep_output.cuh"
+#include "ep_raycast.cuh"
 
 namespace ep {
 __global__ void k_export_lambda(const RowRec* rows, int n, double* lam, double* t1) {
@@ -61,6 +62,8 @@ struct ep_ctx {
   double k_ms[EP_K_COUNT] = {0};
   int64_t k_launches[EP_K_COUNT] = {0};
   int64_t stats[EP_STAT_COUNT] = {0};
+  // ep_raycast scratch (device), grown on demand
+  void* ray_buf = nullptr; size_t ray_cap = 0;
 };
 
 #define CK(call)                                                                                         \
@@ -154,6 +157,7 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_pool(ctx->world_allocs);
   free_pool(ctx->shape_allocs);
+  if (ctx->ray_buf) cudaFree(ctx->ray_buf);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < ep_ctx::kAux; i++) { if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -771,6 +775,45 @@ extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, 
   TRY(ep_step_resident(ctx, n_steps));
   TRY(ep_download_bodies(ctx, bodies));
   if (out) TRY(ep_download_contacts(ctx, out));
+  return EP_OK;
+}
+
+extern "C" int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world, const double* from, const double* direction,
+                          int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal) {
+  if (!ctx || n_rays < 0 || (n_rays > 0 && (!ray_world || !from || !direction || !hit_body || !hit_distance || !hit_point || !hit_normal))) return EP_EINVAL;
+  if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
+  if (n_rays == 0) return EP_OK;
+  Dev& d = ctx->d;
+  for (int i = 0; i < n_rays; i++)
+    if (ray_world[i] < 0 || ray_world[i] >= d.n_worlds) { ctx->err = "ray_world out of range"; return EP_EINVAL; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)n_rays, bytes = n * (4 + 24 + 24 + 4 + 8 + 24 + 24) + 256;
+  if (bytes > ctx->ray_cap) {
+    CK(cudaStreamSynchronize(st));
+    if (ctx->ray_buf) cudaFree(ctx->ray_buf);
+    ctx->ray_buf = nullptr; ctx->ray_cap = 0;
+    CK(cudaMalloc(&ctx->ray_buf, bytes * 2));
+    ctx->ray_cap = bytes * 2;
+  }
+  // layout: doubles first (from, direction, distance, point, normal), then the two int arrays
+  double* d_from = (double*)ctx->ray_buf; double* d_dir = d_from + 3 * n; double* d_dist = d_dir + 3 * n;
+  double* d_point = d_dist + n; double* d_normal = d_point + 3 * n;
+  int* d_world = (int*)(d_normal + 3 * n); int* d_hit = d_world + n;
+  CK(cudaMemcpyAsync(d_from, from, 24 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_dir, direction, 24 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_world, ray_world, 4 * n, cudaMemcpyHostToDevice, st));
+  // worldShapesWithMaterials follow the bodies' CURRENT transforms (SolverBody.elm:212): the placed copies are refreshed
+  // at the start of a step, so refresh them here for the state the last step left
+  if (d.n_pl_all > 0) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
+  k_raycast<<<grid_for(ctx, n_rays, 128, 16), 128, 0, st>>>(d, n_rays, d_world, d_from, d_dir, d_hit, d_dist, d_point, d_normal);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hit_body, d_hit, 4 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hit_distance, d_dist, 8 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hit_point, d_point, 24 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hit_normal, d_normal, 24 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return EP_OK;
 }
 

@@ -17,7 +17,7 @@ _LIB = None
 EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
            "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream",
            "ep_profile", "ep_kernel_times", "ep_kernel_name", "ep_configure", "ep_step_frame", "ep_host_alloc",
-           "ep_host_free")
+           "ep_host_free", "ep_raycast")
 
 
 class EngineError(RuntimeError):
@@ -130,6 +130,20 @@ class Engine:
         """ep_step_frame: one frame of the resident batch through host buffers (state in, state + contacts out)."""
         self._ck(self.lib.ep_step_frame(self.ctx, C.byref(bodies.c), C.byref(out.c) if out is not None else None),
                  "ep_step_frame")
+
+    def raycast(self, ray_world, origins, directions):
+        """ep_raycast (Physics.raycast, src/Physics.elm:802-841) over the resident worlds.  Returns
+        (hit_body rows or -1, distance, point (n,3), normalised normal (n,3))."""
+        rw = np.ascontiguousarray(ray_world, dtype=np.int32)
+        o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
+        dr = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+        n = len(rw)
+        hit, dist, point, normal = np.zeros(n, np.int32), np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3))
+        pf, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._ck(self.lib.ep_raycast(self.ctx, C.c_int32(n), rw.ctypes.data_as(pi), o.ctypes.data_as(pf), dr.ctypes.data_as(pf),
+                                     hit.ctypes.data_as(pi), dist.ctypes.data_as(pf), point.ctypes.data_as(pf),
+                                     normal.ctypes.data_as(pf)), "ep_raycast")
+        return hit, dist, point, normal
 
     def stats(self):
         out = np.zeros(abi.EP_STAT_COUNT, np.int64)

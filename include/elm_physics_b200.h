@@ -207,6 +207,14 @@ int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_co
  * when it changes or when the warm start is not the previous frame. */
 int ep_step_frame(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out);
 
+/* `Physics.raycast` (src/Physics.elm:802-841) for a batch of rays against the RESIDENT worlds in their current state (after
+ * the last step / upload): ray r runs against the bodies of world ray_world[r] in list order; closest hit over every
+ * shape of every body (src/Internal/Body.elm:465-489, src/Internal/Shape.elm:132-148), first hit wins ties, point masses
+ * are never hit, planes only from their front side.  hit_body[r] = global body row (index into ep_bodies) or -1;
+ * hit_normal is normalised (Vec3.normalize).  Host buffers, synchronous. */
+int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world, const double* from /*[n][3]*/, const double* direction /*[n][3]*/,
+               int32_t* hit_body, double* hit_distance, double* hit_point /*[n][3]*/, double* hit_normal /*[n][3]*/);
+
 /* Page-locked host memory for the buffers of ep_bodies / ep_contacts (any host memory works; pinned buffers copy at
  * full PCIe rate and let the copies run asynchronously).  NULL when the allocation fails. */
 void* ep_host_alloc(size_t bytes);

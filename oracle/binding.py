@@ -74,3 +74,19 @@ def support_feature(shapes, s, t, axis):
     out = np.zeros(6)
     n = lib().ep_oracle_support_feature(C.byref(shapes.c), s, pp, pq, pa, out.ctypes.data_as(C.POINTER(C.c_double)))
     return [tuple(out[3 * i:3 * i + 3]) for i in range(n)]
+
+
+def raycast(shapes, bodies, ray_world, origins, directions):
+    """ep_oracle_raycast: Physics.raycast (src/Physics.elm:802-841) against the current state of `bodies`."""
+    rw = np.ascontiguousarray(ray_world, dtype=np.int32)
+    o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
+    dr = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+    n = len(rw)
+    hit, dist, point, normal = np.zeros(n, np.int32), np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3))
+    pf, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    rc = lib().ep_oracle_raycast(C.byref(shapes.c), C.byref(bodies.c), C.c_int32(n), rw.ctypes.data_as(pi), o.ctypes.data_as(pf),
+                                 dr.ctypes.data_as(pf), hit.ctypes.data_as(pi), dist.ctypes.data_as(pf),
+                                 point.ctypes.data_as(pf), normal.ctypes.data_as(pf))
+    if rc != 0:
+        raise RuntimeError(f"ep_oracle_raycast failed: {rc}")
+    return hit, dist, point, normal

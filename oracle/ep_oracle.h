@@ -26,6 +26,9 @@ int ep_oracle_support_feature(const ep_shapes* shapes, int shape, const double* 
                               double* out6);
 int ep_oracle_islands(int32_t n_groups, const int32_t* id1, const int32_t* kind1, const int32_t* id2, const int32_t* kind2,
                       int32_t max_id, int32_t* out_root, int32_t* out_order);
+/* Physics.raycast (src/Physics.elm:802-841) for a batch of rays against the CURRENT state of `bodies`; same contract as ep_raycast. */
+int ep_oracle_raycast(const ep_shapes* shapes, const ep_bodies* bodies, int32_t n_rays, const int32_t* ray_world, const double* from,
+                      const double* direction, int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal);
 #ifdef __cplusplus
 }
 #endif
