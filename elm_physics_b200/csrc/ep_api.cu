@@ -817,6 +817,51 @@ extern "C" int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world,
   return EP_OK;
 }
 
+extern "C" int ep_apply(ep_ctx* ctx, int32_t n_ops, const int32_t* kind, const int32_t* body_row, const double* a, const double* b) {
+  if (!ctx || n_ops < 0 || (n_ops > 0 && (!kind || !body_row || !a || !b))) return EP_EINVAL;
+  if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
+  if (n_ops == 0) return EP_OK;
+  Dev& d = ctx->d;
+  for (int k = 0; k < n_ops; k++)
+    if (body_row[k] < 0 || body_row[k] >= d.n_bodies || kind[k] < 0 || kind[k] > 5) { ctx->err = "ep_apply: body row or kind out of range"; return EP_EINVAL; }
+  // stable sort by body: operations on one body keep their list order and form one run
+  std::vector<int> order(n_ops);
+  for (int k = 0; k < n_ops; k++) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return body_row[x] < body_row[y]; });
+  std::vector<int32_t> h_kind(n_ops), h_row(n_ops), run_off;
+  std::vector<double> h_a(3 * (size_t)n_ops), h_b(3 * (size_t)n_ops);
+  for (int k = 0; k < n_ops; k++) {
+    const int s = order[k];
+    h_kind[k] = kind[s]; h_row[k] = body_row[s];
+    for (int q = 0; q < 3; q++) { h_a[3 * (size_t)k + q] = a[3 * (size_t)s + q]; h_b[3 * (size_t)k + q] = b[3 * (size_t)s + q]; }
+    if (k == 0 || h_row[k] != h_row[k - 1]) run_off.push_back(k);
+  }
+  const int n_runs = (int)run_off.size();
+  run_off.push_back(n_ops);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)n_ops, bytes = n * (24 + 24 + 4 + 4) + (size_t)(n_runs + 1) * 4 + 256;
+  if (bytes > ctx->ray_cap) {
+    CK(cudaStreamSynchronize(st));
+    if (ctx->ray_buf) cudaFree(ctx->ray_buf);
+    ctx->ray_buf = nullptr; ctx->ray_cap = 0;
+    CK(cudaMalloc(&ctx->ray_buf, bytes * 2));
+    ctx->ray_cap = bytes * 2;
+  }
+  double* d_a = (double*)ctx->ray_buf; double* d_b = d_a + 3 * n;
+  int* d_kind = (int*)(d_b + 3 * n); int* d_row = d_kind + n; int* d_run = d_row + n;
+  CK(cudaMemcpyAsync(d_a, h_a.data(), 24 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_b, h_b.data(), 24 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_kind, h_kind.data(), 4 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_row, h_row.data(), 4 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_run, run_off.data(), 4 * (size_t)(n_runs + 1), cudaMemcpyHostToDevice, st));
+  k_apply<<<grid_for(ctx, n_runs, 128, 16), 128, 0, st>>>(d, n_runs, d_run, d_kind, d_row, d_a, d_b);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));     // the host vectors go out of scope
+  return EP_OK;
+}
+
 extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
   if (!ctx || !out) return EP_EINVAL;
   ctx->stats[EP_STAT_KERNEL_LAUNCHES] = ctx->launches;

@@ -140,4 +140,34 @@ __global__ void __launch_bounds__(128) k_raycast(Dev d, int n_rays, const int* r
   }
 }
 
+// ---- between-step body mutators (src/Internal/Body.elm:305-430 behind src/Physics.elm:857-1017) ---------------------
+// ops are sorted by body (stable) on the host; one thread per body runs its operations in list order
+__global__ void __launch_bounds__(128) k_apply(Dev d, int n_runs, const int* run_off, const int* kind, const int* body_row, const double* a, const double* b) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_runs; t += gridDim.x * blockDim.x) {
+    const int r = body_row[run_off[t]];
+    const int bk = d.kind[r];
+    V3 v = ld3(d.vel + 3 * (size_t)r), w = ld3(d.angvel + 3 * (size_t)r), f = ld3(d.force + 3 * (size_t)r), tq = ld3(d.torque + 3 * (size_t)r);
+    const V3 x = ld3(d.pos + 3 * (size_t)r);
+    const double im = d.inv_mass[r];
+    const double* m = d.iiw + 9 * (size_t)r;      // m11,m21,m31,m12,m22,m32,m13,m23,m33
+    for (int k = run_off[t]; k < run_off[t + 1]; k++) {
+      const V3 va = ld3(a + 3 * (size_t)k), vb = ld3(b + 3 * (size_t)k);
+      switch (kind[k]) {
+        case 0: if (bk == 2) { V3 rp = vsub(vb, x); V3 t2 = vcross(rp, va); f = vadd(f, va); tq = vadd(tq, t2); } break;
+        case 1: if (bk == 2) {
+          V3 rp = vsub(vb, x); V3 c = vcross(rp, va);
+          v = mk(v.x + im * va.x, v.y + im * va.y, v.z + im * va.z);
+          w = mk(w.x + m[0] * c.x + m[3] * c.y + m[6] * c.z, w.y + m[1] * c.x + m[4] * c.y + m[7] * c.z, w.z + m[2] * c.x + m[5] * c.y + m[8] * c.z);
+        } break;
+        case 2: if (bk == 2) tq = vadd(tq, va); break;
+        case 3: if (bk == 2) w = mk(w.x + m[0] * va.x + m[3] * va.y + m[6] * va.z, w.y + m[1] * va.x + m[4] * va.y + m[7] * va.z, w.z + m[2] * va.x + m[5] * va.y + m[8] * va.z); break;
+        case 4: if (bk != 1) v = va; break;
+        case 5: if (bk != 1) w = va; break;
+        default: break;
+      }
+    }
+    st3(d.vel + 3 * (size_t)r, v); st3(d.angvel + 3 * (size_t)r, w); st3(d.force + 3 * (size_t)r, f); st3(d.torque + 3 * (size_t)r, tq);
+  }
+}
+
 }  // namespace ep

@@ -17,7 +17,7 @@ _LIB = None
 EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
            "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream",
            "ep_profile", "ep_kernel_times", "ep_kernel_name", "ep_configure", "ep_step_frame", "ep_host_alloc",
-           "ep_host_free", "ep_raycast")
+           "ep_host_free", "ep_raycast", "ep_apply")
 
 
 class EngineError(RuntimeError):
@@ -144,6 +144,16 @@ class Engine:
                                      hit.ctypes.data_as(pi), dist.ctypes.data_as(pf), point.ctypes.data_as(pf),
                                      normal.ctypes.data_as(pf)), "ep_raycast")
         return hit, dist, point, normal
+
+    def apply(self, kind, body_row, a, b):
+        """ep_apply: body mutators on the resident state (src/Physics.elm:857-1017), operations in list order."""
+        k = np.ascontiguousarray(kind, dtype=np.int32)
+        r = np.ascontiguousarray(body_row, dtype=np.int32)
+        va = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 3)
+        vb = np.ascontiguousarray(b, dtype=np.float64).reshape(-1, 3)
+        pf, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._ck(self.lib.ep_apply(self.ctx, C.c_int32(len(k)), k.ctypes.data_as(pi), r.ctypes.data_as(pi),
+                                   va.ctypes.data_as(pf), vb.ctypes.data_as(pf)), "ep_apply")
 
     def stats(self):
         out = np.zeros(abi.EP_STAT_COUNT, np.int64)

@@ -215,6 +215,16 @@ int ep_step_frame(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out);
 int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world, const double* from /*[n][3]*/, const double* direction /*[n][3]*/,
                int32_t* hit_body, double* hit_distance, double* hit_point /*[n][3]*/, double* hit_normal /*[n][3]*/);
 
+/* Between-step body mutators on the RESIDENT state, so that a multi-step batch can push bodies without a host round trip
+ * (src/Physics.elm:857-1017 over src/Internal/Body.elm:305-430).  Operation k acts on global body row body_row[k]; operations
+ * on the same body are applied in list order.  a / b per kind:
+ *   EP_APPLY_FORCE (force a at world point b), EP_APPLY_IMPULSE (impulse a at world point b), EP_APPLY_TORQUE (a),
+ *   EP_APPLY_ANGULAR_IMPULSE (a): dynamic bodies only, others unchanged;
+ *   EP_SET_VELOCITY (a), EP_SET_ANGULAR_VELOCITY (a): every body that is not static. */
+enum { EP_APPLY_FORCE = 0, EP_APPLY_IMPULSE = 1, EP_APPLY_TORQUE = 2, EP_APPLY_ANGULAR_IMPULSE = 3, EP_SET_VELOCITY = 4,
+       EP_SET_ANGULAR_VELOCITY = 5 };
+int ep_apply(ep_ctx* ctx, int32_t n_ops, const int32_t* kind, const int32_t* body_row, const double* a /*[n][3]*/, const double* b /*[n][3]*/);
+
 /* Page-locked host memory for the buffers of ep_bodies / ep_contacts (any host memory works; pinned buffers copy at
  * full PCIe rate and let the copies run asynchronously).  NULL when the allocation fails. */
 void* ep_host_alloc(size_t bytes);

@@ -90,3 +90,13 @@ def raycast(shapes, bodies, ray_world, origins, directions):
     if rc != 0:
         raise RuntimeError(f"ep_oracle_raycast failed: {rc}")
     return hit, dist, point, normal
+
+
+def apply(bodies, kind, body_row, a, b):
+    """ep_oracle_apply: body mutators (src/Physics.elm:857-1017) on the host arrays of `bodies`, in list order."""
+    k = np.ascontiguousarray(kind, dtype=np.int32); r = np.ascontiguousarray(body_row, dtype=np.int32)
+    va = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 3); vb = np.ascontiguousarray(b, dtype=np.float64).reshape(-1, 3)
+    pf, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    rc = lib().ep_oracle_apply(C.byref(bodies.c), C.c_int32(len(k)), k.ctypes.data_as(pi), r.ctypes.data_as(pi), va.ctypes.data_as(pf), vb.ctypes.data_as(pf))
+    if rc != 0:
+        raise RuntimeError(f"ep_oracle_apply failed: {rc}")

@@ -29,6 +29,8 @@ int ep_oracle_islands(int32_t n_groups, const int32_t* id1, const int32_t* kind1
 /* Physics.raycast (src/Physics.elm:802-841) for a batch of rays against the CURRENT state of `bodies`; same contract as ep_raycast. */
 int ep_oracle_raycast(const ep_shapes* shapes, const ep_bodies* bodies, int32_t n_rays, const int32_t* ray_world, const double* from,
                       const double* direction, int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal);
+/* Body mutators on host buffers, in list order; same contract as ep_apply. */
+int ep_oracle_apply(ep_bodies* bodies, int32_t n_ops, const int32_t* kind, const int32_t* body_row, const double* a, const double* b);
 #ifdef __cplusplus
 }
 #endif

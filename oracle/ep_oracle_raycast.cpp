@@ -159,3 +159,47 @@ extern "C" int ep_oracle_raycast(const ep_shapes* S, const ep_bodies* B, int32_t
   }
   return EP_OK;
 }
+
+// Between-step body mutators (src/Physics.elm:857-1017 over src/Internal/Body.elm:305-430), operations applied in list order.
+extern "C" int ep_oracle_apply(ep_bodies* B, int32_t n_ops, const int32_t* kind, const int32_t* body_row, const double* a, const double* b) {
+  for (int k = 0; k < n_ops; k++) {
+    int r = body_row[k];
+    if (r < 0 || r >= B->n_bodies) return EP_EINVAL;
+    int bk = B->kind[r];
+    V3 va = rd3(a + 3 * k), vb = rd3(b + 3 * k);
+    double* v = B->vel + 3 * r; double* w = B->angvel + 3 * r; double* f = B->force + 3 * r; double* tq = B->torque + 3 * r;
+    const double* m = B->inv_inertia_world + 9 * r;      // m11,m21,m31,m12,m22,m32,m13,m23,m33
+    V3 x = rd3(B->pos + 3 * r);
+    double im = B->inv_mass[r];
+    switch (kind[k]) {
+      case EP_APPLY_FORCE:            // Body.elm:341-368, dynamic only (Physics.elm:866-878)
+        if (bk == 2) { V3 t = cross(sub(vb, x), va); f[0] = f[0] + va.x; f[1] = f[1] + va.y; f[2] = f[2] + va.z; tq[0] = tq[0] + t.x; tq[1] = tq[1] + t.y; tq[2] = tq[2] + t.z; }
+        break;
+      case EP_APPLY_IMPULSE:          // Body.elm:305-338
+        if (bk == 2) {
+          V3 c = cross(sub(vb, x), va);
+          v[0] = v[0] + im * va.x; v[1] = v[1] + im * va.y; v[2] = v[2] + im * va.z;
+          double wx = w[0] + m[0] * c.x + m[3] * c.y + m[6] * c.z, wy = w[1] + m[1] * c.x + m[4] * c.y + m[7] * c.z, wz = w[2] + m[2] * c.x + m[5] * c.y + m[8] * c.z;
+          w[0] = wx; w[1] = wy; w[2] = wz;
+        }
+        break;
+      case EP_APPLY_TORQUE:           // Body.elm:371-391
+        if (bk == 2) { tq[0] = tq[0] + va.x; tq[1] = tq[1] + va.y; tq[2] = tq[2] + va.z; }
+        break;
+      case EP_APPLY_ANGULAR_IMPULSE:  // Body.elm:394-430
+        if (bk == 2) {
+          double wx = w[0] + m[0] * va.x + m[3] * va.y + m[6] * va.z, wy = w[1] + m[1] * va.x + m[4] * va.y + m[7] * va.z, wz = w[2] + m[2] * va.x + m[5] * va.y + m[8] * va.z;
+          w[0] = wx; w[1] = wy; w[2] = wz;
+        }
+        break;
+      case EP_SET_VELOCITY:           // Physics.elm:958-983: no effect on static bodies
+        if (bk != 1) { v[0] = va.x; v[1] = va.y; v[2] = va.z; }
+        break;
+      case EP_SET_ANGULAR_VELOCITY:   // Physics.elm:989-1014
+        if (bk != 1) { w[0] = va.x; w[1] = va.y; w[2] = va.z; }
+        break;
+      default: return EP_EINVAL;
+    }
+  }
+  return EP_OK;
+}
