@@ -46,8 +46,8 @@ def kernel_bytes(name, c):
         # per candidate: 2 placed shape blocks read; per contact: ContactRec written (104 B)
         "k_narrowphase": P * 2 * 8 * c["placed_f64_per_body"] + K * 104,
         # per group: 2 bodies x 41 doubles; per contact: raw contact read (88) + warm-start read (56) + ContactRec (104) and
-        # RowRec (320) written
-        "k_equations": G * 2 * 328 + K * (88 + 56 + 104 + 320),
+        # RowRec (464: the three rows + their I.w products) written
+        "k_equations": G * 2 * 328 + K * (88 + 56 + 104 + 464),
         # per candidate slot: rows/kinds/counts (20 B) read, root written (4), island list (4)
         "k_islands": P * 28 + nb * 12,
         # per contact: image rows read once (440 B) + 3 lambdas written (24 B); per dynamic body: image body read (64 B),
@@ -55,9 +55,9 @@ def kernel_bytes(name, c):
         "k_solve": K * 464 + nd * 112,
         # 512 B per body-step (336 read + 176 written)
         "k_integrate": nb * 512,
-        # tile images: RowRec read once (296 B), lane-transposed rows written (55 doubles = 440 B) per contact; per dynamic
-        # body: inverse mass + inverse inertia + deltas read (128 B), 64 B written
-        "k_tile_build": K * 736 + nd * 192,
+        # tile images: RowRec read once (464 B), lane-transposed rows written (55 doubles = 440 B) per contact; per dynamic
+        # body: inverse mass + deltas read (56 B), 64 B written
+        "k_tile_build": K * 904 + nd * 120,
     }
     return table[name]
 

@@ -6,7 +6,7 @@
 # team<256> team<32> lanes<1> x3 lanes<2> x3 lanes<0> integrate) + 1 k_place at upload; 120 pre-roll + 3 warm-up steps.
 set -u
 CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1"
-SKIP=$((1 + 123 * 20))
+SKIP=$((1 + 4 + 123 * 20))   # + the four k_out_* launches of the snapshot download
 $CMD > gpurun_out/prof_plain.json 2> gpurun_out/prof_plain.err || { echo "plain run failed"; tail -5 gpurun_out/prof_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c 100 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -s $SKIP -c 20 -o gpurun_out/prof_step $CMD > gpurun_out/ncu_full.log 2>&1
