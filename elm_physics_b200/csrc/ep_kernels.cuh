@@ -414,22 +414,45 @@ __device__ void rot_row(JointRow& r, double dt, V3 gravity, const Spook& sp, con
 __device__ __forceinline__ int constraint_rows(int kind) { return kind == 0 ? 3 : (kind == 1 ? 5 : (kind == 2 ? 6 : 1)); }
 
 // contactEquations (Equation.elm:364-450) for one contact; lam/ct1 = cached normal lambda and friction-1 direction
+// One row at a time, every field stored as soon as it is known (`r` is the record in global memory): the thread never holds
+// more than one 9-double Jacobian next to the two bodies.
 __device__ __forceinline__ void contact_row(RowRec& r, V3 ni, V3 pi, V3 pj, double bounciness, double friction, double lam, V3 ct1,
                                             double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2) {
   V3 ri = vsub(pi, b1.x), rj = vsub(pj, b2.x);
   V3 t1, t2; stable_tangents(ct1, ni, t1, t2);
-  contact_jac(ni, ri, rj, r.nJ); contact_jac(t1, ri, rj, r.f1J); contact_jac(t2, ri, rj, r.f2J);
-  r.nB = compute_contact_b(sp.a, sp.b, bounciness, pi, pj, ni, b1, b2, r.nJ) - (dt * compute_gimf(gravity, b1, b2, r.nJ));
-  r.nInvC = 1 / (compute_gimgt(b1, b2, r.nJ) + sp.eps);
-  r.f1B = (-compute_gw(b1, b2, r.f1J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f1J));
-  r.f1InvC = 1 / (compute_gimgt(b1, b2, r.f1J) + sp.eps);
-  r.f2B = (-compute_gw(b1, b2, r.f2J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, r.f2J));
-  r.f2InvC = 1 / (compute_gimgt(b1, b2, r.f2J) + sp.eps);
+  double J[9], ia[3], ib[3];
+  {
+    contact_jac(ni, ri, rj, J);
+    r.nB = compute_contact_b(sp.a, sp.b, bounciness, pi, pj, ni, b1, b2, J) - (dt * compute_gimf(gravity, b1, b2, J));
+    r.nInvC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
+    inertia_times(b1.k, J, ia); inertia_times(b2.k, J + 6, ib);
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.nJ[k] = J[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r.nIa[k] = ia[k]; r.nIb[k] = ib[k]; }
+  }
+  {
+    contact_jac(t1, ri, rj, J);
+    r.f1B = (-compute_gw(b1, b2, J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, J));
+    r.f1InvC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
+    inertia_times(b1.k, J, ia); inertia_times(b2.k, J + 6, ib);
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.f1J[k] = J[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r.f1Ia[k] = ia[k]; r.f1Ib[k] = ib[k]; }
+  }
+  {
+    contact_jac(t2, ri, rj, J);
+    r.f2B = (-compute_gw(b1, b2, J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, J));
+    r.f2InvC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
+    inertia_times(b1.k, J, ia); inertia_times(b2.k, J + 6, ib);
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.f2J[k] = J[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r.f2Ia[k] = ia[k]; r.f2Ib[k] = ib[k]; }
+  }
   r.mu = friction;
   r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.dN = 0; r.dF1 = 0; r.dF2 = 0;
-  inertia_times(b1.k, r.nJ, r.nIa); inertia_times(b2.k, r.nJ + 6, r.nIb);
-  inertia_times(b1.k, r.f1J, r.f1Ia); inertia_times(b2.k, r.f1J + 6, r.f1Ib);
-  inertia_times(b1.k, r.f2J, r.f2Ia); inertia_times(b2.k, r.f2J + 6, r.f2Ib);
 }
 // addConstraintEquations (Equation.elm:157-361) for the pair (r1, r2) (global body rows; ncon < 0 == flipped registration):
 // rows are emitted per constraint in list order and consed, so the solver order is the reverse of emission:
@@ -479,7 +502,7 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
   jstart = j0; jcount = E;
 }
 
-__global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
+__global__ void __launch_bounds__(128, 2) k_equations(Dev d) {
   const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
     int ncon = d.cur.slot_ncon[s];
@@ -527,9 +550,7 @@ __global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
             const ContactRec& p = d.prev.contacts[pc0 + m];
             if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
           }
-          RowRec r;
-          contact_row(r, rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, sp, b1, b2);
-          d.cur.rows[out] = r;
+          contact_row(d.cur.rows[out], rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, sp, b1, b2);
         }
       }
     }
