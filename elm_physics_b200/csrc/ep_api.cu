@@ -414,6 +414,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     TRY(dev_alloc(ctx, pool, &d.cls_off, kClasses * 8)); TRY(dev_alloc(ctx, pool, &d.cls_cur, kClasses * 8));
     TRY(dev_alloc(ctx, pool, &d.np_first, kClasses + 1)); TRY(dev_alloc(ctx, pool, &d.np_end, kClasses));
     TRY(dev_alloc(ctx, pool, &d.raw, (size_t)d.item_cap * kRawStride));
+    TRY(dev_alloc(ctx, pool, &d.contact_src, (size_t)d.contact_cap));
     TRY(dev_alloc(ctx, pool, &d.raw_cnt, d.item_cap));
   }
   TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));
@@ -594,14 +595,25 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         }
       } else
       { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d, -1); }
-      { Timed t(ctx, EP_K_EQUATIONS); k_equations<<<gwide, 128, 0, st>>>(d); }
-      { Timed t(ctx, EP_K_ISLANDS);
+      // k_equations and k_islands both consume k_slot_counts' result and nothing of each other.  The light one (islands: a
+      // warp per small world, latency-bound) goes first on the main stream with a grid that leaves CTA slots and registers
+      // free, the heavy one (equations, 168 registers) on a side stream beside it.
+      static const int isl_per_sm = getenv("EP_ISL_CTAS") ? atoi(getenv("EP_ISL_CTAS")) : 12;
+      { Timed t(ctx, EP_K_ISLANDS);        // brackets k_slot_counts + k_islands + k_island_sort
+        k_slot_counts<<<grid_for(ctx, d.slot_cap, 256, 8), 256, 0, st>>>(d);
+        CK(cudaEventRecord(ctx->ev_fork, st));
         // one CTA per world: a warp for small worlds, more for large ones; the union-find arrays sit in shared memory when they fit
         const int it = d.nb_max <= 64 ? 32 : (d.nb_max <= 512 ? 128 : 256);
         const size_t ism = 3 * (size_t)d.nb_max * sizeof(int);
         const int use_smem = ism <= 40 * 1024;
-        k_islands<<<std::max(1, std::min(d.n_worlds, ctx->sm_count * 32)), it, use_smem ? ism : 0, st>>>(d, use_smem);
-        k_island_sort<<<grid_for(ctx, d.n_bodies / 2 + 1, 256, 4), 256, 0, st>>>(d); ctx->launches++; }
+        k_islands<<<std::max(1, std::min(d.n_worlds, ctx->sm_count * isl_per_sm)), it, use_smem ? ism : 0, st>>>(d, use_smem);
+        k_island_sort<<<grid_for(ctx, d.n_bodies / 2 + 1, 256, 4), 256, 0, st>>>(d); ctx->launches += 2; }
+      CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+      { Timed t(ctx, EP_K_EQUATIONS, ctx->aux[0]);
+        k_equations<<<gwide, 128, 0, ctx->aux[0]>>>(d);
+        if (d.n_constraints > 0) { k_joint_equations<<<gwide, 128, 0, ctx->aux[0]>>>(d); ctx->launches++; } }
+      CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
+      CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
       { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
     }
     {   // islands by size class, all launches concurrent: classes 0..3 lane-per-island from shared-memory tiles, 4..6 one warp

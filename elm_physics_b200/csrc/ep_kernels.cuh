@@ -457,14 +457,18 @@ __device__ __forceinline__ void contact_row(RowRec& r, V3 ni, V3 pi, V3 pj, doub
 // addConstraintEquations (Equation.elm:157-361) for the pair (r1, r2) (global body rows; ncon < 0 == flipped registration):
 // rows are emitted per constraint in list order and consed, so the solver order is the reverse of emission:
 // row e of E lands at jstart + E-1-e.
-__device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, const BodyE& b1, const BodyE& b2, double dt, V3 gravity,
-                                    const Spook& sp, int& jstart, int& jcount) {
-  bool flipped = ncon < 0;
-  int ra = flipped ? r2 : r1, rb = flipped ? r1 : r2;
+__device__ __forceinline__ int joint_row_count(const Dev& d, int r1, int r2, int ncon) {
+  const bool flipped = ncon < 0;
+  const int ra = flipped ? r2 : r1, rb = flipped ? r1 : r2;
   int E = 0;
   for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1]; c++) if (d.con_b[c] == rb) E += constraint_rows(d.con_kind[c]);
-  int j0 = atomicAdd(&d.cur.counters[CNT_JROWS], E);
-  if (j0 + E > d.jrow_cap) { d.flags[FLAG_JOINT_OVERFLOW] = 1; E = 0; j0 = 0; }
+  return E;
+}
+// the E rows land at [j0, j0 + E) (allocated by k_slot_counts)
+__device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, const BodyE& b1, const BodyE& b2, double dt, V3 gravity,
+                                    const Spook& sp, int j0, int E) {
+  bool flipped = ncon < 0;
+  int ra = flipped ? r2 : r1, rb = flipped ? r1 : r2;
   int e = 0;
   for (int c = d.con_a_off[ra]; c < d.con_a_off[ra + 1] && E > 0; c++) {
     if (d.con_b[c] != rb) continue;
@@ -499,66 +503,104 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
     }
     for (int k = 0; k < nr; k++, e++) { tmp[k].dl = 0; tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; tmp[k].pad[3] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
   }
-  jstart = j0; jcount = E;
 }
 
-__global__ void __launch_bounds__(128, 2) k_equations(Dev d) {
+// k_slot_counts: one thread per pair slot.  Contact and joint-row ranges of every pair group (the two pool allocations are
+// warp-aggregated: one atomic per warp), the warm-start cache index of this frame, and for every contact of the frame where
+// it comes from (slot, raw contact) -- so that k_equations runs one thread per CONTACT (a thread per group ran 9 of 32 lanes:
+// groups hold 1..8 contacts) and k_islands, which needs only the counts, runs beside it.
+__global__ void __launch_bounds__(256) k_slot_counts(Dev d) {
   const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
-    int ncon = d.cur.slot_ncon[s];
-    const int it0 = d.cur.slot_item0[s], nit = d.cur.slot_nitems[s];
-    int nc = 0;
-    for (int k = 0; k < nit; k++) nc += d.raw_cnt[it0 + k];
-    if (nc <= 0 && ncon == 0) continue;
-    int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-    int w = d.body_world[r1];
-    double dt = d.dt[w]; V3 gravity = ld3(d.gravity + 3 * w);
-    Spook sp = spook(dt);
-    BodyE b1 = load_bodye(d, r1), b2 = load_bodye(d, r2);
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int s0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < total; s0 += stride) {
+    const int s = s0 + lane;
+    int nc = 0, E = 0, ncon = 0, it0 = 0, nit = 0, r1 = 0, r2 = 0;
+    if (s < total) {
+      ncon = d.cur.slot_ncon[s]; it0 = d.cur.slot_item0[s]; nit = d.cur.slot_nitems[s];
+      for (int k = 0; k < nit; k++) nc += d.raw_cnt[it0 + k];
+      if (nc > 0 || ncon != 0) { r1 = d.cur.slot_row1[s]; r2 = d.cur.slot_row2[s]; }
+      if (ncon != 0) E = joint_row_count(d, r1, r2, ncon);
+    }
+    int cs = nc, js = E;                                          // inclusive warp scans
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, cs, o), b = __shfl_up_sync(0xffffffffu, js, o);
+      if (lane >= o) { cs += a; js += b; }
+    }
+    int cbase = 0, jbase = 0;
+    if (lane == 31) {
+      if (cs > 0) cbase = atomicAdd(&d.cur.counters[CNT_CONTACTS], cs);
+      if (js > 0) jbase = atomicAdd(&d.cur.counters[CNT_JROWS], js);
+    }
+    cbase = __shfl_sync(0xffffffffu, cbase, 31); jbase = __shfl_sync(0xffffffffu, jbase, 31);
+    const int ctot = __shfl_sync(0xffffffffu, cs, 31), jtot = __shfl_sync(0xffffffffu, js, 31);
+    if (cbase + ctot > d.contact_cap) { if (nc > 0) d.flags[FLAG_POOL_OVERFLOW] = 1; nc = 0; }
+    if (jbase + jtot > d.jrow_cap) { if (E > 0) d.flags[FLAG_JOINT_OVERFLOW] = 1; E = 0; }
     if (nc > 0) {
-      int c0 = atomicAdd(&d.cur.counters[CNT_CONTACTS], nc);
-      if (c0 + nc > d.contact_cap) { d.flags[FLAG_POOL_OVERFLOW] = 1; nc = 0; c0 = 0; }
+      const int c0 = cbase + cs - nc;
       d.cur.slot_cstart[s] = c0; d.cur.slot_ccount[s] = nc;
-      const int64_t pidx = pair_index(d, w, r1, r2);
-      if (nc > 0) d.cur.pair_slot[pidx] = s;
-      // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128
-      int ps = d.prev.pair_slot[pidx];
-      int pc0 = 0, pcn = 0;
-      if (ps >= 0) { pc0 = d.prev.slot_cstart[ps]; pcn = d.prev.slot_ccount[ps]; }
-      const int i1b = d.inst_off[r1], i2b = d.inst_off[r2], ns2 = d.inst_off[r2 + 1] - i2b;
+      d.cur.pair_slot[pair_index(d, d.body_world[r1], r1, r2)] = s;
       int out = c0;
-      for (int k = 0; k < nit && nc > 0; k++) {          // shape1 outer, shape2 inner (NarrowPhase.elm:33-59)
-        int n = d.raw_cnt[it0 + k];
-        if (n == 0) continue;
-        int a = i1b + k / ns2, b = i2b + k % ns2;
-        int sk = (k / ns2 + 1) * 256 + (k % ns2 + 1);     // ContactId.elm:75-77
-        double f1 = d.inst_friction[a], f2 = d.inst_friction[b], e1 = d.inst_bounciness[a], e2 = d.inst_bounciness[b];
-        double friction = sqrt(f1 * f2);                          // Material.elm:23-25
-        double bounciness = (e1 + e2 + eabs(e1 - e2)) * 0.5;      // Material.elm:31-33
-        for (int x = 0; x < n; x++, out++) {
-          const RawContact rc = d.raw[(size_t)(it0 + k) * kRawStride + x];
-          ContactRec c;
-          c.fk = rc.fk; c.sk = sk; c.slot = s;
-          c.ni[0] = rc.ni.x; c.ni[1] = rc.ni.y; c.ni[2] = rc.ni.z;
-          c.pi[0] = rc.pi.x; c.pi[1] = rc.pi.y; c.pi[2] = rc.pi.z;
-          c.pj[0] = rc.pj.x; c.pj[1] = rc.pj.y; c.pj[2] = rc.pj.z;
-          c.friction = friction; c.bounciness = bounciness;
-          d.cur.contacts[out] = c;
-          // Cache.lookup: first match in pairGroup.contacts order == LAST match in solver order (ContactCache.elm:76-87)
-          double lam = 0; V3 ct1 = mk(0, 0, 0);
-          for (int m = pcn - 1; m >= 0; m--) {
-            const ContactRec& p = d.prev.contacts[pc0 + m];
-            if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
-          }
-          contact_row(d.cur.rows[out], rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, sp, b1, b2);
-        }
+      for (int k = 0; k < nit; k++) {                    // shape1 outer, shape2 inner (NarrowPhase.elm:33-59)
+        const int n = d.raw_cnt[it0 + k];
+        for (int x = 0; x < n; x++) d.contact_src[out++] = make_int2(s, (it0 + k) * kRawStride + x);
       }
     }
-    if (ncon != 0) {
-      int j0, E;
-      joint_rows_for_pair(d, r1, r2, ncon, b1, b2, dt, gravity, sp, j0, E);
-      d.cur.slot_jstart[s] = j0; d.cur.slot_jcount[s] = E;
+    if (ncon != 0) { d.cur.slot_jstart[s] = E > 0 ? jbase + js - E : 0; d.cur.slot_jcount[s] = E; }
+  }
+}
+
+// k_equations: one thread per contact (contactEquations)
+__global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
+  if (d.flags[FLAG_POOL_OVERFLOW]) return;       // contact_src has holes then; ep_sync reports the overflow
+  const int ncont = min(d.cur.counters[CNT_CONTACTS], d.contact_cap);
+  for (int out = blockIdx.x * blockDim.x + threadIdx.x; out < ncont; out += gridDim.x * blockDim.x) {
+    const int2 src = d.contact_src[out];
+    const int s = src.x;
+    const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+    const int w = d.body_world[r1];
+    const int k = src.y / kRawStride - d.cur.slot_item0[s];
+    const int i1b = d.inst_off[r1], i2b = d.inst_off[r2], ns2 = d.inst_off[r2 + 1] - i2b;
+    const int a = i1b + k / ns2, b = i2b + k % ns2;
+    const int sk = (k / ns2 + 1) * 256 + (k % ns2 + 1);     // ContactId.elm:75-77
+    const double f1 = d.inst_friction[a], f2 = d.inst_friction[b], e1 = d.inst_bounciness[a], e2 = d.inst_bounciness[b];
+    const double friction = sqrt(f1 * f2);                          // Material.elm:23-25
+    const double bounciness = (e1 + e2 + eabs(e1 - e2)) * 0.5;      // Material.elm:31-33
+    const RawContact rc = d.raw[src.y];
+    ContactRec c;
+    c.fk = rc.fk; c.sk = sk; c.slot = s;
+    c.ni[0] = rc.ni.x; c.ni[1] = rc.ni.y; c.ni[2] = rc.ni.z;
+    c.pi[0] = rc.pi.x; c.pi[1] = rc.pi.y; c.pi[2] = rc.pi.z;
+    c.pj[0] = rc.pj.x; c.pj[1] = rc.pj.y; c.pj[2] = rc.pj.z;
+    c.friction = friction; c.bounciness = bounciness;
+    d.cur.contacts[out] = c;
+    // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128; Cache.lookup: first match in pairGroup.contacts order == LAST
+    // match in solver order (ContactCache.elm:76-87)
+    double lam = 0; V3 ct1 = mk(0, 0, 0);
+    const int ps = d.prev.pair_slot[pair_index(d, w, r1, r2)];
+    if (ps >= 0) {
+      const int pc0 = d.prev.slot_cstart[ps], pcn = d.prev.slot_ccount[ps];
+      for (int m = pcn - 1; m >= 0; m--) {
+        const ContactRec& p = d.prev.contacts[pc0 + m];
+        if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
+      }
     }
+    const double dt = d.dt[w]; const V3 gravity = ld3(d.gravity + 3 * w);
+    const BodyE b1 = load_bodye(d, r1), b2 = load_bodye(d, r2);
+    contact_row(d.cur.rows[out], rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, spook(dt), b1, b2);
+  }
+}
+// addConstraintEquations: one thread per constrained pair (launched only when the batch has constraints)
+__global__ void __launch_bounds__(128, 2) k_joint_equations(Dev d) {
+  const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    const int ncon = d.cur.slot_ncon[s];
+    if (ncon == 0) continue;
+    const int E = d.cur.slot_jcount[s];
+    if (E <= 0) continue;
+    const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s], w = d.body_world[r1];
+    const double dt = d.dt[w];
+    joint_rows_for_pair(d, r1, r2, ncon, load_bodye(d, r1), load_bodye(d, r2), dt, ld3(d.gravity + 3 * w), spook(dt), d.cur.slot_jstart[s], E);
   }
 }
 
