@@ -334,7 +334,7 @@ def main():
         e.step_frame(eb, eo)
         t_e2e += max_over_ranks(time.perf_counter() - t0)
         h2d = sum(getattr(eb, n).nbytes for n, _ in abi.BODY_F64_FIELDS)
-        d2h = eb.nbytes_out() + eo.n_contacts * 132 + eo.n_groups * 80 + eb.n_worlds * 12
+        d2h = eb.nbytes_out() + eo.nbytes_out()
     e2e_single = n_dyn * args.e2e_steps * world_size / t_e2e
     e2e_parity = None
     if world_size == 1 and not args.no_cpu_baseline:
@@ -352,39 +352,47 @@ def main():
     # sub-batch, the step of another and the D2H of a third overlap (PCIe is full duplex, two copy engines), which is how a
     # host that owns several independent world batches would drive one GPU.  This is the headline e2e.
     K = max(1, min(args.e2e_contexts, W))
-    subs = []
-    for k in range(K):
-        w0k, w1k = sharding.shard_range(W, k, K)
-        bk = end_bodies.slice_worlds(w0k, w1k).copy(alloc=pool.empty)
-        pk = abi.slice_params(params, w0k, w1k)
-        ek = eng.Engine(local_rank)
-        ek.upload_shapes(shapes)
-        ek.upload_worlds(bk, pk, None)
-        capk = H.contacts_for(bk)
-        ok = abi.Contacts(bk.n_worlds, capk.group_cap, capk.contact_cap, alloc=pool.empty)
-        del capk
-        for _ in range(3):
-            ek.step_frame(bk, ok)         # untimed: warm start builds up, host path warms
-        subs.append((ek, bk, ok))
 
-    def frames(sub):
-        ek, bk, ok = sub
-        for _ in range(args.e2e_steps):
-            ek.step_frame(bk, ok)
+    def pipelined(fields):
+        subs = []
+        for k in range(K):
+            w0k, w1k = sharding.shard_range(W, k, K)
+            bk = end_bodies.slice_worlds(w0k, w1k).copy(alloc=pool.empty)
+            pk = abi.slice_params(params, w0k, w1k)
+            ek = eng.Engine(local_rank)
+            ek.upload_shapes(shapes)
+            ek.upload_worlds(bk, pk, None)
+            capk = H.contacts_for(bk)
+            ok = abi.Contacts(bk.n_worlds, capk.group_cap, capk.contact_cap, alloc=pool.empty, fields=fields)
+            del capk
+            for _ in range(3):
+                ek.step_frame(bk, ok)         # untimed: warm start builds up, host path warms
+            subs.append((ek, bk, ok))
 
-    barrier()
-    ths = [threading.Thread(target=frames, args=(sub,)) for sub in subs]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    t_pipe = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = n_dyn * args.e2e_steps * world_size / t_pipe
-    h2d = sum(sum(getattr(bk, n).nbytes for n, _ in abi.BODY_F64_FIELDS) for _, bk, _ in subs)
-    d2h = sum(bk.nbytes_out() + ok.n_contacts * 132 + ok.n_groups * 80 + bk.n_worlds * 12 for _, bk, ok in subs)
-    for ek, _, _ in subs:
-        ek.close()
+        def frames(sub):
+            ek, bk, ok = sub
+            for _ in range(args.e2e_steps):
+                ek.step_frame(bk, ok)
+
+        barrier()
+        ths = [threading.Thread(target=frames, args=(sub,)) for sub in subs]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        t_pipe = max_over_ranks(time.perf_counter() - t0)
+        h2d = sum(sum(getattr(bk, n).nbytes for n, _ in abi.BODY_F64_FIELDS) for _, bk, _ in subs)
+        d2h = sum(bk.nbytes_out() + ok.nbytes_out() for _, bk, ok in subs)
+        for ek, _, _ in subs:
+            ek.close()
+        return n_dyn * args.e2e_steps * world_size / t_pipe, h2d, d2h
+
+    # headline: the host reads back what the public API exposes of a frame -- the integrated bodies and what
+    # Physics.contactPoints consumes (src/Physics.elm:1158-1207); the rest of `Contacts` is the next frame's warm start
+    # and stays resident.  Beside it: the same with EVERY array of ep_contacts copied back.
+    e2e_value, h2d, d2h = pipelined(abi.CONTACT_POINTS_FIELDS)
+    e2e_full, _, d2h_full = pipelined(None)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
@@ -396,10 +404,12 @@ def main():
                    "l2": "resident state (bodies + contacts + rows) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": args.e2e_steps,
-                "call": "ep_step_frame(pinned host buffers): state H2D, one step warm-started by the resident previous frame, "
-                        "state + contacts D2H; the batch is driven as %d contexts from %d host threads so that copies and "
-                        "steps of different sub-batches overlap" % (K, K),
-                "contexts": K, "single_context_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
+                "call": "ep_step_frame(pinned host buffers): H2D of every per-body array, one step warm-started by the resident "
+                        "previous frame, D2H of the integrated state + the contact data Physics.contactPoints reads (pair ids, "
+                        "pre-step body1 frames, contact points); the batch is driven as %d contexts from %d host threads so "
+                        "that copies and steps of different sub-batches overlap" % (K, K),
+                "contexts": K, "all_contact_arrays_value": e2e_full, "all_contact_arrays_d2h_bytes_per_step": int(d2h_full),
+                "single_context_all_arrays_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "final_state_gather_ms": gather_ms,

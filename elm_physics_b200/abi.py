@@ -160,6 +160,13 @@ CONTACT_FIELDS = (("shape_key", np.int32, 1), ("feature_key", np.int64, 1), ("ni
                   ("bounciness", np.float64, 1), ("lambda_", np.float64, 1), ("t1", np.float64, 3))
 
 
+# construction order of the arrays of Contacts (see __init__)
+ALL_CONTACT_ARRAYS = ("world_group_off", "group_id1", "group_id2", "group_n_constraints", "group_contact_off", "group_pre_pos1",
+                      "group_pre_quat1") + tuple(n for n, _, _ in CONTACT_FIELDS) + ("iterations", "world_n_islands", "group_island")
+# what Physics.contactPoints consumes (src/Physics.elm:1158-1207)
+CONTACT_POINTS_FIELDS = ("group_id1", "group_id2", "group_pre_pos1", "group_pre_quat1", "pi")
+
+
 def slice_params(p, w0, w1):
     """Worlds [w0, w1) of a Params without callbacks/constraints (batched scenes)."""
     assert p.collide is None and p.n_constraints == 0
@@ -169,16 +176,24 @@ def slice_params(p, w0, w1):
 class Contacts:
     """Pair groups + contacts (ep_contacts) with caller-chosen capacities."""
 
-    def __init__(self, n_worlds, group_cap, contact_cap, alloc=None):
+    def __init__(self, n_worlds, group_cap, contact_cap, alloc=None, fields=None):
+        """`fields`: names of the optional arrays to hold (None = all).  The others stay NULL in the C struct and are not
+        copied back by the downloads (include/elm_physics_b200.h); CONTACT_POINTS_FIELDS is what contactPoints reads."""
         self.n_worlds, self.group_cap, self.contact_cap = n_worlds, group_cap, contact_cap
         g, c = max(group_cap, 1), max(contact_cap, 1)
-        if alloc is None:
-            zeros = np.zeros
-        else:
-            def zeros(shape, dtype=np.float64):
-                a = alloc(shape, dtype)
-                a[...] = 0
-                return a
+        always = ("world_group_off", "group_contact_off")
+        made = []
+
+        def zeros(shape, dtype=np.float64):
+            made.append(None)
+            name = ALL_CONTACT_ARRAYS[len(made) - 1]
+            if fields is not None and name not in fields and name not in always:
+                return None
+            if alloc is None:
+                return np.zeros(shape, dtype)
+            a = alloc(shape, dtype)
+            a[...] = 0
+            return a
         self.world_group_off = zeros(n_worlds + 1, np.int32)
         self.group_id1 = zeros(g, np.int32)
         self.group_id2 = zeros(g, np.int32)
@@ -206,6 +221,19 @@ class Contacts:
     @property
     def n_contacts(self):
         return int(self.group_contact_off[self.n_groups])
+
+    def nbytes_out(self):
+        """Bytes a download copies into this object (the arrays it holds, trimmed to the used groups / contacts)."""
+        ng, nc, nw = self.n_groups, self.n_contacts, self.n_worlds
+        per = {"world_group_off": nw + 1, "group_contact_off": ng + 1, "iterations": nw, "world_n_islands": nw}
+        total = 0
+        for name in ALL_CONTACT_ARRAYS:
+            a = getattr(self, name)
+            if a is None:
+                continue
+            rows = per.get(name, ng if name.startswith("group_") else nc)
+            total += rows * a.itemsize * (a.shape[1] if a.ndim > 1 else 1)
+        return total
 
     def canonical(self):
         """Everything a frame's contacts are, as comparable numpy arrays trimmed to the used length."""

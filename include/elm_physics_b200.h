@@ -133,6 +133,10 @@ typedef struct ep_params {
  * `lambda` = solved normal lambda, `t1` = friction-1 direction (src/Solver.elm:320-335).
  * As INPUT only world_group_off, group_id1/2, group_contact_off, shape_key, feature_key, lambda,
  * t1 are read.  Capacities are in *_cap; overflow -> EP_ECAPACITY, nothing usable written.
+ * As an OUTPUT every array pointer may be NULL: that array is then not copied back.  A simulate loop that keeps the batch
+ * resident (ep_step_frame) needs on the host only what `Physics.contactPoints` reads (src/Physics.elm:1158-1207:
+ * group_id1/2, group_contact_off, group_pre_pos1/quat1, pi) -- the rest of `Contacts` (warm-start lambdas, keys, normals)
+ * is consumed by the next step only, and that step reads the resident frame.
  */
 typedef struct ep_contacts {
   int32_t n_worlds;

@@ -256,6 +256,31 @@ def test_step_frame_host_buffers_lockstep(engine, oracle):
         pool.close()
 
 
+def test_step_frame_contact_points_fields_only(engine):
+    """ep_step_frame with only the arrays Physics.contactPoints reads (the other ep_contacts pointers NULL) returns the
+    same bodies and, in those arrays, the same bytes as the call that copies every array back; the skipped arrays of the
+    frame stay resident (the next frame's warm start is unaffected)."""
+    shapes, bodies, params = scenes.mixed_worlds(5)
+    cap = H.contacts_for(bodies)
+    runs = []
+    for fields in (None, abi.CONTACT_POINTS_FIELDS):
+        b = bodies.copy()
+        engine.upload_shapes(shapes)
+        engine.upload_worlds(b, params, None)
+        out = abi.Contacts(bodies.n_worlds, cap.group_cap, cap.contact_cap, fields=fields)
+        for _ in range(40):
+            engine.step_frame(b, out)
+        runs.append((b, out))
+    (bf, of), (bl, ol) = runs
+    H.assert_bodies_equal(bf, bl, "lean vs full read-back")
+    assert ol.shape_key is None and ol.lambda_ is None and ol.t1 is None
+    ng, nc = of.n_groups, of.n_contacts
+    assert (ol.n_groups, ol.n_contacts) == (ng, nc) and nc > 0
+    assert ol.nbytes_out() < of.nbytes_out() // 2
+    for name, n in (("group_id1", ng), ("group_id2", ng), ("group_pre_pos1", ng), ("group_pre_quat1", ng), ("pi", nc)):
+        assert getattr(ol, name)[:n].tobytes() == getattr(of, name)[:n].tobytes(), name
+
+
 def test_python_simulate_mirror(engine):
     """The host-side mirror of Physics.simulate (physics.simulate) steps the README scene like the reference's
     own doc example: contacts fed back, ball ends on the floor; contactPoints reports the touching point."""

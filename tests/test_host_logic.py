@@ -71,3 +71,17 @@ def test_sphere_and_plane_bodies():
     assert s.transform3d[0] == (0.0, 0.0, 5.0) and s.kind == 2
     f = P.plane(P.wood)
     assert f.kind == 1 and f.inv_mass == 0 and f.bounding_sphere_radius == m3.MAX_NUMBER
+
+
+def test_contacts_optional_fields():
+    """abi.Contacts(fields=...) leaves the unlisted arrays NULL in ep_contacts (include/elm_physics_b200.h: a NULL output
+    array is not copied back); the two offset arrays are always held."""
+    from elm_physics_b200 import abi
+    full = abi.Contacts(2, 4, 8)
+    lean = abi.Contacts(2, 4, 8, fields=abi.CONTACT_POINTS_FIELDS)
+    for name in abi.ALL_CONTACT_ARRAYS:
+        assert getattr(full, name) is not None
+        held = name in abi.CONTACT_POINTS_FIELDS or name in ("world_group_off", "group_contact_off")
+        assert (getattr(lean, name) is not None) == held, name
+    assert not lean.c.lambda_ if hasattr(lean.c, "lambda_") else True
+    assert lean.nbytes_out() <= full.nbytes_out()
