@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/elm_physics_b200.h"
@@ -754,6 +755,13 @@ extern "C" void* ep_host_alloc(size_t bytes) {
 }
 extern "C" void ep_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+// one gate per device, shared by every context of the process (see ep_step_frame)
+struct FrameGate { std::mutex mu; cudaEvent_t ev = nullptr; };
+static FrameGate& frame_gate(int device) {
+  static FrameGate gates[64];
+  return gates[device < 0 || device >= 64 ? 0 : device];
+}
+
 extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
   if (!ctx || !B) return EP_EINVAL;
   if (!ctx->have_worlds) { ctx->err = "no resident worlds (ep_upload_worlds first)"; return EP_ESTATE; }
@@ -768,9 +776,24 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
   CK(H2D(d.force, B->force, 3 * nb)); CK(H2D(d.torque, B->torque, 3 * nb)); CK(H2D(d.iiw, B->inv_inertia_world, 9 * nb));
   CK(H2D(d.inv_mass, B->inv_mass, nb)); CK(H2D(d.inv_inertia, B->inv_inertia, 3 * nb)); CK(H2D(d.ldp, B->lin_damp_pow, nb)); CK(H2D(d.adp, B->ang_damp_pow, nb));
   CK(H2D(d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(d.ang_lock, B->ang_lock, 3 * nb)); CK(H2D(d.radius, B->bounding_radius, nb));
-  // static bodies may have been moved by the caller between frames: place every shape, not only the moving ones
-  if (d.n_pl_all > d.n_pl_moving) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
-  TRY(ep_step_resident(ctx, 1));
+  {
+    // Several contexts on one device (sub-batches driven from their own host threads) take turns on the SMs: the step of a
+    // context waits for the step of the context before it, so that it runs beside the OTHER contexts' copies instead of
+    // beside their steps.  Left alone the contexts fall into lock step -- all stepping (sharing the SMs), then all copying
+    // (sharing PCIe) -- and nothing overlaps: measured 5.1 ms per frame for 2 x 4096 worlds instead of 3.9.
+    static const bool gated = !(getenv("EP_FRAME_GATE") && atoi(getenv("EP_FRAME_GATE")) == 0);
+    FrameGate& g = frame_gate(ctx->device);
+    std::unique_lock<std::mutex> lock(g.mu, std::defer_lock);
+    if (gated) {
+      lock.lock();
+      if (!g.ev) CK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
+      else CK(cudaStreamWaitEvent(st, g.ev, 0));
+    }
+    // static bodies may have been moved by the caller between frames: place every shape, not only the moving ones
+    if (d.n_pl_all > d.n_pl_moving) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
+    TRY(ep_step_resident(ctx, 1));
+    if (gated) CK(cudaEventRecord(g.ev, st));
+  }
   CK(cudaMemcpyAsync(B->pos, d.pos, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(B->quat, d.quat, 4 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(B->vel, d.vel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -231,28 +231,34 @@ __device__ __forceinline__ void tile_store_sb(const TT& T, int b, const SB& s) {
 }
 template <class TT>
 __device__ __forceinline__ void pair_load_body(const TT& T, int b, double& im, SB& s) {
-  if (b == 0) { im = 0; s.vX = s.vY = s.vZ = s.wX = s.wY = s.wZ = 0; }
-  else {
-    const int L = T.L();
-    const double* p = T.bd + ((size_t)b * kBodyF64 * L + T.lane);
-    im = p[0]; s.vX = p[L]; s.vY = p[2 * L]; s.vZ = p[3 * L]; s.wX = p[4 * L]; s.wY = p[5 * L]; s.wZ = p[6 * L];
-  }
+  const int L = T.L();
+  const double* p = T.bd + ((size_t)b * kBodyF64 * L + T.lane);
+  im = p[0]; s.vX = p[L]; s.vY = p[2 * L]; s.vZ = p[3 * L]; s.wX = p[4 * L]; s.wY = p[5 * L]; s.wZ = p[6 * L];
 }
+// Changing the body pair is decided by the WARP: when any active lane's row couples other bodies than its previous row,
+// every active lane writes its two bodies back to its tile column and reads the two of the new row -- straight-line code,
+// no per-lane branches (ncu: the per-lane version spent 35 % of the solver's samples in these four divergent sections).
+// A lane that keeps its pair rewrites and rereads the same values; local body 0 (the stand-in of every non-dynamic body) is
+// an ordinary column of zeros: +0 written back, +0 and inverse mass 0 read.
 template <class TT>
 __device__ __forceinline__ void pair_enter(const TT& T, Pair& P, int desc) {
   const int nb1 = desc & 0xff, nb2 = (desc >> 8) & 0xff;
-  if (nb1 == P.b1 && nb2 == P.b2) return;
-  // a body that changes sides goes through the tile: stores first, loads after
-  if (nb1 != P.b1 && P.b1 > 0) tile_store_sb(T, P.b1, P.s1);
-  if (nb2 != P.b2 && P.b2 > 0) tile_store_sb(T, P.b2, P.s2);
-  if (nb1 != P.b1) { pair_load_body(T, nb1, P.im1, P.s1); P.b1 = nb1; }
-  if (nb2 != P.b2) { pair_load_body(T, nb2, P.im2, P.s2); P.b2 = nb2; }
+  if (!__any_sync(__activemask(), (nb1 != P.b1) | (nb2 != P.b2))) return;
+  tile_store_sb(T, P.b1, P.s1);
+  tile_store_sb(T, P.b2, P.s2);
+  pair_load_body(T, nb1, P.im1, P.s1); P.b1 = nb1;
+  pair_load_body(T, nb2, P.im2, P.s2); P.b2 = nb2;
+}
+__device__ __forceinline__ void pair_reset(Pair& P) {      // both sides hold the stand-in
+  P.b1 = 0; P.b2 = 0; P.im1 = 0; P.im2 = 0;
+  P.s1.vX = P.s1.vY = P.s1.vZ = P.s1.wX = P.s1.wY = P.s1.wZ = 0;
+  P.s2.vX = P.s2.vY = P.s2.vZ = P.s2.wX = P.s2.wY = P.s2.wZ = 0;
 }
 template <class TT>
 __device__ __forceinline__ void pair_flush(const TT& T, Pair& P) {
-  if (P.b1 > 0) tile_store_sb(T, P.b1, P.s1);
-  if (P.b2 > 0) tile_store_sb(T, P.b2, P.s2);
-  P.b1 = -1; P.b2 = -1;
+  tile_store_sb(T, P.b1, P.s1);
+  tile_store_sb(T, P.b2, P.s2);
+  pair_reset(P);
 }
 // applyVelocityBody1/2 (Solver.elm:505-550) with the precomputed I.w; branch-free (see the stand-in note above)
 __device__ __forceinline__ void apply_pre(double dl, const double* J, const double* ia, const double* ib, Pair& P) {
@@ -268,9 +274,12 @@ __device__ __forceinline__ void apply_pre(double dl, const double* J, const doub
 // predicated off where a lane has fewer rows, has converged, or holds no island) and re-converge with __syncwarp after
 // every row, so changing the body pair is the only divergent section and it never outlives its row.
 // the [first, first + bytes) block of the tile image towards L1, lines shared out over the lanes
-__device__ __forceinline__ void prefetch_block(const double* first, int bytes, int lane) {
-  const char* p = (const char*)first;
-  for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + o));
+template <int BYTES>
+__device__ __forceinline__ void prefetch_block(const double* first, int lane) {
+  const char* p = (const char*)first + lane * 128;
+#pragma unroll
+  for (int o = 0; o < BYTES; o += 32 * 128)
+    if (o + 32 * 128 <= BYTES || o + lane * 128 < BYTES) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + o));
 }
 
 template <int PREFETCH, class TT>      // 0: rows read where they are used (staged tiles); 1: next row prefetched to L1 (rows in L2)
@@ -278,7 +287,7 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   const bool have = isl >= 0;
   const int gn = have ? d.isl_cnt[isl] : 0, w = have ? d.isl_world[isl] : 0, C = have ? d.isl_nc[isl] : 0, R = have ? C + d.isl_nj[isl] : 0;
   const int Rmax = warp_max(R), Cmax = warp_max(C);
-  Pair P; P.b1 = -1; P.b2 = -1;
+  Pair P; pair_reset(P);
   // warm start (applyContactsWarmStart, Solver.elm:102-119): groups in REVERSE enumeration order (buildAndWarmStart walks
   // pairGroups, Solver.elm:122-208), the seeded normal impulses of a group in solver order
   for (int hi = R - 1; hi >= 0;) {
@@ -309,9 +318,9 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
     // sweep 1: velocityNonFrictionGroup (Solver.elm:850-864) group by group: joint rows (572-619), then contact normals (625-672)
     double p1 = 0;
     {
-      if (PREFETCH) prefetch_block(T.rd, kNRowF64 * 32 * 8, T.lane);
+      if (PREFETCH) prefetch_block<kNRowF64 * 32 * 8>(T.rd, T.lane);
       for (int r = 0; r < Rmax; r++) {
-        if (PREFETCH && r + 1 < Rmax) prefetch_block(T.rd + (size_t)(r + 1) * kNRowF64 * 32, kNRowF64 * 32 * 8, T.lane);
+        if (PREFETCH && r + 1 < Rmax) prefetch_block<kNRowF64 * 32 * 8>(T.rd + (size_t)(r + 1) * kNRowF64 * 32, T.lane);
         if (!done && r < R) {
           RowN cur;
           load_row_n(T, r, cur);
@@ -333,9 +342,9 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
     double p2 = (gn == 1) ? p1 : 0;
     {
       const double* fbase = T.rd + (size_t)T.t.maxR * kNRowF64 * 32;
-      if (PREFETCH) prefetch_block(fbase, kFRowF64 * 32 * 8, T.lane);
+      if (PREFETCH) prefetch_block<kFRowF64 * 32 * 8>(fbase, T.lane);
       for (int c = 0; c < Cmax; c++) {
-        if (PREFETCH && c + 1 < Cmax) prefetch_block(fbase + (size_t)(c + 1) * kFRowF64 * 32, kFRowF64 * 32 * 8, T.lane);
+        if (PREFETCH && c + 1 < Cmax) prefetch_block<kFRowF64 * 32 * 8>(fbase + (size_t)(c + 1) * kFRowF64 * 32, T.lane);
         if (!done && c < C) {
           RowF cur;
           load_row_f(T, c, cur);
