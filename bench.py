@@ -280,7 +280,6 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     launches0 = e.stats()["kernel_launches"]
-    e.profile(True)
     barrier()
     torch.cuda.synchronize()
     sampler.start()
@@ -292,8 +291,6 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
-    ktimes = e.kernel_times()
-    e.profile(False)
     launches = e.stats()["kernel_launches"] - launches0
     end_bodies = bodies.copy()
     e.download_bodies(end_bodies)
@@ -394,6 +391,21 @@ def main():
     e2e_value, h2d, d2h = pipelined(abi.CONTACT_POINTS_FIELDS)
     e2e_full, _, d2h_full = pipelined(None)
 
+    # the same K steps once more with a CUDA-event pair around every launch (ep_profile): the per-kernel durations behind
+    # `roofline` / `kernels`.  Kept out of the pass above because ~60 event records per step cost ~3 % of it.
+    counts_p0 = e.stats()
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e.profile(True)
+    pv0.record(stream)
+    e.step_resident(args.steps)
+    pv1.record(stream)
+    e.sync()
+    torch.cuda.synchronize()
+    ms_profiled = pv0.elapsed_time(pv1)
+    ktimes = e.kernel_times()
+    e.profile(False)
+    counts_prof = e.stats()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -410,7 +422,7 @@ def main():
                         "that copies and steps of different sub-batches overlap" % (K, K),
                 "contexts": K, "all_contact_arrays_value": e2e_full, "all_contact_arrays_d2h_bytes_per_step": int(d2h_full),
                 "single_context_all_arrays_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "ms_per_step_with_per_kernel_events": ms_profiled / args.steps,
         "clocks": clocks,
         "final_state_gather_ms": gather_ms,
     }
@@ -439,8 +451,8 @@ def main():
         # The solver is not an HBM kernel (each row crosses HBM once per step): its ceiling is the FP64 pipe without FMA
         # (tools/fp64_peak.cu: profiles/r01_fp64_peak.json) and, in practice, the dependent-issue latency of the PGS chain.
         # Algorithmic fp64 ops: 270 per contact-iteration, 90 per joint-row-iteration, counted on the device.
-        ci = counts["contact_iterations"] - work0[0]
-        ji = counts["joint_row_iterations"] - work0[1]
+        ci = counts_prof["contact_iterations"] - counts_p0["contact_iterations"]        # of the profiled pass, like ktimes
+        ji = counts_prof["joint_row_iterations"] - counts_p0["joint_row_iterations"]
         fp64_peak = 18.52
         try:
             fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))["dadd_tops"])
