@@ -220,6 +220,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-contexts", type=int, default=2, help="sub-batches (contexts + host threads) of the end-to-end measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pile", action="store_true", help="skip the second half of BASELINE's metric (ms/step of the 2k-body convex pile)")
+    ap.add_argument("--pile-preroll", type=int, default=600)
+    ap.add_argument("--pile-steps", type=int, default=60)
     args = ap.parse_args()
     rank, world_size, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -487,6 +490,27 @@ def main():
                 for name in abi.BODY_INOUT:
                     exact = exact and getattr(end_bodies, name)[r0:r1].tobytes() == getattr(ch[0], name).tobytes()
             line["parity"] = {"worlds": sample, "steps": args.steps, "bit_exact_vs_oracle": bool(exact)}
+        # ---- second half of BASELINE's metric: ms/step of the 2k-body convex pile (config 4; one world, one GPU) ------
+        if world_size == 1 and not args.no_pile:
+            ps, pb, pp = pack.pack_worlds(scenes.pile_scene(2000))
+            ep = eng.Engine(local_rank)
+            ep.upload_shapes(ps)
+            ep.upload_worlds(pb, pp, None)
+            ep.step_resident(args.pile_preroll)
+            ep.sync()
+            pstream = torch.cuda.ExternalStream(ep.stream_handle(), device=torch.device("cuda", local_rank))
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(pstream)
+            ep.step_resident(args.pile_steps)
+            q1.record(pstream)
+            ep.sync()
+            torch.cuda.synchronize()
+            pst = ep.stats()
+            line["pile"] = {"workload": "C4: 2000 convex hulls / compounds dropped into a walled pit, one world, 20 iterations",
+                            "ms_per_step": q0.elapsed_time(q1) / args.pile_steps, "steps": args.pile_steps,
+                            "preroll_steps": args.pile_preroll, "bodies": int(pb.n_bodies), "contacts": pst["contacts"],
+                            "islands": pst["islands"], "unit": "ms/step", "higher_is_better": False}
+            ep.close()
         print(json.dumps(line), flush=True)
     pool.close()
     e.close()

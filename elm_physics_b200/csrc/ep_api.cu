@@ -906,6 +906,11 @@ extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
     if (cudaMemcpy(wk, ctx->d.work, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess) {
       ctx->stats[EP_STAT_CONTACT_ITERATIONS] = (int64_t)wk[0]; ctx->stats[EP_STAT_JOINT_ROW_ITERATIONS] = (int64_t)wk[1];
     }
+    int32_t cnt[CNT_COUNT];      // counts of the last computed frame (the group count comes with a contact download only)
+    if (cudaMemcpy(cnt, ctx->d.prev.counters, sizeof cnt, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      ctx->stats[EP_STAT_CANDIDATE_PAIRS] = cnt[CNT_CAND]; ctx->stats[EP_STAT_CONTACTS] = std::min(cnt[CNT_CONTACTS], ctx->d.contact_cap);
+      ctx->stats[EP_STAT_ISLANDS] = cnt[CNT_ISLANDS];
+    }
   }
   for (int i = 0; i < n && i < EP_STAT_COUNT; i++) out[i] = ctx->stats[i];
   return EP_OK;
