@@ -206,10 +206,28 @@ def run_reference(args, rank, world_size):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep the process's stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL's version banner comes from
+    C code, whatever NCCL_DEBUG says on the box) goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -511,7 +529,7 @@ def main():
                             "preroll_steps": args.pile_preroll, "bodies": int(pb.n_bodies), "contacts": pst["contacts"],
                             "islands": pst["islands"], "unit": "ms/step", "higher_is_better": False}
             ep.close()
-        print(json.dumps(line), flush=True)
+        emit(line)
     pool.close()
     e.close()
     if world_size > 1:
