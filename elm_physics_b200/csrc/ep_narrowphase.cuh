@@ -294,6 +294,48 @@ EPD void sphere_convex(bool flip, const Sph& s, const Cvx& c, ContactSink& out) 
   if (bestD2 - radius * radius < 0) sphere_emit(flip, feat(5, kOnVertex, 0, 0, 0), center, bestP, radius - sqrt(bestD2), out);
 }
 
+// ---- fp32 screening of SAT axes ------------------------------------------------------------------------------------
+// The SAT needs the exact overlap only of the axes that can still matter.  If T is any upper bound of the smallest TRUE
+// overlap of a set of axes, an axis whose true overlap is > T neither wins (`dist - best < 0` is a strict improvement,
+// first wins ties: ConvexConvex.elm:447-470, 540-573) nor changes the verdict "separated" (the smallest one decides it as
+// well: every separating axis yields the same empty result).  Bounds come from fp32 projections of an fp32 copy of the
+// hull's vertices RELATIVE to an origin o near the pair (v.n = (v - o).n + o.n; differences of two hulls' projections do
+// not depend on o): pass 1 walks ALL axes in fp32 and keeps a bit mask of the survivors, pass 2 evaluates the survivors in
+// fp64 exactly as the reference does, in the reference's order.  The lanes of a warp walk pass 1 in lock step and pass 2
+// over their OWN survivor lists, so a warp runs max-over-lanes(survivors) exact projections instead of all of them.
+// The copy lives in local memory (interleaved per thread: the lanes read it coalesced).
+// Error of one projected value against the reference's fp64 value: |fl32(v - o) - (v - o)| <= 2^-24 D per component
+// (D = largest |component| of any v - o), |fl32(n) - n| <= 2^-24, three products and two sums in fp32 on terms <= D
+// =>  <= 15 * 2^-24 * D < 9e-7 D per value, < 2e-6 D per overlap (a difference of two values).  kScrE doubles that.
+// Screening only skips work: every value that is USED is the exact fp64 one.
+constexpr int kScrVerts = 32;
+constexpr double kScrE = 4.0e-6;
+struct Scr { float r[3 * kScrVerts]; int nv; };
+EPD void scr_build(Scr& s, const Cvx& c, V3 o, double& D) {
+  for (int i = 0; i < c.nv; i++) {
+    V3 v = c.vert(i);
+    double dx = v.x - o.x, dy = v.y - o.y, dz = v.z - o.z;
+    s.r[3 * i] = (float)dx; s.r[3 * i + 1] = (float)dy; s.r[3 * i + 2] = (float)dz;
+    D = emax(D, emax(eabs(dx), emax(eabs(dy), eabs(dz))));
+  }
+  s.nv = c.nv;
+}
+EPD void scr_project(const Scr& s, V3 n, float& lo, float& hi) {
+  const float nx = (float)n.x, ny = (float)n.y, nz = (float)n.z;
+  float lo0 = 3.0e38f, lo1 = 3.0e38f, hi0 = -3.0e38f, hi1 = -3.0e38f;
+  int i = 0;
+  for (; i + 1 < s.nv; i += 2) {
+    const float a = fmaf(s.r[3 * i + 2], nz, fmaf(s.r[3 * i + 1], ny, s.r[3 * i] * nx));
+    const float b = fmaf(s.r[3 * i + 5], nz, fmaf(s.r[3 * i + 4], ny, s.r[3 * i + 3] * nx));
+    lo0 = fminf(lo0, a); hi0 = fmaxf(hi0, a); lo1 = fminf(lo1, b); hi1 = fmaxf(hi1, b);
+  }
+  if (i < s.nv) {
+    const float a = fmaf(s.r[3 * i + 2], nz, fmaf(s.r[3 * i + 1], ny, s.r[3 * i] * nx));
+    lo0 = fminf(lo0, a); hi0 = fmaxf(hi0, a);
+  }
+  lo = fminf(lo0, lo1); hi = fmaxf(hi0, hi1);
+}
+
 // ---- ConvexConvex.elm -----------------------------------------------------------------------------
 // projectConvex 596-610 / project 689-710
 EPD void project_convex(V3 axis, const Cvx& c, double& mn, double& mx) {
@@ -387,10 +429,11 @@ EPD int clip_polygon(V3 pn, double pc, const TagPt* src, int n, TagPt* dst, bool
   for (int i = 0; i < m / 2; i++) { TagPt t = dst[i]; dst[i] = dst[m - 1 - i]; dst[m - 1 - i] = t; }
   return m;
 }
-// addContacts 40-63 with findFaceSAT 420-479, findEdgeSAT 517-580, dispatchBestFaces 69-114, clipTwoFaces 204-269
-EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
+struct SatResult { int winIdx, winSide, winK; double dmin; bool edgeBeats; V3 eAxis; int dir1, dir2; };
+// findFaceSAT 420-479 + findEdgeSAT 517-580 (threshold pre-divided by edgeBiasFactor 1.05), every axis in fp64; false = separated
+EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R) {
   // face SAT: convex1's groups then convex2's, strict improvement => first wins ties
-  int winIdx = -1, winSide = 1, winK = 0; double dmin = kMaxNumber;
+  R.winIdx = -1; R.winSide = 1; R.winK = 0; R.dmin = kMaxNumber;
   for (int side = 1; side <= 2; side++) {
     const Cvx& own = side == 1 ? c1 : c2;
     const Cvx& other = side == 1 ? c2 : c1;
@@ -401,15 +444,14 @@ EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa
       face_extent(axis, own, k, omn, omx);
       project_convex(axis, other, pmn, pmx);
       bool ok = side == 1 ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist);
-      if (!ok) return;
-      if (dist - dmin < 0) { winIdx = nextIdx; winSide = side; winK = k; dmin = dist; }
+      if (!ok) return false;
+      if (dist - R.dmin < 0) { R.winIdx = nextIdx; R.winSide = side; R.winK = k; R.dmin = dist; }
       nextIdx += own.gi(k)[0] != 0 ? 2 : 1;
     }
   }
-  if (winIdx == -1) return;
-  // edge SAT, threshold pre-divided by edgeBiasFactor 1.05
-  bool edgeBeats = false; V3 eAxis = mk(0, 0, 0); int dir1 = 0, dir2 = 0;
-  double emin_ = dmin / 1.05;
+  if (R.winIdx == -1) return false;
+  R.edgeBeats = false; R.eAxis = mk(0, 0, 0); R.dir1 = 0; R.dir2 = 0;
+  double emin_ = R.dmin / 1.05;
   for (int a = 0; a < c1.ne; a++) {
     int n1; const int* e1 = c1.edges(a, n1);
     if (n1 < 2) continue;
@@ -424,10 +466,104 @@ EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa
       double mn1, mx1, mn2, mx2, dist;
       project_convex(n, c1, mn1, mx1);
       project_convex(n, c2, mn2, mx2);
-      if (!overlap(mn1, mx1, mn2, mx2, dist)) return;       // EdgeSeparates
-      if (dist - emin_ < 0) { edgeBeats = true; eAxis = n; dir1 = a + 1; dir2 = b + 1; emin_ = dist; }
+      if (!overlap(mn1, mx1, mn2, mx2, dist)) return false;       // EdgeSeparates
+      if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
     }
   }
+  return true;
+}
+// The same verdict and the same winners with the axes screened in fp32 first (see above).  For two non-box hulls of at most
+// kScrVerts vertices, 32 face groups and 8 x 8 edge directions.
+EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R) {
+  const V3 so = c1.pos();
+  Scr s1, s2; double sD = 0;
+  scr_build(s1, c1, so, sD); scr_build(s2, c2, so, sD);
+  const double sE = kScrE * sD + 1.0e-15 * (eabs(so.x) + eabs(so.y) + eabs(so.z)) + 1.0e-12;
+  // ---- face axes, pass 1: axis j = group k of convex1 (j = k) or of convex2 (j = ng1 + k)
+  unsigned fmask = 0; double thr = kMaxNumber;
+  for (int j = 0; j < c1.ng + c2.ng; j++) {
+    const bool first = j < c1.ng;
+    const Cvx& own = first ? c1 : c2;
+    const int k = first ? j : j - c1.ng;
+    const V3 axis = ld3(own.gf(k));
+    double omn, omx;
+    face_extent(axis, own, k, omn, omx);
+    float lo, hi; scr_project(first ? s2 : s1, axis, lo, hi);
+    const double on = vdot(axis, so);
+    const double a = omx - ((double)lo + on), b = ((double)hi + on) - omn;
+    const double est = (a - b > 0) ? b : a;
+    if (!(est - sE > thr)) fmask |= 1u << j;
+    if (est + sE < thr) thr = est + sE;
+  }
+  // ---- face axes, pass 2: the survivors in fp64, ascending j = the reference's order
+  R.winIdx = -1; R.winSide = 1; R.winK = 0; R.dmin = kMaxNumber;
+  while (fmask) {
+    const int j = __ffs(fmask) - 1; fmask &= fmask - 1;
+    const bool first = j < c1.ng;
+    const Cvx& own = first ? c1 : c2;
+    const Cvx& other = first ? c2 : c1;
+    const int k = first ? j : j - c1.ng;
+    int idx = 1;
+    for (int q = 0; q < k; q++) idx += own.gi(q)[0] != 0 ? 2 : 1;
+    const V3 axis = ld3(own.gf(k));
+    double omn, omx, pmn, pmx, dist;
+    face_extent(axis, own, k, omn, omx);
+    project_convex(axis, other, pmn, pmx);
+    const bool ok = first ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist);
+    if (!ok) return false;
+    if (dist - R.dmin < 0) { R.winIdx = idx; R.winSide = first ? 1 : 2; R.winK = k; R.dmin = dist; }
+  }
+  if (R.winIdx == -1) return false;
+  // ---- edge axes, pass 1: axis e = a * ne2 + b
+  R.edgeBeats = false; R.eAxis = mk(0, 0, 0); R.dir1 = 0; R.dir2 = 0;
+  double emin_ = R.dmin / 1.05;
+  double d2s[3 * 8]; unsigned ok2 = 0;
+  for (int b = 0; b < c2.ne; b++) {
+    int n2; const int* e2 = c2.edges(b, n2);
+    if (n2 < 2) continue;
+    const V3 d2 = vdirection(c2.vert(e2[0]), c2.vert(e2[1]));
+    d2s[3 * b] = d2.x; d2s[3 * b + 1] = d2.y; d2s[3 * b + 2] = d2.z; ok2 |= 1u << b;
+  }
+  unsigned long long emask = 0; thr = emin_;
+  for (int a = 0; a < c1.ne; a++) {
+    int n1; const int* e1 = c1.edges(a, n1);
+    if (n1 < 2) continue;
+    const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
+    for (int b = 0; b < c2.ne; b++) {
+      if (!((ok2 >> b) & 1u)) continue;
+      const V3 cr = vcross(d1, mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2]));
+      if (valmost0(cr)) continue;
+      const V3 n = vnormalize(cr);
+      float lo1, hi1, lo2, hi2; scr_project(s1, n, lo1, hi1); scr_project(s2, n, lo2, hi2);
+      const double x = (double)hi1 - (double)lo2, y = (double)hi2 - (double)lo1;
+      const double est = (x - y > 0) ? y : x;
+      if (!(est - 2 * sE > thr)) emask |= 1ull << (a * c2.ne + b);
+      if (est + 2 * sE < thr) thr = est + 2 * sE;
+    }
+  }
+  // ---- edge axes, pass 2
+  while (emask) {
+    const int e = __ffsll((long long)emask) - 1; emask &= emask - 1;
+    const int a = e / c2.ne, b = e - a * c2.ne;
+    int n1; const int* e1 = c1.edges(a, n1);
+    const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
+    const V3 n = vnormalize(vcross(d1, mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2])));
+    double mn1, mx1, mn2, mx2, dist;
+    project_convex(n, c1, mn1, mx1);
+    project_convex(n, c2, mn2, mx2);
+    if (!overlap(mn1, mx1, mn2, mx2, dist)) return false;       // EdgeSeparates
+    if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
+  }
+  return true;
+}
+// addContacts 40-63 with dispatchBestFaces 69-114, clipTwoFaces 204-269
+EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
+  SatResult R;
+  const bool screened = !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
+                        c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
+  if (!(screened ? convex_sat_screened(c1, c2, R) : convex_sat(c1, c2, R))) return;
+  const int winIdx = R.winIdx, winSide = R.winSide, winK = R.winK, dir1 = R.dir1, dir2 = R.dir2;
+  const bool edgeBeats = R.edgeBeats; const V3 eAxis = R.eAxis;
   if (edgeBeats) {   // addEdgeContact 148-169
     V3 sep = orient_axis(c1, c2, eAxis), rev = vneg(sep);
     int n1, n2; const int* e1 = c1.edges(dir1 - 1, n1); const int* e2 = c2.edges(dir2 - 1, n2);
@@ -552,6 +688,8 @@ EPD void capsule_convex(bool flip, const Cap& cap, const Cvx& c, ContactSink& ou
   V3 ep1 = mk(cap.pos.x - cap.h * cap.axis.x, cap.pos.y - cap.h * cap.axis.y, cap.pos.z - cap.h * cap.axis.z);
   V3 ep2 = mk(cap.pos.x + cap.h * cap.axis.x, cap.pos.y + cap.h * cap.axis.y, cap.pos.z + cap.h * cap.axis.z);
   // findSeparatingAxis 494-572: group normals, then closest-point axes of every unique edge
+  // (screening these axes in fp32 like convex_sat_screened was measured SLOWER: forming an edge's axis -- closest points
+  // of two segments -- costs as much as projecting the hull on it, and the two passes form every axis twice)
   V3 target = mk(0, 0, 0); double dmin = kMaxNumber;
   for (int k = 0; k < c.ng; k++) {
     V3 n = ld3(c.gf(k)); double dist;
