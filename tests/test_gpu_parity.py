@@ -92,6 +92,36 @@ def test_batched_mixed_worlds_resident(engine, oracle):
     assert og.n_contacts > 48 * 20
 
 
+def test_mixed_worlds_far_from_the_origin(engine, oracle):
+    """The same piles 20 km away from the origin (translated in x / y; the floor plane is z = 0): the fp32 screening of the
+    SAT axes works on vertices relative to the pair, so large coordinates must neither break its bound nor change any
+    result -- bit-exact against the oracle, and cylinder-cylinder contacts (the screened path) do occur."""
+    shapes, bodies, params = scenes.mixed_worlds(12)
+    bodies.pos[:, 0] += 20000.0
+    bodies.pos[:, 1] -= 12345.678
+    _, _, _, og = H.resident_vs_oracle(oracle, engine, shapes, bodies, params, 200, what="far c3x12")
+    assert og.n_contacts > 12 * 20
+
+
+def test_cylinder_ties_lockstep(engine, oracle):
+    """Hull-hull configurations with exactly tied SAT axes (the screened path must keep the reference's first-wins order):
+    a coaxial tower of cylinders at exact rest (cap on cap: every side-face axis ties), two parallel cylinders lying side by
+    side, a cylinder across another at a right angle, cone on cylinder; 240 frames in lock step."""
+    import math
+    bodies = [("floor", P.plane(P.wood))]
+    for k in range(4):
+        bodies.append((f"tower{k}", P.move_to((0.0, 0.0, 0.5 + k * 1.0), P.cylinder(0.5, 1.0, P.wood))))
+    lying = P.rotate_around((0, 0, 0), (0, 1, 0), math.pi / 2, P.cylinder(0.5, 1.0, P.steel))
+    bodies.append(("lie0", P.move_to((3.0, 0.0, 0.5), lying)))
+    bodies.append(("lie1", P.move_to((3.0, 1.0, 0.5), lying)))
+    bodies.append(("cross", P.move_to((3.0, 0.5, 1.5), P.rotate_around((0, 0, 0), (1, 0, 0), math.pi / 2, P.cylinder(0.4, 1.6, P.rubber)))))
+    bodies.append(("base", P.move_to((-3.0, 0.0, 0.5), P.cylinder(0.6, 1.0, P.wood))))
+    bodies.append(("cone", P.move_to((-3.0, 0.0, 1.5), P.cone(0.5, 1.0, P.plastic))))
+    with_ids, _ = P.assign_ids(bodies)
+    shapes, b, params = _packed([(P.on_earth(), with_ids)])
+    H.lockstep(oracle, engine, shapes, b, params, 240, check_every=1, what="cylinder ties")
+
+
 def test_batch_equals_single_worlds(engine):
     """Worlds are independent (src/Physics.elm:522-525): a world stepped inside a batch equals the same world
     stepped alone, bit for bit — the property the multi-GPU sharding relies on."""
