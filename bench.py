@@ -437,10 +437,11 @@ def main():
                    "l2": "resident state (bodies + contacts + rows) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": args.e2e_steps,
-                "call": "ep_step_frame(pinned host buffers): H2D of every per-body array, one step warm-started by the resident "
-                        "previous frame, D2H of the integrated state + the contact data Physics.contactPoints reads (pair ids, "
-                        "pre-step body1 frames, contact points); the batch is driven as %d contexts from %d host threads so "
-                        "that copies and steps of different sub-batches overlap" % (K, K),
+                "call": "ep_step_frame(pinned host buffers): H2D of every per-body array (the bulk of it beside the front kernels), "
+                        "one step warm-started by the resident previous frame, D2H of the integrated state + the contact data "
+                        "Physics.contactPoints reads (pair ids, pre-step body1 frames, contact points; marshalled and copied "
+                        "beside the solver); the batch is driven as %d contexts from %d host threads so that copies and steps "
+                        "of different sub-batches overlap" % (K, K),
                 "contexts": K, "all_contact_arrays_value": e2e_full, "all_contact_arrays_d2h_bytes_per_step": int(d2h_full),
                 "single_context_all_arrays_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
         "gpu_launches": int(launches), "ms_per_step_with_per_kernel_events": ms_profiled / args.steps,

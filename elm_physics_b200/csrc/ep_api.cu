@@ -48,6 +48,10 @@ struct ep_ctx {
   static constexpr int kAux = 8;                   // side streams of the solver's concurrent launches
   cudaStream_t aux[kAux] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
+  // ep_step_frame's copy streams: the bulk of the H2D runs beside the front kernels, the contact read-back beside the solver
+  cudaStream_t cin = nullptr, cout = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_mid = nullptr, ev_out_done = nullptr;
+  bool hook_wait_in = false, hook_early_out = false;     // set by ep_step_frame around its one step
   int tile_grid[kTileBins] = {0, 0, 0, 0};
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
@@ -120,6 +124,9 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->cin, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->cout, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->ev_out_done, cudaEventDisableTiming) == cudaSuccess;
   // side streams in launch order of the solver (longest class first): earlier ones get the higher priority so that the
   // long tiles are scheduled onto SMs before the short ones fill them
   int prio_lo = 0, prio_hi = 0;
@@ -162,6 +169,11 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < ep_ctx::kAux; i++) { if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->cin) { cudaStreamSynchronize(ctx->cin); cudaStreamDestroy(ctx->cin); }
+  if (ctx->cout) { cudaStreamSynchronize(ctx->cout); cudaStreamDestroy(ctx->cout); }
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+  if (ctx->ev_out_done) cudaEventDestroy(ctx->ev_out_done);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -562,6 +574,8 @@ extern "C" const char* ep_kernel_name(int32_t k) {
   return (k >= 0 && k < EP_K_COUNT) ? names[k] : "";
 }
 
+static void launch_out_kernels(ep_ctx* ctx, const FrameBuf& f, cudaStream_t sx, int early);
+
 extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   if (!ctx || n_steps < 0) return EP_EINVAL;
   if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
@@ -600,6 +614,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       // warp per small world, latency-bound) goes first on the main stream with a grid that leaves CTA slots and registers
       // free, the heavy one (equations, 168 registers) on a side stream beside it.
       static const int isl_per_sm = getenv("EP_ISL_CTAS") ? atoi(getenv("EP_ISL_CTAS")) : 12;
+      if (ctx->hook_wait_in) CK(cudaStreamWaitEvent(st, ctx->ev_in, 0));     // velocities, forces, masses: first read by k_equations
       { Timed t(ctx, EP_K_ISLANDS);        // brackets k_slot_counts + k_islands + k_island_sort
         k_slot_counts<<<grid_for(ctx, d.slot_cap, 256, 8), 256, 0, st>>>(d);
         CK(cudaEventRecord(ctx->ev_fork, st));
@@ -615,6 +630,12 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         if (d.n_constraints > 0) { k_joint_equations<<<gwide, 128, 0, ctx->aux[0]>>>(d); ctx->launches++; } }
       CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
       CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+      if (ctx->hook_early_out) {     // the frame's pair groups and contacts are complete: marshal them beside the solver
+        CK(cudaEventRecord(ctx->ev_mid, st));
+        CK(cudaStreamWaitEvent(ctx->cout, ctx->ev_mid, 0));
+        launch_out_kernels(ctx, d.cur, ctx->cout, 1);
+        CK(cudaEventRecord(ctx->ev_out_done, ctx->cout));
+      }
       { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
     }
     {   // islands by size class, all launches concurrent: classes 0..3 lane-per-island from shared-memory tiles, 4..6 one warp
@@ -657,6 +678,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       { Timed tt(ctx, EP_K_SOLVE_LANES_INPLACE, st); k_solve_lanes<0><<<std::min(ctx->lanes_grid, tiles_cap / 4 + 1), 128, 0, st>>>(d, 0, kLaneBinMax); }
       for (int i = 0; i < ax; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }
+    if (ctx->hook_early_out) CK(cudaStreamWaitEvent(st, ctx->ev_out_done, 0));     // k_out_groups reads the pre-step transforms
     { Timed t(ctx, EP_K_INTEGRATE); k_integrate<<<grid_for(ctx, d.n_bodies, 256, 16), 256, 0, st>>>(d); }
     CK(cudaGetLastError());
     std::swap(d.cur, d.prev);     // the frame just computed becomes the warm-start cache
@@ -700,17 +722,20 @@ extern "C" int ep_download_bodies(ep_ctx* ctx, ep_bodies* B) {
   return check_flags(ctx);
 }
 
-// Compact the last computed frame on the device and copy it into the caller's ep_contacts (one D2H per array).
-static int download_contacts_async(ep_ctx* ctx, ep_contacts* out) {
+// Compact a frame on the device into the layout of ep_contacts (ep_output.cuh)
+static void launch_out_kernels(ep_ctx* ctx, const FrameBuf& f, cudaStream_t sx, int early) {
   const Dev& d = ctx->d;
-  const FrameBuf& f = d.prev;     // last computed frame
-  cudaStream_t st = ctx->stream;
   const int nw = d.n_worlds;
-  k_out_count<<<grid_for(ctx, (int64_t)nw * 32, 128, 16), 128, 0, st>>>(d, f);
-  k_out_scan<<<1, 1024, 0, st>>>(d);
-  k_out_groups<<<grid_for(ctx, (int64_t)nw * 32, 128, 16), 128, 0, st>>>(d, f);
-  k_out_contacts<<<grid_for(ctx, d.contact_cap, 256, 8), 256, 0, st>>>(d, f);
-  CK(cudaGetLastError());
+  k_out_count<<<grid_for(ctx, (int64_t)nw * 32, 128, 16), 128, 0, sx>>>(d, f);
+  k_out_scan<<<1, 1024, 0, sx>>>(d);
+  k_out_groups<<<grid_for(ctx, (int64_t)nw * 32, 128, 16), 128, 0, sx>>>(d, f, early);
+  k_out_contacts<<<grid_for(ctx, d.contact_cap, 256, 8), 256, 0, sx>>>(d, f, early);
+  ctx->launches += 4;
+}
+// ... and copy it into the caller's ep_contacts (one D2H per array the caller holds) on stream sx
+static int copy_out_contacts(ep_ctx* ctx, const FrameBuf& f, ep_contacts* out, cudaStream_t st) {
+  const Dev& d = ctx->d;
+  const int nw = d.n_worlds;
   int32_t tot[2], cnt[CNT_COUNT];
   CK(cudaMemcpyAsync(tot, d.out.totals, sizeof tot, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
@@ -735,8 +760,13 @@ static int download_contacts_async(ep_ctx* ctx, ep_contacts* out) {
   if (e != cudaSuccess) { ctx->err = std::string("download: ") + cudaGetErrorString(e); return EP_ECUDA; }
   ctx->stats[EP_STAT_CANDIDATE_PAIRS] = cnt[CNT_CAND]; ctx->stats[EP_STAT_GROUPS] = (int64_t)ng; ctx->stats[EP_STAT_CONTACTS] = (int64_t)nc;
   ctx->stats[EP_STAT_ISLANDS] = cnt[CNT_ISLANDS];
-  ctx->launches += 4;
   return EP_OK;
+}
+// Compact the last computed frame on the device and copy it into the caller's ep_contacts (one D2H per array).
+static int download_contacts_async(ep_ctx* ctx, ep_contacts* out) {
+  launch_out_kernels(ctx, ctx->d.prev, ctx->stream, 0);
+  CK(cudaGetLastError());
+  return copy_out_contacts(ctx, ctx->d.prev, out, ctx->stream);
 }
 
 extern "C" int ep_download_contacts(ep_ctx* ctx, ep_contacts* out) {
@@ -771,17 +801,29 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
   cudaStream_t st = ctx->stream;
   const size_t nb = d.n_bodies;
   if (nb == 0) return EP_OK;
-  auto H2D = [&](const double* dst, const double* src, size_t n) { return cudaMemcpyAsync((void*)dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st); };
-  CK(H2D(d.pos, B->pos, 3 * nb)); CK(H2D(d.quat, B->quat, 4 * nb)); CK(H2D(d.vel, B->vel, 3 * nb)); CK(H2D(d.angvel, B->angvel, 3 * nb));
-  CK(H2D(d.force, B->force, 3 * nb)); CK(H2D(d.torque, B->torque, 3 * nb)); CK(H2D(d.iiw, B->inv_inertia_world, 9 * nb));
-  CK(H2D(d.inv_mass, B->inv_mass, nb)); CK(H2D(d.inv_inertia, B->inv_inertia, 3 * nb)); CK(H2D(d.ldp, B->lin_damp_pow, nb)); CK(H2D(d.adp, B->ang_damp_pow, nb));
-  CK(H2D(d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(d.ang_lock, B->ang_lock, 3 * nb)); CK(H2D(d.radius, B->bounding_radius, nb));
+  // The frame as a pipeline over three streams (EP_FRAME_PIPELINE=0: everything on the main stream):
+  //   main     H2D of what the front kernels read (pos, quat, bounding radius) | place .. narrowphase | rows, islands | solver | integrate | D2H of the state
+  //   copy-in  H2D of everything else (80 % of the bytes), awaited by the first kernel that reads it (k_equations)
+  //   copy-out when the caller does not ask for solver results in `out` (lambda, t1, iterations, world_n_islands NULL: all
+  //            that Physics.contactPoints needs is known once the rows are built): marshalling + D2H of the contacts beside the solver
+  static const bool pipelined = !(getenv("EP_FRAME_PIPELINE") && atoi(getenv("EP_FRAME_PIPELINE")) == 0);
+  const bool early_out = pipelined && out && !out->lambda && !out->t1 && !out->iterations && !out->world_n_islands;
+  cudaStream_t sin = pipelined ? ctx->cin : st;
+  auto H2D = [&](cudaStream_t sx, const double* dst, const double* src, size_t n) { return cudaMemcpyAsync((void*)dst, src, n * sizeof(double), cudaMemcpyHostToDevice, sx); };
+  CK(H2D(st, d.pos, B->pos, 3 * nb)); CK(H2D(st, d.quat, B->quat, 4 * nb)); CK(H2D(st, d.radius, B->bounding_radius, nb));
+  CK(H2D(sin, d.vel, B->vel, 3 * nb)); CK(H2D(sin, d.angvel, B->angvel, 3 * nb));
+  CK(H2D(sin, d.force, B->force, 3 * nb)); CK(H2D(sin, d.torque, B->torque, 3 * nb)); CK(H2D(sin, d.iiw, B->inv_inertia_world, 9 * nb));
+  CK(H2D(sin, d.inv_mass, B->inv_mass, nb)); CK(H2D(sin, d.inv_inertia, B->inv_inertia, 3 * nb)); CK(H2D(sin, d.ldp, B->lin_damp_pow, nb)); CK(H2D(sin, d.adp, B->ang_damp_pow, nb));
+  CK(H2D(sin, d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(sin, d.ang_lock, B->ang_lock, 3 * nb));
+  if (pipelined) CK(cudaEventRecord(ctx->ev_in, ctx->cin));
   {
-    // Several contexts on one device (sub-batches driven from their own host threads) take turns on the SMs: the step of a
-    // context waits for the step of the context before it, so that it runs beside the OTHER contexts' copies instead of
-    // beside their steps.  Left alone the contexts fall into lock step -- all stepping (sharing the SMs), then all copying
-    // (sharing PCIe) -- and nothing overlaps: measured 5.1 ms per frame for 2 x 4096 worlds instead of 3.9.
-    static const bool gated = !(getenv("EP_FRAME_GATE") && atoi(getenv("EP_FRAME_GATE")) == 0);
+    // Several contexts on one device (sub-batches driven from their own host threads) take turns on the SMs when the
+    // contact read-back FOLLOWS the step: the step of a context waits for the step of the context before it, so that it
+    // runs beside the other contexts' copies instead of beside their steps (left alone the contexts fall into lock step --
+    // all stepping, then all copying -- measured 49.6 -> 56.0 M body-steps/s for 2 x 4096 worlds).  When the read-back
+    // already runs beside the frame's own solver the gate only serialises: 68.1 M without, 59.5 M with.
+    static const int gate_env = getenv("EP_FRAME_GATE") ? atoi(getenv("EP_FRAME_GATE")) : -1;
+    const bool gated = gate_env < 0 ? !early_out : gate_env != 0;
     FrameGate& g = frame_gate(ctx->device);
     std::unique_lock<std::mutex> lock(g.mu, std::defer_lock);
     if (gated) {
@@ -791,7 +833,10 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
     }
     // static bodies may have been moved by the caller between frames: place every shape, not only the moving ones
     if (d.n_pl_all > d.n_pl_moving) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
-    TRY(ep_step_resident(ctx, 1));
+    ctx->hook_wait_in = pipelined; ctx->hook_early_out = early_out;
+    const int rc = ep_step_resident(ctx, 1);
+    ctx->hook_wait_in = false; ctx->hook_early_out = false;
+    if (rc != EP_OK) return rc;
     if (gated) CK(cudaEventRecord(g.ev, st));
   }
   CK(cudaMemcpyAsync(B->pos, d.pos, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -801,7 +846,12 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
   CK(cudaMemcpyAsync(B->force, d.force, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(B->torque, d.torque, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(B->inv_inertia_world, d.iiw, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (out) TRY(download_contacts_async(ctx, out));
+  if (out) {
+    if (early_out) {       // marshalled in the middle of the step on the copy-out stream (the frame is d.prev by now)
+      TRY(copy_out_contacts(ctx, d.prev, out, ctx->cout));
+      CK(cudaStreamSynchronize(ctx->cout));
+    } else TRY(download_contacts_async(ctx, out));
+  }
   return check_flags(ctx);
 }
 

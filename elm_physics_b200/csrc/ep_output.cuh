@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(1024) k_out_scan(Dev d) {
 }
 
 // one warp per world: group records in enumeration order + the slot -> group map
-__global__ void __launch_bounds__(128) k_out_groups(Dev d, FrameBuf f) {
+// early != 0: launched in the middle of the step (after the rows, beside the solver): the pre-step transform of body1 is the
+// CURRENT one and the per-world solver results do not exist yet (the caller does not read them)
+__global__ void __launch_bounds__(128) k_out_groups(Dev d, FrameBuf f, int early) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   if (d.out.totals[0] > d.out.group_cap) return;
@@ -82,14 +84,14 @@ __global__ void __launch_bounds__(128) k_out_groups(Dev d, FrameBuf f) {
           d.out.group_island[gi] = root >= 0 ? d.body_id[root] : -1;
           d.out.group_contact_off[gi] = c + scan - cv;
 #pragma unroll
-          for (int k = 0; k < 3; k++) d.out.group_pre_pos1[3 * (size_t)gi + k] = d.pre_pos[3 * (size_t)r1 + k];
+          for (int k = 0; k < 3; k++) d.out.group_pre_pos1[3 * (size_t)gi + k] = (early ? d.pos : d.pre_pos)[3 * (size_t)r1 + k];
 #pragma unroll
-          for (int k = 0; k < 4; k++) d.out.group_pre_quat1[4 * (size_t)gi + k] = d.pre_quat[4 * (size_t)r1 + k];
+          for (int k = 0; k < 4; k++) d.out.group_pre_quat1[4 * (size_t)gi + k] = (early ? d.quat : d.pre_quat)[4 * (size_t)r1 + k];
         }
       }
       g += __popc(bal); c += tot;
     }
-    if (lane == 0) {
+    if (lane == 0 && !early) {
       const int nbw = d.world_body_off[w + 1] - d.world_body_off[w];
       const int used = d.iterations[w] - d.world_min_rem[w];
       d.out.iterations[w] = nbw == 0 ? 0 : (1 - used > 0 ? 1 : used);      // Solver.elm:225-231, 275-276
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(128) k_out_groups(Dev d, FrameBuf f) {
 }
 
 // one thread per contact of the frame
-__global__ void __launch_bounds__(256) k_out_contacts(Dev d, FrameBuf f) {
+// early != 0: the solver is still running on the rows: lambda / t1 are not exported (the caller does not read them)
+__global__ void __launch_bounds__(256) k_out_contacts(Dev d, FrameBuf f, int early) {
   if (d.out.totals[0] > d.out.group_cap || d.out.totals[1] > d.out.contact_cap) return;
   const int n = min(f.counters[CNT_CONTACTS], d.contact_cap);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(256) k_out_contacts(Dev d, FrameBuf f) {
 #pragma unroll
     for (int k = 0; k < 3; k++) { d.out.ni[3 * o + k] = r.ni[k]; d.out.pi[3 * o + k] = r.pi[k]; d.out.pj[3 * o + k] = r.pj[k]; }
     d.out.friction[o] = r.friction; d.out.bounciness[o] = r.bounciness;
+    if (early) continue;
     const RowRec& row = f.rows[c];
     d.out.lambda[o] = row.lamN;
     d.out.t1[3 * o] = row.f1J[3]; d.out.t1[3 * o + 1] = row.f1J[4]; d.out.t1[3 * o + 2] = row.f1J[5];
