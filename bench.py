@@ -484,7 +484,7 @@ def main():
             tops = (270.0 * ci + 90.0 * ji) / (ktimes["k_solve"][0] * 1e-3) / 1e12
             line["roofline_fp64"] = {"kernel": "k_solve", "achieved": tops, "peak": fp64_peak, "unit": "T fp64 op/s (no FMA)",
                                      "frac": tops / fp64_peak, "contact_iterations_per_step": ci / args.steps,
-                                     "mean_iterations_per_contact": ci / max(1.0, args.steps * c["contacts"]),
+                                     "mean_iterations_per_contact": ci / max(1.0, args.steps * 0.5 * (counts_p0["contacts"] + counts_prof["contacts"])),
                                      "peak_source": "tools/fp64_peak.cu measured on this pool's B200 (profiles/r01_fp64_peak.json)"}
         line["kernels"] = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1], "share": v[0] / total_k if total_k else None,
                                "algorithmic_GBps": kernel_bytes(k, c) / (max(v[0], 1e-9) / max(v[1], 1) * 1e-3) / 1e9}
