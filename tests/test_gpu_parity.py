@@ -311,6 +311,33 @@ def test_step_frame_contact_points_fields_only(engine):
         assert getattr(ol, name)[:n].tobytes() == getattr(of, name)[:n].tobytes(), name
 
 
+def test_contact_pool_overflow_is_reported_not_fatal():
+    """A contact pool that is too small (ep_configure) is reported as EP_ECAPACITY by ep_sync / the downloads -- never a
+    crash, never silently -- and the context keeps working after it is given room again."""
+    from elm_physics_b200 import engine as eng
+    e = eng.Engine(0)
+    try:
+        shapes, bodies, params = scenes.mixed_worlds(8)
+        e.upload_shapes(shapes)
+        e.configure(contact_cap=64)
+        e.upload_worlds(bodies.copy(), params, None)
+        e.step_resident(150)                         # the pile needs ~600 contacts
+        with pytest.raises(eng.EngineError, match="overflow"):
+            e.sync()
+        with pytest.raises(eng.EngineError):
+            e.download_contacts(H.contacts_for(bodies))
+        e.configure(contact_cap=1 << 16)
+        b = bodies.copy()
+        e.upload_worlds(b, params, None)
+        e.step_resident(150)
+        e.sync()
+        out = H.contacts_for(bodies)
+        e.download_contacts(out)
+        assert out.n_contacts > 64
+    finally:
+        e.close()
+
+
 def test_python_simulate_mirror(engine):
     """The host-side mirror of Physics.simulate (physics.simulate) steps the README scene like the reference's
     own doc example: contacts fed back, ball ends on the floor; contactPoints reports the touching point."""
