@@ -226,6 +226,27 @@ def emit(line):
     _REAL_STDOUT.flush()
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Run this rank (and the pinned buffers it allocates: first touch) on the CPUs next to its GPU, so that the host<->device
+    copies of an 8-GPU box do not cross the socket interconnect.  Best effort; EP_BENCH_NO_BIND=1 disables."""
+    if os.environ.get("EP_BENCH_NO_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -255,6 +276,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world_size > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line

@@ -52,6 +52,7 @@ struct ep_ctx {
   cudaStream_t cin = nullptr, cout = nullptr;
   cudaEvent_t ev_in = nullptr, ev_mid = nullptr, ev_out_done = nullptr;
   bool hook_wait_in = false, hook_early_out = false;     // set by ep_step_frame around its one step
+  cudaEvent_t ev_block = nullptr;                        // blocking-sync event of wait_stream
   int tile_grid[kTileBins] = {0, 0, 0, 0};
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
@@ -172,6 +173,7 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   if (ctx->cin) { cudaStreamSynchronize(ctx->cin); cudaStreamDestroy(ctx->cin); }
   if (ctx->cout) { cudaStreamSynchronize(ctx->cout); cudaStreamDestroy(ctx->cout); }
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
   if (ctx->ev_out_done) cudaEventDestroy(ctx->ev_out_done);
   cudaStreamDestroy(ctx->stream);
@@ -686,10 +688,21 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   return EP_OK;
 }
 
+// Wait for a stream without spinning a host core (EP_BLOCKING_SYNC=0: spin): a host that drives one context per GPU of an
+// 8-GPU box from 2 threads each has as many waiting threads as cores.
+static int wait_stream(ep_ctx* ctx, cudaStream_t sx) {
+  static const bool blocking = !(getenv("EP_BLOCKING_SYNC") && atoi(getenv("EP_BLOCKING_SYNC")) == 0);
+  if (!blocking) { CK(cudaStreamSynchronize(sx)); return EP_OK; }
+  if (!ctx->ev_block) CK(cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+  CK(cudaEventRecord(ctx->ev_block, sx));
+  CK(cudaEventSynchronize(ctx->ev_block));
+  return EP_OK;
+}
+
 static int check_flags(ep_ctx* ctx) {
   int32_t fl[FLAG_COUNT];
   CK(cudaMemcpyAsync(fl, ctx->d.flags, sizeof fl, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  TRY(wait_stream(ctx, ctx->stream));
   if (fl[FLAG_POOL_OVERFLOW]) { ctx->err = "contact pool overflow (raise EP_CONTACT_CAP)"; return EP_ECAPACITY; }
   if (fl[FLAG_PAIR_OVERFLOW]) { ctx->err = "pair slot / per-pair contact buffer overflow"; return EP_ECAPACITY; }
   if (fl[FLAG_POLY_OVERFLOW]) { ctx->err = "clip polygon buffer overflow (face with too many vertices)"; return EP_ECAPACITY; }
@@ -739,7 +752,7 @@ static int copy_out_contacts(ep_ctx* ctx, const FrameBuf& f, ep_contacts* out, c
   int32_t tot[2], cnt[CNT_COUNT];
   CK(cudaMemcpyAsync(tot, d.out.totals, sizeof tot, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(cnt, f.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  TRY(wait_stream(ctx, st));
   const size_t ng = (size_t)tot[0], nc = (size_t)tot[1];
   if ((int64_t)ng > d.out.group_cap || (int64_t)nc > d.out.contact_cap) { ctx->err = "device contact image overflow"; return EP_ECAPACITY; }
   if ((int64_t)ng > out->group_cap || (int64_t)nc > out->contact_cap) { ctx->err = "ep_contacts capacity too small"; return EP_ECAPACITY; }
@@ -849,7 +862,7 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
   if (out) {
     if (early_out) {       // marshalled in the middle of the step on the copy-out stream (the frame is d.prev by now)
       TRY(copy_out_contacts(ctx, d.prev, out, ctx->cout));
-      CK(cudaStreamSynchronize(ctx->cout));
+      TRY(wait_stream(ctx, ctx->cout));
     } else TRY(download_contacts_async(ctx, out));
   }
   return check_flags(ctx);
