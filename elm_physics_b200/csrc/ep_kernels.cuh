@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls) {
   }
 }
 
-// ---- k_equations : one thread per pair group --------------------------------------------------------------
+// ---- k_slot_counts / k_equations / k_joint_equations : rows of every contact and constraint ---------------
 struct BodyK { int kind; double invMass; M33 I; };
 __device__ __forceinline__ BodyK load_bodyk(const Dev& d, int r) {
   BodyK b; b.kind = d.kind[r]; b.invMass = d.inv_mass[r];

@@ -208,7 +208,11 @@ int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_co
  * moved bodies between frames, src/Physics.elm:857-1017), one step with the resident contacts of the previous frame as
  * the warm start, D2H of the integrated state and (if `out` is not NULL) of the frame's contacts.  The topology (worlds,
  * body ids and kinds, shape instances, params, constraints) must be the one of the last ep_upload_worlds; use ep_step
- * when it changes or when the warm start is not the previous frame. */
+ * when it changes or when the warm start is not the previous frame.
+ * Pass pinned buffers (ep_host_alloc): the call is a pipeline over three streams -- the bulk of the input is copied in beside
+ * the front kernels, and when `out` asks for no solver result (lambda, t1, iterations, world_n_islands NULL) the frame's pair
+ * groups and contact points are marshalled and copied back beside the solver.  Synchronous: every buffer is complete on
+ * return.  Contexts of one device may be driven from different host threads concurrently (one thread per context). */
 int ep_step_frame(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out);
 
 /* `Physics.raycast` (src/Physics.elm:802-841) for a batch of rays against the RESIDENT worlds in their current state (after
