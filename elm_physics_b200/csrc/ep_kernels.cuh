@@ -68,6 +68,17 @@ __global__ void k_sort(Dev d) {
 
 // ---- k_broadphase -------------------------------------------------------------------------------------
 __device__ __forceinline__ void pair_from_index(int64_t p, int n, int& i, int& j) {
+  if (n <= 1024) {      // everything below is exact in fp32 / int32 (t*t, 8p < 2^23); the two loops fix a sqrt off by one
+    const int q = (int)p;
+    const float t = 2.0f * n - 1.0f;
+    int ii = (int)((t - sqrtf(t * t - 8.0f * (float)q)) * 0.5f);
+    if (ii < 0) ii = 0;
+    while (ii * n - ii * (ii + 1) / 2 > q) ii--;
+    while ((ii + 1) * n - (ii + 1) * (ii + 2) / 2 <= q) ii++;
+    i = ii;
+    j = q - (ii * n - ii * (ii + 1) / 2) + ii + 1;
+    return;
+  }
   double t = 2.0 * n - 1.0;
   int ii = (int)((t - sqrt(t * t - 8.0 * (double)p)) * 0.5);
   if (ii < 0) ii = 0;
