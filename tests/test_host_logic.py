@@ -85,3 +85,43 @@ def test_contacts_optional_fields():
         assert (getattr(lean, name) is not None) == held, name
     assert not lean.c.lambda_ if hasattr(lean.c, "lambda_") else True
     assert lean.nbytes_out() <= full.nbytes_out()
+
+
+# ---- tests/PlaceInTest.elm:20-119 (Physics.place / Physics.frame of the host-side mirror) -------------------
+def _frame_close(f, origin, x, y, z, tol=1e-12):
+    from elm_physics_b200 import math3d as m3
+    o, q = f
+    got = (o, m3.q_rotate(q, (1.0, 0.0, 0.0)), m3.q_rotate(q, (0.0, 1.0, 0.0)), m3.q_rotate(q, (0.0, 0.0, 1.0)))
+    for a, b in zip(got, (origin, x, y, z)):
+        assert all(abs(p - r) < tol for p, r in zip(a, b)), (got, (origin, x, y, z))
+
+
+def test_place_sets_position_and_orientation_and_overwrites_previous_moves():
+    import math
+    from elm_physics_b200 import physics as P
+    block = P.block((1.0, 1.0, 1.0), P.wood)
+    X, Y, Z = (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)
+    _frame_close(P.frame(P.place((0, 0, 0), X, Y, block)), (0, 0, 0), X, Y, Z)                 # place atOrigin is identity
+    _frame_close(P.frame(P.place((1, 2, 3), X, Y, block)), (1, 2, 3), X, Y, Z)                 # place sets position
+    rz = ((0.0, 1.0, 0.0), (-1.0, 0.0, 0.0))                                                    # rotateAround Axis3d.z 90 deg
+    _frame_close(P.frame(P.place((0, 0, 0), rz[0], rz[1], block)), (0, 0, 0), rz[0], rz[1], Z)
+    c, s = math.cos(math.pi / 4), math.sin(math.pi / 4)                                         # x axis, 45 deg, at (3, 4, 5)
+    _frame_close(P.frame(P.place((3, 4, 5), X, (0.0, c, s), block)), (3, 4, 5), X, (0.0, c, s), (0.0, -s, c))
+    moved = P.move_to((1, 2, 3), block)                                                         # place overwrites moveTo
+    _frame_close(P.frame(P.place((10, 0, 0), X, Y, moved)), (10, 0, 0), X, Y, Z)
+    turned = P.rotate_around((0, 0, 0), Z, math.pi / 2, block)                                  # ... and rotateAround
+    c30, s30 = math.cos(math.pi / 6), math.sin(math.pi / 6)
+    _frame_close(P.frame(P.place((0, 0, 0), (c30, 0.0, -s30), Y, turned)), (0, 0, 0), (c30, 0.0, -s30), Y, (s30, 0.0, c30))
+
+
+def test_place_roundtrips_with_frame():
+    import math
+    from elm_physics_b200 import math3d as m3, physics as P
+    block = P.block((1.0, 1.0, 1.0), P.wood)
+    moved = P.rotate_around((0, 0, 0), (0.0, 0.0, 1.0), math.pi / 4, P.move_to((1, 2, 3), block))
+    o, q = P.frame(moved)
+    x, y = m3.q_rotate(q, (1.0, 0.0, 0.0)), m3.q_rotate(q, (0.0, 1.0, 0.0))
+    o2, q2 = P.frame(P.place(o, x, y, block))
+    assert all(abs(a - b) < 1e-12 for a, b in zip(o, o2))
+    for axis in ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)):
+        assert all(abs(a - b) < 1e-12 for a, b in zip(m3.q_rotate(q, axis), m3.q_rotate(q2, axis)))

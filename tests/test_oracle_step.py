@@ -103,3 +103,30 @@ def test_distance_constraint_registered_on_the_later_body_keeps_its_length(oracl
         d = float(np.linalg.norm(bodies.pos[1] - bodies.pos[0]))
         assert abs(d - 1.0) < 0.05, (registrant, d)
         assert contacts.group_n_constraints[0] == 1
+
+
+# ---- tests/ConvexSphereSimTest.elm:32-50 -----------------------------------------------------------------
+def test_icosphere_body_bounces_off_the_floor_and_does_not_pass_through_the_cube(oracle):
+    """Floor at z = -1, a 2 m cube body (5 kg) dropped from z = 8 onto an icosphere body (5 kg, the 42-vertex mesh of
+    tests/ConvexSphereSimTest.elm:142-277) dropped from z = 5 at x = 0.3: over 200 frames the two centres never come closer
+    than 0.4 m (the sum of the half extents is ~2 m; deep penetration / tunnelling would be < 0.5)."""
+    import json
+    import os
+    mesh = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "icosphere.json")))
+    cube_v = [(1, 1, -1), (1, -1, -1), (1, 1, 1), (1, -1, 1), (-1, 1, -1), (-1, -1, -1), (-1, 1, 1), (-1, -1, 1)]
+    cube_f = [(0, 4, 6), (0, 6, 2), (3, 2, 6), (3, 6, 7), (7, 6, 4), (7, 4, 5), (5, 1, 3), (5, 3, 7), (1, 0, 2), (1, 2, 3),
+              (5, 4, 0), (5, 0, 1)]
+    cube = P.scale_mass_to(5.0, P.dynamic([(P.shape_unsafe_convex(cube_f, cube_v), P.wood)]))
+    ico = P.scale_mass_to(5.0, P.dynamic([(P.shape_unsafe_convex([tuple(f) for f in mesh["faces"]],
+                                                                 [tuple(v) for v in mesh["vertices"]]), P.wood)]))
+    bodies = [(0, P.move_to((0, 0, -1), P.plane(P.wood))), (1, P.move_to((0, 0, 8), cube)), (2, P.move_to((0.3, 0, 5), ico))]
+    with_ids, _ = P.assign_ids(bodies)
+    shapes, b, params = pack.pack_worlds([(P.on_earth(), with_ids)])
+    warm, min_dist = None, 1e9
+    for _ in range(200):
+        o = H.contacts_for(b)
+        oracle.step(shapes, b, params, warm, o, 1)
+        warm = o
+        min_dist = min(min_dist, float(np.linalg.norm(b.pos[1] - b.pos[2])))
+    assert min_dist > 0.4, f"min cube-ico centre distance was {min_dist} m (deep penetration / tunnelling)"
+    assert b.pos[2][2] > -1.0 and b.pos[1][2] > b.pos[2][2]        # the icosphere rests on the floor, the cube on top of it or beside
