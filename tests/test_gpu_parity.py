@@ -122,6 +122,25 @@ def test_cylinder_ties_lockstep(engine, oracle):
     H.lockstep(oracle, engine, shapes, b, params, 240, check_every=1, what="cylinder ties")
 
 
+def test_icosphere_and_cube_meshes_lockstep(engine, oracle):
+    """tests/ConvexSphereSimTest.elm's scene (a 42-vertex icosphere body and a cube given as a triangle mesh, both
+    `unsafeConvex`, over a floor) 200 frames in lock step: hulls beyond the screening limit take the exact SAT path."""
+    import json
+    import os
+    mesh = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "icosphere.json")))
+    cube_v = [(1, 1, -1), (1, -1, -1), (1, 1, 1), (1, -1, 1), (-1, 1, -1), (-1, -1, -1), (-1, 1, 1), (-1, -1, 1)]
+    cube_f = [(0, 4, 6), (0, 6, 2), (3, 2, 6), (3, 6, 7), (7, 6, 4), (7, 4, 5), (5, 1, 3), (5, 3, 7), (1, 0, 2), (1, 2, 3),
+              (5, 4, 0), (5, 0, 1)]
+    cube = P.scale_mass_to(5.0, P.dynamic([(P.shape_unsafe_convex(cube_f, cube_v), P.wood)]))
+    ico = P.scale_mass_to(5.0, P.dynamic([(P.shape_unsafe_convex([tuple(f) for f in mesh["faces"]],
+                                                                 [tuple(v) for v in mesh["vertices"]]), P.wood)]))
+    bodies = [(0, P.move_to((0, 0, -1), P.plane(P.wood))), (1, P.move_to((0, 0, 8), cube)), (2, P.move_to((0.3, 0, 5), ico)),
+              (3, P.move_to((0.2, 0.1, 11), cube)), (4, P.move_to((2.5, 0.3, 3), cube))]
+    with_ids, _ = P.assign_ids(bodies)
+    shapes, b, params = _packed([(P.on_earth(), with_ids)])
+    H.lockstep(oracle, engine, shapes, b, params, 200, check_every=1, what="icosphere + cube meshes")
+
+
 def test_batch_equals_single_worlds(engine):
     """Worlds are independent (src/Physics.elm:522-525): a world stepped inside a batch equals the same world
     stepped alone, bit for bit — the property the multi-GPU sharding relies on."""
