@@ -125,3 +125,53 @@ def test_place_roundtrips_with_frame():
     assert all(abs(a - b) < 1e-12 for a, b in zip(o, o2))
     for axis in ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)):
         assert all(abs(a - b) < 1e-12 for a, b in zip(m3.q_rotate(q, axis), m3.q_rotate(q2, axis)))
+
+
+# ---- tests/BodyTest.elm:16-152 (Body.compound of the host-side mirror: the bodies the C4 / C5 scenes are made of) --------
+def _mat(density=700.0, friction=0.0, bounciness=0.0):
+    from elm_physics_b200 import physics as P
+    return P.Material(friction=friction, bounciness=bounciness, density=density)
+
+
+def test_compound_bounding_sphere_radius():
+    from elm_physics_b200 import math3d as m3, physics as P, shapes as sh
+    box = lambda x, y, z: sh.from_block(x, y, z)
+    assert P.compound(2, []).bounding_sphere_radius == 0
+    r = P.compound(2, [(box(2, 2, 2), P.wood, 1)]).bounding_sphere_radius
+    assert abs(r - m3.length((1, 1, 1))) < 1e-5
+    r = P.compound(2, [(box(2, 2, 2), P.wood, 1), (box(4, 4, 4), P.wood, 1)]).bounding_sphere_radius
+    assert abs(r - m3.length((2, 2, 2))) < 1e-5
+    r = P.compound(2, [(sh.Plane(m3.ZERO, m3.Z_AXIS), P.wood, 1)]).bounding_sphere_radius
+    assert r >= 3.40282347e38
+
+
+def test_compound_inertia():
+    from elm_physics_b200 import math3d as m3, physics as P, shapes as sh
+    mat = _mat()
+    two = P.compound(2, [(sh.convex_place_in(m3.t_at_point((-1.0, 0.0, 0.0)), sh.from_block(2, 2, 2)), mat, 1),
+                         (sh.convex_place_in(m3.t_at_point((1.0, 0.0, 0.0)), sh.from_block(2, 2, 2)), mat, 1)])
+    one = P.compound(2, [(sh.from_block(4, 2, 2), mat, 1)])
+    assert sorted(round(v, 12) for v in two.inv_inertia) == sorted(round(v, 12) for v in one.inv_inertia)
+    lx, ly, lz = 1.0, 1.5, 0.5          # blockOfTetrahedrons 2 3 1, tests/Fixtures/Convex.elm:62-96
+    corners = [((lx, ly, -lz), (-lx, ly, lz), (lx, ly, lz)), ((lx, ly, -lz), (-lx, ly, -lz), (-lx, ly, lz)),
+               ((lx, -ly, lz), (-lx, ly, lz), (-lx, -ly, lz)), ((lx, -ly, lz), (lx, ly, lz), (-lx, ly, lz)),
+               ((-lx, -ly, lz), (-lx, ly, -lz), (-lx, -ly, -lz)), ((-lx, -ly, lz), (-lx, ly, lz), (-lx, ly, -lz)),
+               ((-lx, -ly, -lz), (lx, -ly, lz), (-lx, -ly, lz)), ((-lx, -ly, -lz), (lx, -ly, -lz), (lx, -ly, lz)),
+               ((lx, -ly, -lz), (lx, ly, lz), (lx, -ly, lz)), ((lx, -ly, -lz), (lx, ly, -lz), (lx, ly, lz)),
+               ((-lx, -ly, -lz), (lx, ly, -lz), (lx, -ly, -lz)), ((-lx, -ly, -lz), (-lx, ly, -lz), (lx, ly, -lz))]
+    tets = [sh.from_triangular_mesh([(1, 0, 2), (2, 0, 3), (3, 0, 1), (3, 1, 2)], [(0.0, 0.0, 0.0), p1, p2, p3])
+            for p1, p2, p3 in corners]
+    from_tets = P.compound(2, [(t, mat, 1) for t in tets])
+    block = P.compound(2, [(sh.from_block(2, 3, 1), mat, 1)])
+    for a, b in zip(sorted(from_tets.inv_inertia), sorted(block.inv_inertia)):
+        assert abs(a - b) <= 1e-9 * abs(b)
+
+
+def test_compound_volume_and_hollow_crate():
+    from elm_physics_b200 import physics as P, shapes as sh
+    assert abs(P.compound(2, [(sh.from_block(2, 3, 4), P.wood, 1)]).volume - 24) < 1e-5
+    hollow = P.compound(2, [(sh.from_block(1, 1, 1), P.wood, 1), (sh.from_block(0.8, 0.8, 0.8), P.wood, -1)])
+    assert abs(hollow.mass - 700 * (1 - 0.8 ** 3)) < 1e-3
+    assert abs(hollow.volume - (1 - 0.8 ** 3)) < 1e-5
+    expected = 6 / (700 * (1 - 0.8 ** 5))
+    assert abs(hollow.inv_inertia[0] - expected) <= 1e-4 * expected
