@@ -175,3 +175,79 @@ def test_compound_volume_and_hollow_crate():
     assert abs(hollow.volume - (1 - 0.8 ** 3)) < 1e-5
     expected = 6 / (700 * (1 - 0.8 ** 5))
     assert abs(hollow.inv_inertia[0] - expected) <= 1e-4 * expected
+
+
+# ---- tests/Shapes/ConvexTest.elm (the hull data the hot path consumes: group / edge order decides the feature keys) --------
+def _mesh_block(t, sx, sy, sz):
+    """tests/Fixtures/Convex.elm:20-59."""
+    from elm_physics_b200 import math3d as m3
+    hx, hy, hz = sx / 2, sy / 2, sz / 2
+    v = [(hx, -hy, -hz), (hx, hy, -hz), (-hx, hy, -hz), (-hx, -hy, -hz), (hx, -hy, hz), (hx, hy, hz), (-hx, -hy, hz), (-hx, hy, hz)]
+    f = [(1, 7, 5), (1, 2, 7), (4, 7, 6), (4, 5, 7), (6, 2, 3), (6, 7, 2), (3, 4, 6), (3, 0, 4), (0, 5, 4), (0, 1, 5), (3, 1, 0), (3, 2, 1)]
+    return sh.from_triangular_mesh(f, [m3.point_place_in(t, p) for p in v])
+
+
+def _square_like_pyramid(eps):
+    """tests/Fixtures/Convex.elm:138-175."""
+    zo = 0.5 ** (1.0 / 3.0)
+    v = [(-1.0, -1.0, -zo), (1.0, -1.0, -zo), (1.0 + eps, 1.0 + eps, -zo), (-1.0, 1.0, -zo), (0.0, 0.0, 1.0 - zo)]
+    return sh.from_triangular_mesh([(3, 2, 1), (3, 1, 0), (0, 1, 4), (1, 2, 4), (2, 3, 4), (3, 0, 4)], v)
+
+
+def _flat_faces(c):
+    out = []
+    for g in c.faces:
+        out.append((g.normal, g.indices))
+        if g.two_sided:
+            out.append((g.partner_normal, g.partner_indices))
+    return out
+
+
+def _mat_close(a, b, tol=1e-9):
+    for k in a:
+        assert abs(a[k] - b[k]) <= tol * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+def test_convex_inertia_center_of_mass_volume():
+    import math
+    from elm_physics_b200 import math3d as m3
+    _mat_close(_mesh_block(m3.AT_ORIGIN, 2, 3, 5).inertia, sh.from_block(2, 3, 5).inertia)
+    t = m3.rotate_around_own(m3.X_AXIS, math.pi / 5, m3.rotate_around_own(m3.Z_AXIS, math.pi / 5, m3.t_at_point((12.0, 2.0, -3.0))))
+    _mat_close(_mesh_block(t, 2, 3, 5).inertia, m3.inertia_rotate_in(t, sh.from_block(2, 3, 5).inertia))
+    t = m3.rotate_around_own(m3.X_AXIS, math.pi / 5, m3.rotate_around_own(m3.Z_AXIS, math.pi / 5, m3.t_at_point((2.0, 1.0, -2.0))))
+    a, b = _mesh_block(t, 2, 3, 5).position, sh.convex_place_in(t, sh.from_block(2, 3, 5)).position
+    assert all(abs(p - q) < 1e-9 for p, q in zip(a, b))
+    assert abs(_mesh_block(m3.AT_ORIGIN, 2, 3, 1).volume - sh.from_block(2, 3, 1).volume) < 1e-12
+
+
+def test_convex_faces_normals_and_winding():
+    from elm_physics_b200 import math3d as m3
+    import json
+    import os
+    block = sh.from_block(2, 2, 2)
+    assert [n for n, _ in _flat_faces(block)] == [(0.0, 0.0, 1.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), (0.0, -1.0, 0.0),
+                                                  (1.0, 0.0, 0.0), (-1.0, 0.0, 0.0)]
+    assert [g.normal for g in block.faces] == [(0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0)]      # .uniqeNormals
+    huge = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "huge_convex.json")))
+    hulls = [block, _square_like_pyramid(0.0), sh.from_cylinder(6, 4, 5), _mesh_block(m3.AT_ORIGIN, 4, 4, 4),
+             sh.from_triangular_mesh([tuple(f) for f in huge["faces"]], [tuple(v) for v in huge["vertices"]])]
+    for c in hulls:
+        for normal, idx in _flat_faces(c):
+            v = [c.vertices[i] for i in idx]
+            # the normal points away from the hull's position ...
+            assert m3.dot(normal, m3.sub(v[0], c.position)) > 0
+            # ... and every fan triangle of the face winds counter-clockwise around it
+            for k in range(1, len(v) - 1):
+                n = sh.compute_normal(v[0], v[k], v[k + 1])
+                assert all(abs(p - q) < 1e-6 for p, q in zip(n, normal)), (normal, n)
+    assert len(_square_like_pyramid(0.0).faces) == 5
+
+
+def test_convex_unique_edges():
+    from elm_physics_b200 import math3d as m3
+    assert sh.from_block(2, 2, 2).unique_edges == [[0, 4, 3, 7, 2, 6, 1, 5], [0, 3, 5, 6, 4, 7, 1, 2], [0, 1, 7, 6, 4, 5, 3, 2]]
+    assert [len(g) // 2 for g in sh.from_block(2, 3, 5).unique_edges] == [4, 4, 4]
+    assert sorted(len(g) // 2 for g in _mesh_block(m3.AT_ORIGIN, 2, 3, 5).unique_edges) == [4, 4, 4]
+    assert len(_square_like_pyramid(0.0).unique_edges) == 6
+    assert len(_square_like_pyramid(1.0e-5).unique_edges) == 6        # askew: below the parallel tolerance
+    assert len(_square_like_pyramid(1.0e-2).unique_edges) == 8        # above it: all edges unique, none parallel
