@@ -251,3 +251,40 @@ def test_convex_unique_edges():
     assert len(_square_like_pyramid(0.0).unique_edges) == 6
     assert len(_square_like_pyramid(1.0e-5).unique_edges) == 6        # askew: below the parallel tolerance
     assert len(_square_like_pyramid(1.0e-2).unique_edges) == 8        # above it: all edges unique, none parallel
+
+
+# ---- tests/Transform3dTest.elm:9-92 (the placement math of the path, host-side mirror) -----------------------------------
+def test_transform3d_round_trips():
+    import math
+    from elm_physics_b200 import math3d as m3
+    t = m3.rotate_around_own(m3.X_AXIS, math.pi / 5, m3.rotate_around_own(m3.Z_AXIS, math.pi / 5, m3.t_at_point((0.5, 0.6, 0.7))))
+    close = lambda a, b: all(abs(p - q) < 1e-12 for p, q in zip(a, b))
+    point, direction = (0.4, 0.6, 0.8), (0.4, 0.6, 0.8)
+    assert close(m3.point_relative_to(t, m3.point_place_in(t, point)), point)
+    assert close(m3.direction_relative_to(t, m3.direction_place_in(t, direction)), direction)
+    inv = m3.t_inverse(t)          # Transform3d.relativeTo t atOrigin
+    assert close(m3.direction_place_in(inv, m3.direction_place_in(t, direction)), direction)
+    assert close(m3.point_place_in(inv, m3.point_place_in(t, (0.3, 0.5, 0.7))), (0.3, 0.5, 0.7))
+
+
+# ---- tests/EigenDecompositionTest.elm (properties): Body.compound's principal frame comes from this ----------------------
+def test_eigen_decomposition_properties():
+    import numpy as np
+    from elm_physics_b200 import math3d as m3
+    rng = np.random.RandomState(7)
+    for trial in range(40):
+        a = rng.uniform(-1, 1, (3, 3))
+        sym = a @ a.T + (np.eye(3) * rng.uniform(0, 2) if trial % 3 else 0)
+        if trial % 5 == 0:
+            sym = np.diag(rng.uniform(0.1, 3, 3))                     # already diagonal
+        m = dict(m11=sym[0, 0], m21=sym[1, 0], m31=sym[2, 0], m12=sym[0, 1], m22=sym[1, 1], m32=sym[2, 1],
+                 m13=sym[0, 2], m23=sym[1, 2], m33=sym[2, 2])
+        e = m3.eigen_decomposition(m)
+        vs = [np.array(e[k]) for k in ("v1", "v2", "v3")]
+        ev = e["eigenvalues"]
+        for lam, v in zip(ev, vs):
+            assert abs(np.linalg.norm(v) - 1) < 1e-9
+            assert np.linalg.norm(sym @ v - lam * v) < 1e-8 * max(1.0, abs(lam))
+        assert abs(np.dot(vs[0], vs[1])) < 1e-9 and abs(np.dot(vs[0], vs[2])) < 1e-9 and abs(np.dot(vs[1], vs[2])) < 1e-9
+        assert np.dot(np.cross(vs[0], vs[1]), vs[2]) > 0.999          # right-handed: usable as a body frame
+        assert np.allclose(sorted(ev), np.linalg.eigvalsh(sym), atol=1e-9)
