@@ -76,6 +76,14 @@ def support_feature(shapes, s, t, axis):
     return [tuple(out[3 * i:3 * i + 3]) for i in range(n)]
 
 
+def project(shapes, s, t, axis):
+    """Collision.ConvexConvex.project over Convex.convexVertices of the placed hull: (min, max)."""
+    p, pp = _p(t[0]); q, pq = _p(t[1]); a, pa = _p(axis)
+    out = np.zeros(2)
+    lib().ep_oracle_project(C.byref(shapes.c), s, pp, pq, pa, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return float(out[0]), float(out[1])
+
+
 def raycast(shapes, bodies, ray_world, origins, directions):
     """ep_oracle_raycast: Physics.raycast (src/Physics.elm:802-841) against the current state of `bodies`."""
     rw = np.ascontiguousarray(ray_world, dtype=np.int32)

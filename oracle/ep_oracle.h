@@ -24,6 +24,7 @@ int ep_oracle_find_separating_axis(const ep_shapes* shapes, int shape1, const do
                                    const double* pos2, const double* quat2, double* axis);
 int ep_oracle_support_feature(const ep_shapes* shapes, int shape, const double* pos, const double* quat, const double* axis,
                               double* out6);
+int ep_oracle_project(const ep_shapes* shapes, int shape, const double* pos, const double* quat, const double* axis, double* out2);
 int ep_oracle_islands(int32_t n_groups, const int32_t* id1, const int32_t* kind1, const int32_t* id2, const int32_t* kind2,
                       int32_t max_id, int32_t* out_root, int32_t* out_order);
 /* Physics.raycast (src/Physics.elm:802-841) for a batch of rays against the CURRENT state of `bodies`; same contract as ep_raycast. */

@@ -290,6 +290,11 @@ static MinMax project(V3 axis, const std::vector<V3>& vs) {
   }
   return {minVal, maxVal};
 }
+// Collision.ConvexConvex.project over Convex.convexVertices (tests/Collision/ConvexConvexTest.elm:256-319)
+void projectVertices(V3 axis, const WConvex& c, double* out2) {
+  MinMax m = project(axis, convexVertices(c));
+  out2[0] = m.min; out2[1] = m.max;
+}
 // ConvexConvex.elm:596-610
 MinMax projectConvex(V3 axis, const WConvex& c) {
   if (c.isBox) {

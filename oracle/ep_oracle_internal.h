@@ -15,5 +15,6 @@ void getContactsSolverOrder(const std::vector<WShape>& shapes1, const std::vecto
 bool testSeparatingAxis(const WConvex& c1, const WConvex& c2, V3 axis, double& depth);
 bool findSeparatingAxis(const WConvex& c1, const WConvex& c2, V3& axis);
 std::vector<V3> supportFeature(V3 axis, const WConvex& cv);
+void projectVertices(V3 axis, const WConvex& c, double* out2);
 
 }  // namespace epo

@@ -623,6 +623,14 @@ extern "C" int ep_oracle_support_feature(const ep_shapes* S, int shape, const do
   return (int)v.size();
 }
 
+// Collision.ConvexConvex.project (ConvexConvex.elm:689-710) of a placed hull's convexVertices: out2 = {min, max}
+extern "C" int ep_oracle_project(const ep_shapes* S, int shape, const double* pos, const double* quat, const double* axis, double* out2) {
+  Tf t{rd3(pos), Quat{quat[0], quat[1], quat[2], quat[3]}};
+  WShape a = placeShape(S, shape, t, 0, 0);
+  projectVertices(rd3(axis), a.convex, out2);
+  return EP_OK;
+}
+
 // Islands.fold visiting order for the known-answer test tests/SolverIslandsTest.elm:136-163.
 extern "C" int ep_oracle_islands(int32_t n_groups, const int32_t* id1, const int32_t* kind1, const int32_t* id2, const int32_t* kind2,
                                  int32_t max_id, int32_t* out_root, int32_t* out_order) {

@@ -164,6 +164,19 @@ def test_find_separating_axis(oracle):
                                        rot(at_point((0.2, 0, 0)), m3.Z_AXIS, math.pi / 4)) == (-1.0, 0.0, 0.0)
 
 
+# ---- tests/Collision/ConvexConvexTest.elm:256-319 ------------------------------------------------------
+def test_project(oracle):
+    sc = Scene(oracle)
+    b = sc.add(sh.from_block(1, 1, 1))
+    S = sc.shapes()
+    assert oracle.project(S, b, m3.AT_ORIGIN, (1.0, 0.0, 0.0)) == (-0.5, 0.5)
+    assert oracle.project(S, b, m3.AT_ORIGIN, (-1.0, 0.0, 0.0)) == (-0.5, 0.5)
+    assert oracle.project(S, b, m3.AT_ORIGIN, (0.0, 1.0, 0.0)) == (-0.5, 0.5)
+    assert oracle.project(S, b, at_point((0, 1, 0)), (0.0, 1.0, 0.0)) == (0.5, 1.5)
+    mn, mx = oracle.project(S, b, rot(at_point((0, 1, 0)), m3.X_AXIS, math.pi / 2), (0.0, 1.0, 0.0))
+    assert abs(mn - 0.5) < 1e-5 and abs(mx - 1.5) < 1e-5
+
+
 # ---- tests/ConvexSphereBoxTest.elm:21-182 (full-precision expectation) -------------------------------
 def test_icosphere_box_edge_contact_full_precision(oracle):
     mesh = json.load(open(os.path.join(GOLDEN, "icosphere.json")))
