@@ -130,3 +130,77 @@ def test_icosphere_body_bounces_off_the_floor_and_does_not_pass_through_the_cube
         min_dist = min(min_dist, float(np.linalg.norm(b.pos[1] - b.pos[2])))
     assert min_dist > 0.4, f"min cube-ico centre distance was {min_dist} m (deep penetration / tunnelling)"
     assert b.pos[2][2] > -1.0 and b.pos[1][2] > b.pos[2][2]        # the icosphere rests on the floor, the cube on top of it or beside
+
+
+# ---- tests/FrictionTest.elm:184-369 with the reference's own scene, forces, frame counts and tolerances ------------------
+_G = 9.80665
+_BOX_MASS = 10.0
+
+
+def _friction_scene(material):
+    box = P.move_to((0, 0, 0.5), P.scale_mass_to(_BOX_MASS, P.block((1, 1, 1), material)))
+    return P.assign_ids([(0, P.plane(material)), (1, box)])[0]
+
+
+def _friction_run(oracle, gravity, force, n, state):
+    """FrictionTest.run: n frames, force (fx, fz) re-applied at the box's centre of mass before every frame; the contact
+    cache is threaded through the frames of ONE run (each run starts from emptyContacts, like the reference's helpers)."""
+    shapes, bodies, params = state
+    params.gravity[0] = gravity
+    warm = None
+    for _ in range(n):
+        if force != (0.0, 0.0):
+            bodies.force[1] += (force[0], 0.0, force[1])
+        o = H.contacts_for(bodies)
+        oracle.step(shapes, bodies, params, warm, o, 1)
+        warm = o
+    return state
+
+
+def _push_vx_fz(oracle, fx, fz):
+    state = pack.pack_worlds([(P.on_earth(), _friction_scene(P.wood))])
+    _friction_run(oracle, (0.0, 0.0, -_G), (0.0, 0.0), 120, state)
+    _friction_run(oracle, (0.0, 0.0, -_G), (float(fx), float(fz)), 30, state)
+    return float(state[1].vel[1][0])
+
+
+def _slide_vx(oracle, material, degs, frames):
+    r = math.radians(degs)
+    state = pack.pack_worlds([(P.on_earth(), _friction_scene(material))])
+    _friction_run(oracle, (_G * math.sin(r), 0.0, -_G * math.cos(r)), (0.0, 0.0), frames, state)
+    return float(state[1].vel[1][0])
+
+
+def test_friction_flat_floor_horizontal_push(oracle):
+    f_max = P.wood.friction * _BOX_MASS * _G
+    assert abs(_push_vx_fz(oracle, 0, 0)) < 0.005                      # settles to rest under gravity alone
+    assert abs(_push_vx_fz(oracle, 0.5 * f_max, 0)) < 0.005            # half Fmax: static friction holds
+    force = 2 * f_max
+    expected = (force / _BOX_MASS - P.wood.friction * _G) * 0.5         # a = (F - mu m g) / m over 30 frames
+    assert abs(_push_vx_fz(oracle, force, 0) - expected) <= 0.05 * expected
+
+
+def test_friction_clip_follows_the_applied_normal_load(oracle):
+    slide_push = 1.5 * P.wood.friction * _BOX_MASS * _G
+    alone = _push_vx_fz(oracle, slide_push, 0)
+    assert alone > 0.3                                                  # slides under the gravity-only normal
+    assert abs(_push_vx_fz(oracle, slide_push, -100)) < 0.01            # pressed down: the clip rises, it holds
+    assert _push_vx_fz(oracle, slide_push, 100) > alone                 # lifted: the clip drops, it slides faster
+
+
+def test_friction_inclined_contact(oracle):
+    mu = P.wood.friction
+    critical = math.degrees(math.atan(mu))
+    assert abs(_slide_vx(oracle, P.wood, 15, 200)) < 0.005
+    assert _slide_vx(oracle, P.wood, 24, 200) > 0.5
+    breakaway = min(d for d in (18 + 0.5 * i for i in range(13)) if not abs(_slide_vx(oracle, P.wood, d, 200)) < 0.01)
+    assert abs(breakaway - critical) <= 1.0
+    r = math.radians(30)
+    measured = (_slide_vx(oracle, P.wood, 30, 200) - _slide_vx(oracle, P.wood, 30, 100)) / (100 / 60)
+    expected = _G * (math.sin(r) - mu * math.cos(r))
+    assert abs(measured - expected) <= 0.05 * expected
+
+
+def test_friction_ice_slides_where_wood_holds(oracle):
+    assert abs(_slide_vx(oracle, P.wood, 10, 200)) < 0.005
+    assert _slide_vx(oracle, P.ice, 10, 200) > 1
