@@ -204,3 +204,17 @@ def test_friction_inclined_contact(oracle):
 def test_friction_ice_slides_where_wood_holds(oracle):
     assert abs(_slide_vx(oracle, P.wood, 10, 200)) < 0.005
     assert _slide_vx(oracle, P.ice, 10, 200) > 1
+
+
+# ---- tests/KinematicTest.elm:27-135, the four cases as written there -------------------------------------------------------
+def test_kinematic_cases_of_the_reference(oracle):
+    ball = [(P.shape_sphere(0.5), P.wood)]
+    platform = P.set_velocity_to((1, 0, 0), P.move_to((0, 0, 5), P.kinematic(ball)))
+    bodies, _ = run(oracle, [(P.on_earth(), P.assign_ids([("floor", P.plane(P.wood)), ("platform", platform)])[0])], 1)
+    assert abs(bodies.pos[1][0] - 1 / 60) < 1e-4 and abs(bodies.pos[1][2] - 5) < 1e-4          # translates by velocity * dt
+    bodies, _ = run(oracle, [(P.on_earth(), P.assign_ids([("platform", P.set_velocity_to((1, 0, 0), P.kinematic(ball)))])[0])], 1)
+    assert abs(bodies.vel[0][0] - 1) < 1e-4 and abs(bodies.vel[0][1]) < 1e-4 and abs(bodies.vel[0][2]) < 1e-4   # gravity does not touch it
+    moved = P.move_to((100, 0, 5), P.set_velocity_to((2, 0, 0), P.kinematic(ball)))
+    assert abs(moved.velocity[0] - 2) < 1e-4                                                   # moveTo keeps the velocity
+    wall = P.set_velocity_to((5, 0, 0), P.static(ball))
+    assert abs(wall.velocity[0]) < 1e-4                                                        # static bodies ignore setVelocityTo
