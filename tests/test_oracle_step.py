@@ -218,3 +218,50 @@ def test_kinematic_cases_of_the_reference(oracle):
     assert abs(moved.velocity[0] - 2) < 1e-4                                                   # moveTo keeps the velocity
     wall = P.set_velocity_to((5, 0, 0), P.static(ball))
     assert abs(wall.velocity[0]) < 1e-4                                                        # static bodies ignore setVelocityTo
+
+
+# ---- sandbox/tests/StabilityTest.elm:383-447 at reduced length (the reference runs 100 000 frames) ------------------------
+def test_box_resting_on_a_slope_creeps_but_never_slides(oracle):
+    """sandbox/src/Stability/Scenarios.elm:107-133: a wood box flush on a static wood ramp tilted 15 degrees, 10 solver
+    iterations.  The reference's limits: max speed < 0.05 m/s, drift < 0.7 m over 100 000 frames, and it documents what it
+    observes with friction working: a peak speed of ~4e-4 m/s and a steady creep of ~0.27 mm/s (0.59 m over 100 000
+    frames).  6000 frames here: the same speed limit, and the creep RATE has to agree with the documented one."""
+    th = math.radians(15)
+    box = P.move_to((0.5 * math.sin(th), 0, 2 + 0.5 * math.cos(th)), P.rotate_around((0, 0, 0), (0, 1, 0), th, P.block((1, 1, 1), P.wood)))
+    ramp = P.static([(P.shape_block((10.0, 6.0, 0.5)), P.wood)])
+    ramp = P.move_to((-0.25 * math.sin(th), 0, 2 - 0.25 * math.cos(th)), P.rotate_around((0, 0, 0), (0, 1, 0), th, ramp))
+    cfg = P.on_earth()
+    cfg.solver_iterations = 10
+    shapes, bodies, params = pack.pack_worlds([(cfg, P.assign_ids([(1, box), (0, ramp)])[0])])
+    start = bodies.pos[0].copy()
+    warm, max_speed, settled_speed, frames = None, 0.0, 0.0, 6000
+    for f in range(frames + 1):
+        o = H.contacts_for(bodies)
+        oracle.step(shapes, bodies, params, warm, o, 1)
+        warm = o
+        if f >= 1:              # frame 0 is skipped: initial-contact velocity spike (StabilityTest.elm:391-395)
+            max_speed = max(max_speed, float(np.linalg.norm(bodies.vel[0])))
+        if f >= 100:
+            settled_speed = max(settled_speed, float(np.linalg.norm(bodies.vel[0])))
+    drift = float(np.linalg.norm(bodies.pos[0] - start))
+    assert max_speed < 0.05, max_speed                      # the reference's limit
+    assert 2.0e-4 < settled_speed < 4.5e-4, settled_speed   # the reference's observation: creep ~0.27 mm/s, peak ~4e-4 m/s
+    rate_mm_s = 1e3 * drift / (frames / 60.0)
+    assert 0.15 < rate_mm_s < 0.45, rate_mm_s
+
+
+def test_dropped_stack_of_five_lands_without_toppling(oracle):
+    """Scenarios.elm:178-200 + StabilityTest.elm:420-447: boxes released with 0.4 m of air between them, 10 iterations: no
+    box ever strays more than 0.25 m sideways and the stack is at rest (max speed < 0.05 m/s) at the end; 3000 frames."""
+    bodies = [(k, P.move_to((0, 0, k - 0.5 + k * 0.4), P.block((1, 1, 1), P.wood))) for k in range(5, 0, -1)] + [(0, P.plane(P.wood))]
+    cfg = P.on_earth()
+    cfg.solver_iterations = 10
+    shapes, b, params = pack.pack_worlds([(cfg, P.assign_ids(bodies)[0])])
+    warm = None
+    for f in range(3000):
+        o = H.contacts_for(b)
+        oracle.step(shapes, b, params, warm, o, 1)
+        warm = o
+        assert float(np.hypot(b.pos[:5, 0], b.pos[:5, 1]).max()) <= 0.25, f
+    assert float(np.sqrt((b.vel[:5] ** 2).sum(axis=1)).max()) < 0.05
+    assert np.allclose(np.sort(b.pos[:5, 2]), [0.5, 1.5, 2.5, 3.5, 4.5], atol=0.02)
