@@ -15,7 +15,7 @@ EP_POINT_TO_POINT, EP_HINGE, EP_LOCK, EP_DISTANCE = 0, 1, 2, 3
 EP_CONVEX_F64_HEADER, EP_CONVEX_I32_HEADER, EP_GROUP_F64, EP_GROUP_I32, EP_EDGE_I32 = 15, 4, 8, 5, 2
 EP_STAT_COUNT = 8
 EP_K_COUNT = 18
-EP_OPT_PATH, EP_OPT_CONTACT_CAP, EP_OPT_RAW_CAP = 0, 1, 2
+EP_OPT_PATH, EP_OPT_CONTACT_CAP, EP_OPT_RAW_CAP, EP_OPT_ITEM_CAP = 0, 1, 2, 3
 
 _pi32 = C.POINTER(C.c_int32)
 _pi64 = C.POINTER(C.c_int64)
@@ -241,6 +241,7 @@ class Contacts:
         d = dict(world_group_off=self.world_group_off.copy(), group_id1=self.group_id1[:ng].copy(),
                  group_id2=self.group_id2[:ng].copy(), group_n_constraints=self.group_n_constraints[:ng].copy(),
                  group_contact_off=self.group_contact_off[:ng + 1].copy(),
+                 group_pre_pos1=self.group_pre_pos1[:ng].copy(), group_pre_quat1=self.group_pre_quat1[:ng].copy(),
                  group_island=self.group_island[:ng].copy(), iterations=self.iterations[:self.n_worlds].copy(),
                  world_n_islands=self.world_n_islands[:self.n_worlds].copy())
         for name, _, _ in CONTACT_FIELDS:

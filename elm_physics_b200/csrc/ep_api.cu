@@ -57,7 +57,7 @@ struct ep_ctx {
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
   int lanes_grid = 0, build_grid = 0;
-  size_t team_smem_set = 48 * 1024;
+  size_t team_smem_max = 48 * 1024;            // device opt-in maximum of dynamic shared memory per CTA (set in ep_create)
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -155,7 +155,15 @@ extern "C" int ep_create(ep_ctx** out, int device) {
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_build, 128, 0) == cudaSuccess && per_sm >= 1;
     ctx->build_grid = per_sm * ctx->sm_count;
   }
-  if (!ok) { cudaStreamDestroy(ctx->stream); delete ctx; return EP_ENODEVICE; }
+  // The team kernels' dynamic shared memory depends on the largest world of a batch.  The attribute is per function and per
+  // DEVICE, i.e. shared by every context of the process: it is set once, here, to the device's opt-in maximum, and a batch
+  // that needs more falls back to the variant that keeps the bodies in global memory (ep_step_resident).
+  int smem_optin = 0;
+  ok = ok && cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess;
+  ctx->team_smem_max = (size_t)smem_optin;
+  ok = ok && cudaFuncSetAttribute(k_solve_team<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_solve_team<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) == cudaSuccess;
+  if (!ok) { ep_destroy(ctx); return EP_ENODEVICE; }
   *out = ctx;
   return EP_OK;
 }
@@ -163,7 +171,7 @@ extern "C" int ep_create(ep_ctx** out, int device) {
 extern "C" void ep_destroy(ep_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_pool(ctx->world_allocs);
   free_pool(ctx->shape_allocs);
   if (ctx->ray_buf) cudaFree(ctx->ray_buf);
@@ -176,7 +184,7 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
   if (ctx->ev_out_done) cudaEventDestroy(ctx->ev_out_done);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -292,6 +300,14 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     for (int r = B->world_body_off[w]; r < B->world_body_off[w + 1]; r++) body_world[r] = w;
   }
   if (slot_cap >= (int64_t)1 << 31) { ctx->err = "too many body pairs for 32-bit pair slots"; return EP_ECAPACITY; }
+  {   // the dense warm-start table stands for bodyKey(id1, id2) (ContactId.elm:62-68) only while ids are unique in a world
+    std::vector<int32_t> ids;
+    for (int w = 0; w < nw; w++) {
+      ids.assign(B->body_id + B->world_body_off[w], B->body_id + B->world_body_off[w + 1]);
+      std::sort(ids.begin(), ids.end());
+      if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) { ctx->err = "duplicate body id inside a world (run AssignIds.assignIds first)"; return EP_EINVAL; }
+    }
+  }
   for (int r = 0; r < nb; r++) {
     if (B->body_id[r] < 0 || B->body_id[r] >= 262144) { ctx->err = "body id out of range [0, 2^18)"; return EP_EINVAL; }
     for (int k = B->inst_off[r]; k < B->inst_off[r + 1]; k++) inst_body[k] = r;
@@ -367,7 +383,8 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_upload(ctx, pool, &d.dt, P->dt, nw));
   TRY(dev_upload(ctx, pool, &d.iterations, P->iterations, nw));
   d.collide = nullptr; d.collide_off = nullptr;
-  if (P->collide) {
+  if (P->collide && nw > 0) {
+    if (!P->collide_off) { ctx->err = "collide without collide_off"; return EP_EINVAL; }
     std::vector<int64_t> off(P->collide_off, P->collide_off + nw);
     int64_t n_last = B->world_body_off[nw] - B->world_body_off[nw - 1];
     size_t total = (size_t)(off[nw - 1] + n_last * n_last);
@@ -658,14 +675,9 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       // longest first: CTA-per-island teams, warp-per-island teams, then the lane classes from the largest down
       // team kernels: shared memory = level-walk chunk (3 x 8T ints) + per-body last level / inverse mass / deltas of the largest world
       const size_t body_b = (size_t)((d.nb_max + 1) & ~1) * 4 + (size_t)d.nb_max * 56;
-      const bool smemb = body_b + 3 * 8 * 256 * 4 <= 200 * 1024;
+      const bool smemb = body_b + 3 * 8 * 256 * 4 <= std::min<size_t>(200 * 1024, ctx->team_smem_max);
       const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
       if (smemb) {
-        if (sm_cta > ctx->team_smem_set) {
-          CK(cudaFuncSetAttribute(k_solve_team<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cta));
-          CK(cudaFuncSetAttribute(k_solve_team<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cta));
-          ctx->team_smem_set = sm_cta;
-        }
         TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1); }));
         TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7); }));
       } else {
@@ -678,6 +690,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       for (int i = 2; i >= 0; i--)
         TRY(side(EP_K_SOLVE_LANES_B0 + i, [&](cudaStream_t sx) { k_solve_lanes<2><<<std::min(ctx->head_grid[i], tiles_cap), 32, ctx->tile_smem[i], sx>>>(d, i, i); }));
       { Timed tt(ctx, EP_K_SOLVE_LANES_INPLACE, st); k_solve_lanes<0><<<std::min(ctx->lanes_grid, tiles_cap / 4 + 1), 128, 0, st>>>(d, 0, kLaneBinMax); }
+      CK(cudaGetLastError());       // a solver launch that failed must not be followed by the integration of unsolved islands
       for (int i = 0; i < ax; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }
     if (ctx->hook_early_out) CK(cudaStreamWaitEvent(st, ctx->ev_out_done, 0));     // k_out_groups reads the pre-step transforms
@@ -704,6 +717,7 @@ static int check_flags(ep_ctx* ctx) {
   CK(cudaMemcpyAsync(fl, ctx->d.flags, sizeof fl, cudaMemcpyDeviceToHost, ctx->stream));
   TRY(wait_stream(ctx, ctx->stream));
   if (fl[FLAG_POOL_OVERFLOW]) { ctx->err = "contact pool overflow (raise EP_CONTACT_CAP)"; return EP_ECAPACITY; }
+  if (fl[FLAG_PAIR_OVERFLOW] == 5) { ctx->err = "narrowphase work-item pool overflow (raise EP_OPT_ITEM_CAP)"; return EP_ECAPACITY; }
   if (fl[FLAG_PAIR_OVERFLOW]) { ctx->err = "pair slot / per-pair contact buffer overflow"; return EP_ECAPACITY; }
   if (fl[FLAG_POLY_OVERFLOW]) { ctx->err = "clip polygon buffer overflow (face with too many vertices)"; return EP_ECAPACITY; }
   if (fl[FLAG_JOINT_OVERFLOW]) { ctx->err = "joint row pool overflow"; return EP_ECAPACITY; }

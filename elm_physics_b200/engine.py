@@ -95,12 +95,13 @@ class Engine:
         if rc != 0:
             raise EngineError(f"{what} failed with {rc}: {self.lib.ep_last_error(self.ctx).decode()}")
 
-    def configure(self, contact_cap=None, raw_cap=None):
-        """ep_configure: capacities in contacts."""
+    def configure(self, contact_cap=None, item_cap=None):
+        """ep_configure, read by the next upload_worlds: `contact_cap` = device contact pool (contacts per step over all
+        worlds), `item_cap` = narrowphase work items (shape pairs of candidate body pairs) per step."""
         if contact_cap is not None:
             self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_CONTACT_CAP, C.c_int64(contact_cap)), "ep_configure")
-        if raw_cap is not None:
-            self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_RAW_CAP, C.c_int64(raw_cap)), "ep_configure")
+        if item_cap is not None:
+            self._ck(self.lib.ep_configure(self.ctx, abi.EP_OPT_ITEM_CAP, C.c_int64(item_cap)), "ep_configure")
 
     def upload_shapes(self, shapes):
         self._ck(self.lib.ep_upload_shapes(self.ctx, C.byref(shapes.c)), "ep_upload_shapes")
@@ -188,7 +189,7 @@ class Engine:
         if config.contacts is not None and config.contacts.packed is not None:
             warm = pack.contacts_from_world_dicts([config.contacts.packed])
         n = bodies.n_bodies
-        out = abi.Contacts(1, n * (n - 1) // 2 + 1, 16 * n + 64)
+        out = abi.Contacts(1, n * (n - 1) // 2 + 1, max(1 << 14, 16 * n))      # the device pool's default size (ep_upload_worlds)
         self.upload_shapes(shapes)
         self.step(bodies, params, warm, out, 1)
         new_bodies = pack.unpack_bodies(bodies, [(config, with_ids)])[0]

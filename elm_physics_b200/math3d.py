@@ -142,6 +142,12 @@ def t_place_in(g, l):
     return (add(g[0], q_rotate(g[1], l[0])), q_mul(g[1], l[1]))
 
 
+def t_relative_to(t1, t2):
+    """Transform3d.elm:233-241 : t2 expressed in the frame t1 (conjugate of a normalised quaternion as its inverse)."""
+    x, y, z, w = t1[1]
+    return (point_relative_to(t1, t2[0]), q_mul((-x, -y, -z, w), t2[1]))
+
+
 def t_inverse(t):
     """Transform3d.elm:245-253."""
     x, y, z, w = t[1]

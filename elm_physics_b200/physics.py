@@ -483,23 +483,28 @@ def on_earth():
 
 
 def contact_points(predicate, contacts):
-    """Physics.elm:651-653, 1158-1207 : world contact points on body1 of each pair, re-expressed in
-    the post-step frame of body1."""
+    """Physics.elm:651-653, 1158-1207 (contactPointsHelp): world contact points on body1 of each pair group that has
+    contacts, moved from the pre-step frame of body1 to its post-step frame.  The predicate is tried in both argument
+    orders (1177), groups without contacts are skipped (1169-1171), and because the reference conses while walking
+    `pairGroups` (itself the reverse of the enumeration) the result comes out in pair-enumeration order."""
     out = []
     if contacts.packed is None or contacts.bodies is None:
         return out
     from .pack import unpack_pair_groups
     by_id = {b.id: (ext, b) for ext, b in contacts.bodies}
     for g in unpack_pair_groups(contacts.packed):
+        if not g["contacts"]:
+            continue
         if g["id1"] not in by_id or g["id2"] not in by_id:
             continue
         ext1, b1 = by_id[g["id1"]]
         ext2, _ = by_id[g["id2"]]
-        if not predicate(ext1, ext2):
+        if not (predicate(ext1, ext2) or predicate(ext2, ext1)):
             continue
-        pre = g["pre_transform1"]
-        pts = [m3.point_place_in(b1.transform3d, m3.point_relative_to(pre, c["pi"])) for c in g["contacts"]]
-        out.append((ext1, ext2, pts))
+        # Transform3d.atOrigin |> relativeTo pre |> placeIn post, then pointPlaceIn of every contact.pi (1180-1192)
+        transform = m3.t_place_in(b1.transform3d, m3.t_relative_to(g["pre_transform1"], (m3.ZERO, m3.IDENTITY_Q)))
+        pts = [m3.point_place_in(transform, c["pi"]) for c in g["contacts"]]
+        out.insert(0, (ext1, ext2, pts))
     return out
 
 

@@ -288,3 +288,37 @@ def test_eigen_decomposition_properties():
         assert abs(np.dot(vs[0], vs[1])) < 1e-9 and abs(np.dot(vs[0], vs[2])) < 1e-9 and abs(np.dot(vs[1], vs[2])) < 1e-9
         assert np.dot(np.cross(vs[0], vs[1]), vs[2]) > 0.999          # right-handed: usable as a body frame
         assert np.allclose(sorted(ev), np.linalg.eigvalsh(sym), atol=1e-9)
+
+
+def test_contact_points_follows_contactPointsHelp():
+    """Physics.elm:1158-1207: the predicate is tried in both argument orders, pair groups without contacts (constraint-only
+    pairs) are skipped, the result is in pair-enumeration order (the reference conses while walking the reversed list),
+    and the points go through the COMPOSED transform `atOrigin |> relativeTo pre |> placeIn post`."""
+    import numpy as np
+    a = with_id(0, plane()); b = with_id(1, plane()); c = with_id(2, plane())
+    qz = (0.0, 0.0, 0.14943813247359922, 0.9887710779360422)         # 0.3 rad about z
+    pre_a = ((0.0, 0.0, 1.0), qz)
+    moved_a = replace(a, transform3d=((0.5, -1.0, 2.0), (0.0, 0.0, 0.0, 1.0)))
+    packed = dict(
+        group_id1=np.array([0, 0, 1]), group_id2=np.array([1, 2, 2]), group_n_constraints=np.array([0, 1, 0]),
+        group_contact_off=np.array([0, 1, 1, 3]),
+        group_pre_pos1=np.array([pre_a[0], pre_a[0], (0.0, 0.0, 0.0)]), group_pre_quat1=np.array([qz, qz, (0.0, 0.0, 0.0, 1.0)]),
+        shape_key=np.array([257, 257, 257]), feature_key=np.array([1, 2, 3]),
+        ni=np.zeros((3, 3)), pi=np.array([(1.0, 0.0, 1.0), (0.0, 2.0, 0.0), (0.0, 3.0, 0.0)]), pj=np.zeros((3, 3)),
+        friction=np.zeros(3), bounciness=np.zeros(3), lambda_=np.zeros(3), t1=np.zeros((3, 3)), iterations=1)
+    contacts = P.Contacts(packed=packed, iterations=1, bodies=[("jeep", moved_a), ("wall", b), ("crate", c)])
+    everything = P.contact_points(lambda x, y: True, contacts)
+    assert [(e1, e2, len(p)) for e1, e2, p in everything] == [("jeep", "wall", 1), ("wall", "crate", 2)]     # (0,2) has no contacts
+    # pairGroup.contacts is the reverse of the solver order the arrays hold
+    assert everything[1][2] == [(0.0, 3.0, 0.0), (0.0, 2.0, 0.0)]
+    # asymmetric predicates match whichever body is body1 (Physics.elm:1177)
+    assert [(e1, e2) for e1, e2, _ in P.contact_points(lambda x, y: x == "wall" and y == "jeep", contacts)] == [("jeep", "wall")]
+    assert [(e1, e2) for e1, e2, _ in P.contact_points(lambda x, y: x == "crate" and y == "wall", contacts)] == [("wall", "crate")]
+    assert P.contact_points(lambda x, y: x == "jeep" and y == "crate", contacts) == []
+    # the point: relative to the pre-step frame of body1, placed in its post-step frame, as one composed transform
+    t = m3.t_place_in(moved_a.transform3d, m3.t_relative_to(pre_a, m3.AT_ORIGIN))
+    assert everything[0][2][0] == m3.point_place_in(t, (1.0, 0.0, 1.0))
+    x, y, z = everything[0][2][0]
+    # (1,0,1) is (1,0,0) from the old origin; derotated by 0.3 rad about z, then put at the new origin
+    import math
+    assert abs(x - (0.5 + math.cos(0.3))) < 1e-12 and abs(y - (-1.0 - math.sin(0.3))) < 1e-12 and abs(z - 2.0) < 1e-12
