@@ -160,7 +160,8 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   // that needs more falls back to the variant that keeps the bodies in global memory (ep_step_resident).
   int smem_optin = 0;
   ok = ok && cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess;
-  ctx->team_smem_max = (size_t)smem_optin;
+  smem_optin -= 1024;                           // room for the kernels' static shared memory
+  ctx->team_smem_max = (size_t)std::max(smem_optin, 0);
   ok = ok && cudaFuncSetAttribute(k_solve_team<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_solve_team<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) == cudaSuccess;
   if (!ok) { ep_destroy(ctx); return EP_ENODEVICE; }
@@ -456,8 +457,8 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   // tile images: 37 doubles per contact + 16 per dynamic body, with slack for the max-over-lanes padding of a tile
   d.tile_arena_cap = (int64_t)d.contact_cap * 72 + (int64_t)d.jrow_cap * 24 + (int64_t)nb * 24 + 4096;
   TRY(dev_alloc(ctx, pool, &d.tile_arena, (size_t)d.tile_arena_cap));
-  TRY(dev_alloc(ctx, pool, &d.work, 2));
-  CK(cudaMemsetAsync(d.work, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  TRY(dev_alloc(ctx, pool, &d.work, 4));
+  CK(cudaMemsetAsync(d.work, 0, 4 * sizeof(unsigned long long), ctx->stream));
   TRY(dev_alloc(ctx, pool, &d.flags, FLAG_COUNT));
   CK(cudaMemsetAsync(d.flags, 0, FLAG_COUNT * sizeof(int32_t), ctx->stream));
   TRY(alloc_frame(ctx, d.cur, d));
@@ -661,6 +662,8 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         // per island, 7.. one CTA per island (level-scheduled, ep_solve.cuh).  EP_K_SOLVE brackets the whole fork/join.
       Timed t(ctx, EP_K_SOLVE, nullptr, false);
       static const bool serial = getenv("EP_SOLVE_SERIAL") != nullptr;     // profiling aid: one class after the other
+      const char* fr = getenv("EP_FORCE_RESUM");      // test hook, read per step: always decide the early exit from the canonical-order sum
+      const int force_resum = fr && atoi(fr) != 0;
       CK(cudaEventRecord(ctx->ev_fork, st));
       int ax = 0;
       auto side = [&](int kind, auto&& launch) -> int {
@@ -678,11 +681,11 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       const bool smemb = body_b + 3 * 8 * 256 * 4 <= std::min<size_t>(200 * 1024, ctx->team_smem_max);
       const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
       if (smemb) {
-        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1); }));
-        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7); }));
+        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
+        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
       } else {
-        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1); }));
-        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7); }));
+        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
+        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
       }
       TRY(side(EP_K_SOLVE_LANES_B5, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5); }));
       TRY(side(EP_K_SOLVE_LANES_B4, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4); }));
@@ -978,10 +981,11 @@ extern "C" int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n) {
   if (!ctx || !out) return EP_EINVAL;
   ctx->stats[EP_STAT_KERNEL_LAUNCHES] = ctx->launches;
   if (ctx->have_worlds) {
-    unsigned long long wk[2] = {0, 0};
+    unsigned long long wk[4] = {0, 0, 0, 0};
     cudaStreamSynchronize(ctx->stream);
     if (cudaMemcpy(wk, ctx->d.work, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess) {
       ctx->stats[EP_STAT_CONTACT_ITERATIONS] = (int64_t)wk[0]; ctx->stats[EP_STAT_JOINT_ROW_ITERATIONS] = (int64_t)wk[1];
+      ctx->stats[EP_STAT_RESUMS] = (int64_t)wk[2];
     }
     int32_t cnt[CNT_COUNT];      // counts of the last computed frame (the group count comes with a contact download only)
     if (cudaMemcpy(cnt, ctx->d.prev.counters, sizeof cnt, cudaMemcpyDeviceToHost) == cudaSuccess) {

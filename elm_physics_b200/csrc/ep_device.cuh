@@ -108,7 +108,7 @@ struct Dev {
   int32_t* world_n_islands;   // [n_worlds]
   JointRow* jrows;
   int32_t* flags;             // [FLAG_COUNT]
-  unsigned long long* work;   // [2] cumulative contact-iterations, joint-row-iterations of the solver (roofline denominators)
+  unsigned long long* work;   // [4] cumulative contact-iterations, joint-row-iterations of the solver (roofline denominators), canonical re-sums
   int64_t slot_cap; int32_t contact_cap; int32_t jrow_cap;
   // narrowphase work items, binned by class so that the lanes of a warp run the same Collision.* module
   int32_t item_cap;

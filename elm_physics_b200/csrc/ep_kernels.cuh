@@ -520,8 +520,13 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
 // warp-aggregated: one atomic per warp), the warm-start cache index of this frame, and for every contact of the frame where
 // it comes from (slot, raw contact) -- so that k_equations runs one thread per CONTACT (a thread per group ran 9 of 32 lanes:
 // groups hold 1..8 contacts) and k_islands, which needs only the counts, runs beside it.
+// Pair slots of the frame.  After a pair-slot / work-item overflow (a world's slots were counted but never emitted, and the
+// narrowphase did not run) there are none: the frame is void and ep_sync reports the overflow.
+__device__ __forceinline__ int slot_total(const Dev& d) {
+  return d.flags[FLAG_PAIR_OVERFLOW] ? 0 : min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
+}
 __global__ void __launch_bounds__(256) k_slot_counts(Dev d) {
-  const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
+  const int total = slot_total(d);
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * blockDim.x;
   for (int s0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < total; s0 += stride) {
@@ -603,7 +608,7 @@ __global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
 }
 // addConstraintEquations: one thread per constrained pair (launched only when the batch has constraints)
 __global__ void __launch_bounds__(128, 2) k_joint_equations(Dev d) {
-  const int total = min(d.cur.counters[CNT_CAND], (int)d.slot_cap);
+  const int total = slot_total(d);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
     const int ncon = d.cur.slot_ncon[s];
     if (ncon == 0) continue;

@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int
 struct TeamRec { int b1, b2, c0, cn, j0, jn, pad0, pad1; };      // world-local dynamic body index or -1; contact / joint row ranges
 
 template <int T, bool SMEMB>
-__global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi) {
+__global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi, int force_resum) {
   constexpr int CH = 8 * T;                 // groups per pass of the level walk
   extern __shared__ __align__(16) unsigned char team_smem[];
   __shared__ int s_nlev, s_decide;
@@ -643,9 +643,10 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi)
         double S = 0;
         for (int k = 0; k < T / 32; k++) S += s_part[k];
         int below;
-        if (S < kSolverTolerance * (1.0 - 1e-9)) below = 1;
-        else if (S > kSolverTolerance * (1.0 + 1e-9)) below = 0;
-        else {      // the reference's association: sweep 1 then sweep 2 left to right (`step` adds the two sums, `solve2Body` runs one through)
+        if (!force_resum && S < kSolverTolerance * (1.0 - 1e-9)) below = 1;
+        else if (!force_resum && S > kSolverTolerance * (1.0 + 1e-9)) below = 0;
+        else {
+          atomicAdd(&d.work[2], 1ull);      // the reference's association: sweep 1 then sweep 2 left to right (`step` adds the two sums, `solve2Body` runs one through)
           double p1 = 0;
           for (int gi = 0; gi < gn; gi++) {
             int s = d.isl_groups[g0 + gi];

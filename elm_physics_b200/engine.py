@@ -161,7 +161,7 @@ class Engine:
         self._ck(self.lib.ep_stats(self.ctx, out.ctypes.data_as(C.POINTER(C.c_int64)), abi.EP_STAT_COUNT), "ep_stats")
         return dict(kernel_launches=int(out[0]), candidate_pairs=int(out[1]), groups=int(out[2]),
                     contacts=int(out[3]), islands=int(out[4]), contact_iterations=int(out[5]),
-                    joint_row_iterations=int(out[6]))
+                    joint_row_iterations=int(out[6]), resums=int(out[7]))
 
     def profile(self, enable=True):
         self._ck(self.lib.ep_profile(self.ctx, C.c_int(1 if enable else 0)), "ep_profile")

@@ -351,3 +351,44 @@ def replicate_worlds(shapes, bodies, params, times):
                    con_kind=np.tile(params.con_kind, times) if nc else (),
                    con_data=np.tile(params.con_data, (times, 1)) if nc else ())
     return shapes, b, p
+
+
+def slice_batch(bodies, params, worlds):
+    """The listed worlds of a packed batch as a batch of their own (rows, shape instances, constraint endpoints rebased;
+    same shape table): worlds are independent `simulate` calls (src/Physics.elm:522-525), so a sample of a large batch can
+    be stepped on its own -- by the CPU oracle in the full-size parity tests -- and compared with the same worlds of the
+    whole batch.  Batches with `collide` masks are not supported."""
+    from . import abi
+    assert params.collide is None
+    worlds = [int(w) for w in worlds]
+    rows = np.concatenate([np.arange(bodies.world_body_off[w], bodies.world_body_off[w + 1]) for w in worlds]).astype(np.int64)
+    new_row = -np.ones(bodies.n_bodies, np.int64)
+    new_row[rows] = np.arange(len(rows))
+    counts = [int(bodies.world_body_off[w + 1] - bodies.world_body_off[w]) for w in worlds]
+    wbo = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    icount = (bodies.inst_off[rows + 1] - bodies.inst_off[rows]).astype(np.int64)
+    ioff = np.concatenate([[0], np.cumsum(icount)]).astype(np.int32)
+    inst = np.concatenate([np.arange(bodies.inst_off[r], bodies.inst_off[r + 1]) for r in rows]).astype(np.int64) if len(rows) else np.zeros(0, np.int64)
+    b = abi.Bodies(wbo, bodies.body_id[rows], bodies.kind[rows], ioff, bodies.inst_shape[inst], bodies.inst_friction[inst],
+                   bodies.inst_bounciness[inst], **{name: getattr(bodies, name)[rows] for name, _ in abi.BODY_F64_FIELDS})
+    keep = np.nonzero(new_row[params.con_body_a] >= 0)[0] if params.n_constraints else np.zeros(0, np.int64)
+    p = abi.Params(params.gravity[worlds], params.dt[worlds], params.iterations[worlds],
+                   con_body_a=new_row[params.con_body_a[keep]] if len(keep) else (), con_body_b=new_row[params.con_body_b[keep]] if len(keep) else (),
+                   con_kind=params.con_kind[keep] if len(keep) else (), con_data=params.con_data[keep] if len(keep) else ())
+    return b, p, rows
+
+
+def car_batch(n_worlds, distinct=64, seed=55):
+    """C5 at any size without building every world through the Python object layer: `distinct` car worlds (car_world seeds
+    0..distinct-1) tiled to n_worlds, then every world made different -- each dynamic body gets its own small seeded
+    velocity and spin kick -- so that a sample of worlds is a real test of the whole batch."""
+    from . import pack
+    distinct = min(distinct, n_worlds)
+    assert n_worlds % distinct == 0
+    shapes, bodies, params = pack.pack_worlds(car_worlds(distinct))
+    shapes, bodies, params = replicate_worlds(shapes, bodies, params, n_worlds // distinct)
+    u = uniforms(scene_seed(5, seed), (bodies.n_bodies, 6))
+    dyn = (bodies.kind == 2)[:, None]
+    bodies.vel[...] = bodies.vel + dyn * (u[:, 0:3] - 0.5) * 0.6
+    bodies.angvel[...] = bodies.angvel + dyn * (u[:, 3:6] - 0.5) * 1.0
+    return shapes, bodies, params

@@ -243,7 +243,10 @@ int ep_stats(ep_ctx* ctx, int64_t* out, int32_t n);   /* see EP_STAT_* */
 enum { EP_STAT_KERNEL_LAUNCHES = 0, EP_STAT_CANDIDATE_PAIRS = 1, EP_STAT_GROUPS = 2, EP_STAT_CONTACTS = 3,
        EP_STAT_ISLANDS = 4,
        /* cumulative since ep_upload_worlds: sum over islands of contacts x PGS iterations run, joint rows x iterations run */
-       EP_STAT_CONTACT_ITERATIONS = 5, EP_STAT_JOINT_ROW_ITERATIONS = 6, EP_STAT_COUNT = 8 };
+       EP_STAT_CONTACT_ITERATIONS = 5, EP_STAT_JOINT_ROW_ITERATIONS = 6,
+       /* cumulative: early-exit decisions of the multi-lane island solvers that were taken from the re-summation of
+          |deltaLambda| in the reference's association (src/Internal/Solver.elm:345-367) instead of the parallel sum */
+       EP_STAT_RESUMS = 7, EP_STAT_COUNT = 8 };
 /* Per-kernel device timing.  ep_profile(ctx, 1) makes ep_step_resident bracket every kernel launch with
  * CUDA events on the context's stream and resets the accumulators; ep_kernel_times synchronises and returns
  * the accumulated milliseconds and launch counts per kernel kind (EP_K_*).  Launch counts are always kept. */

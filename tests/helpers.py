@@ -134,3 +134,45 @@ def pair_worlds(seed, per_combo=6, gravity=(0.0, 0.0, -9.80665), spread=0.9):
                 bodies, _ = P.assign_ids([("a", place(a, oa)), ("b", place(b, ob))])
                 worlds.append((cfg, bodies))
     return worlds
+
+
+def assert_world_contacts_equal(a, wa, b, wb, what=""):
+    """World `wa` of contact block `a` == world `wb` of block `b`, bit for bit (groups, contacts, islands, iterations):
+    the comparison behind the full-size tests, where `b` is the CPU oracle run on a SAMPLE of the worlds of `a`."""
+    ga0, ga1 = int(a.world_group_off[wa]), int(a.world_group_off[wa + 1])
+    gb0, gb1 = int(b.world_group_off[wb]), int(b.world_group_off[wb + 1])
+    assert ga1 - ga0 == gb1 - gb0, f"{what}: world {wa}: {ga1 - ga0} vs {gb1 - gb0} pair groups"
+    ca0, ca1 = int(a.group_contact_off[ga0]), int(a.group_contact_off[ga1])
+    cb0, cb1 = int(b.group_contact_off[gb0]), int(b.group_contact_off[gb1])
+    assert ca1 - ca0 == cb1 - cb0, f"{what}: world {wa}: {ca1 - ca0} vs {cb1 - cb0} contacts"
+    assert ((a.group_contact_off[ga0:ga1 + 1] - ca0) == (b.group_contact_off[gb0:gb1 + 1] - cb0)).all(), f"{what}: world {wa}: group_contact_off"
+    for name in ("group_id1", "group_id2", "group_n_constraints", "group_pre_pos1", "group_pre_quat1", "group_island"):
+        x, y = getattr(a, name)[ga0:ga1], getattr(b, name)[gb0:gb1]
+        assert x.tobytes() == y.tobytes(), f"{what}: world {wa}: {name} differs"
+    for name, _, _ in abi.CONTACT_FIELDS:
+        x, y = getattr(a, name)[ca0:ca1], getattr(b, name)[cb0:cb1]
+        assert x.tobytes() == y.tobytes(), f"{what}: world {wa}: contact field {name} differs"
+    assert a.iterations[wa] == b.iterations[wb] and a.world_n_islands[wa] == b.world_n_islands[wb], f"{what}: world {wa}: iterations / islands"
+
+
+def sample_vs_oracle(oracle, engine, shapes, bodies, params, steps, sample, group_cap, contact_cap, what=""):
+    """`steps` resident GPU steps of the WHOLE batch; the CPU oracle steps only the worlds in `sample` (as a batch of their
+    own: worlds are independent, src/Physics.elm:522-525); those worlds must agree bit for bit -- bodies and contacts."""
+    from elm_physics_b200 import scenes
+    bs, ps, rows = scenes.slice_batch(bodies, params, sample)
+    os_ = contacts_for(bs)
+    oracle.step(shapes, bs, ps, None, os_, steps)
+    bg = bodies.copy()
+    og = abi.Contacts(bodies.n_worlds, group_cap, contact_cap)
+    engine.upload_shapes(shapes)
+    engine.upload_worlds(bg, params, None)
+    engine.step_resident(steps)
+    engine.sync()
+    engine.download_bodies(bg)
+    engine.download_contacts(og)
+    for name in abi.BODY_INOUT:
+        x, y = getattr(bg, name)[rows], getattr(bs, name)
+        assert x.tobytes() == y.tobytes(), f"{what}: body field {name} differs in the sampled worlds"
+    for k, w in enumerate(sample):
+        assert_world_contacts_equal(og, int(w), os_, k, what)
+    return bg, og, bs, os_

@@ -391,3 +391,28 @@ def test_full_size_c3_properties(engine):
     for name in abi.BODY_INOUT:
         assert getattr(bodies, name)[:r1].tobytes() == getattr(b1, name).tobytes(), name
     assert (o1.iterations[:16] >= 1).all() and (o1.iterations[:16] <= 20).all()
+
+
+def test_upload_rejects_duplicate_ids_and_reports_item_overflow(engine):
+    """The dense warm-start table equals bodyKey(id1, id2) (ContactId.elm:62-68) only for ids unique in a world: duplicates
+    are refused (the caller runs AssignIds.assignIds first).  A narrowphase work-item pool that is too small is reported
+    under its own name."""
+    from elm_physics_b200 import engine as eng
+    shapes, bodies, params = scenes.mixed_worlds(2)
+    engine.upload_shapes(shapes)
+    dup = bodies.copy()
+    dup.body_id = dup.body_id.copy()          # Bodies.copy shares the topology arrays
+    dup.body_id[3] = dup.body_id[2]
+    dup._rebuild()
+    with pytest.raises(eng.EngineError, match="duplicate body id"):
+        engine.upload_worlds(dup, params, None)
+    e = eng.Engine(0)
+    try:
+        e.upload_shapes(shapes)
+        e.configure(item_cap=64)
+        e.upload_worlds(bodies.copy(), params, None)
+        e.step_resident(100)
+        with pytest.raises(eng.EngineError, match="work-item pool overflow"):
+            e.sync()
+    finally:
+        e.close()
