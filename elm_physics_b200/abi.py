@@ -16,6 +16,11 @@ EP_CONVEX_F64_HEADER, EP_CONVEX_I32_HEADER, EP_GROUP_F64, EP_GROUP_I32, EP_EDGE_
 EP_STAT_COUNT = 8
 EP_K_COUNT = 18
 EP_OPT_PATH, EP_OPT_CONTACT_CAP, EP_OPT_RAW_CAP, EP_OPT_ITEM_CAP = 0, 1, 2, 3
+# ep_step_frame_fields masks
+EP_F_POS, EP_F_QUAT, EP_F_VEL, EP_F_ANGVEL, EP_F_FORCE, EP_F_TORQUE, EP_F_INV_INERTIA_WORLD, EP_F_CONSTANTS = 1, 2, 4, 8, 16, 32, 64, 128
+EP_F_STATE, EP_F_ALL = 15, 255
+BODY_FIELD_MASK = {"pos": 1, "quat": 2, "vel": 4, "angvel": 8, "force": 16, "torque": 32, "inv_inertia_world": 64, "inv_mass": 128,
+                   "inv_inertia": 128, "lin_damp_pow": 128, "ang_damp_pow": 128, "lin_lock": 128, "ang_lock": 128, "bounding_radius": 128}
 
 _pi32 = C.POINTER(C.c_int32)
 _pi64 = C.POINTER(C.c_int64)

@@ -70,6 +70,7 @@ struct ep_ctx {
   int64_t stats[EP_STAT_COUNT] = {0};
   // ep_raycast scratch (device), grown on demand
   void* ray_buf = nullptr; size_t ray_cap = 0;
+  bool placed_current = false;      // the world-placed shape copies match the bodies' current transforms (ep_raycast)
 };
 
 #define CK(call)                                                                                         \
@@ -525,6 +526,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_worlds = true;
+  ctx->placed_current = false;
   return EP_OK;
 }
 
@@ -605,6 +607,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
   if (d.n_bodies == 0) return EP_OK;
   const int gw = std::max(1, std::min(d.n_worlds, ctx->sm_count * 16));
   const int gwide = ctx->sm_count * 8;
+  if (n_steps > 0) ctx->placed_current = false;
   for (int s = 0; s < n_steps; s++) {
     CK(cudaMemsetAsync(d.cur.counters, 0, CNT_COUNT * sizeof(int32_t), st));
     CK(cudaMemsetAsync(d.key_cnt, 0, 2 * kKeys * sizeof(int32_t), st));
@@ -742,13 +745,15 @@ extern "C" int ep_download_bodies(ep_ctx* ctx, ep_bodies* B) {
   const Dev& d = ctx->d;
   size_t nb = d.n_bodies;
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(B->pos, d.pos, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->quat, d.quat, 4 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->vel, d.vel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->angvel, d.angvel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->force, d.force, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->torque, d.torque, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->inv_inertia_world, d.iiw, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  const uint32_t down = EP_F_ALL;
+  auto D2H = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st); };
+  if (down & EP_F_POS) CK(D2H(B->pos, d.pos, 3 * nb));
+  if (down & EP_F_QUAT) CK(D2H(B->quat, d.quat, 4 * nb));
+  if (down & EP_F_VEL) CK(D2H(B->vel, d.vel, 3 * nb));
+  if (down & EP_F_ANGVEL) CK(D2H(B->angvel, d.angvel, 3 * nb));
+  if (down & EP_F_FORCE) CK(D2H(B->force, d.force, 3 * nb));          // zeros for every non-static body (SolverBody.elm:139-141, 221-223)
+  if (down & EP_F_TORQUE) CK(D2H(B->torque, d.torque, 3 * nb));
+  if (down & EP_F_INV_INERTIA_WORLD) CK(D2H(B->inv_inertia_world, d.iiw, 9 * nb));
   return check_flags(ctx);
 }
 
@@ -822,7 +827,9 @@ static FrameGate& frame_gate(int device) {
   return gates[device < 0 || device >= 64 ? 0 : device];
 }
 
-extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
+extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) { return ep_step_frame_fields(ctx, B, out, EP_F_ALL, EP_F_ALL); }
+
+extern "C" int ep_step_frame_fields(ep_ctx* ctx, ep_bodies* B, ep_contacts* out, uint32_t up, uint32_t down) {
   if (!ctx || !B) return EP_EINVAL;
   if (!ctx->have_worlds) { ctx->err = "no resident worlds (ep_upload_worlds first)"; return EP_ESTATE; }
   Dev& d = ctx->d;
@@ -840,11 +847,20 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
   const bool early_out = pipelined && out && !out->lambda && !out->t1 && !out->iterations && !out->world_n_islands;
   cudaStream_t sin = pipelined ? ctx->cin : st;
   auto H2D = [&](cudaStream_t sx, const double* dst, const double* src, size_t n) { return cudaMemcpyAsync((void*)dst, src, n * sizeof(double), cudaMemcpyHostToDevice, sx); };
-  CK(H2D(st, d.pos, B->pos, 3 * nb)); CK(H2D(st, d.quat, B->quat, 4 * nb)); CK(H2D(st, d.radius, B->bounding_radius, nb));
-  CK(H2D(sin, d.vel, B->vel, 3 * nb)); CK(H2D(sin, d.angvel, B->angvel, 3 * nb));
-  CK(H2D(sin, d.force, B->force, 3 * nb)); CK(H2D(sin, d.torque, B->torque, 3 * nb)); CK(H2D(sin, d.iiw, B->inv_inertia_world, 9 * nb));
-  CK(H2D(sin, d.inv_mass, B->inv_mass, nb)); CK(H2D(sin, d.inv_inertia, B->inv_inertia, 3 * nb)); CK(H2D(sin, d.ldp, B->lin_damp_pow, nb)); CK(H2D(sin, d.adp, B->ang_damp_pow, nb));
-  CK(H2D(sin, d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(sin, d.ang_lock, B->ang_lock, 3 * nb));
+  // what the front kernels read goes first, on the main stream; the rest on the copy-in stream beside them.  Arrays the caller
+  // did not touch since the last frame are not sent: the resident copy is what the last frame returned (`up`, EP_F_*)
+  if (up & EP_F_POS) CK(H2D(st, d.pos, B->pos, 3 * nb));
+  if (up & EP_F_QUAT) CK(H2D(st, d.quat, B->quat, 4 * nb));
+  if (up & EP_F_CONSTANTS) CK(H2D(st, d.radius, B->bounding_radius, nb));
+  if (up & EP_F_VEL) CK(H2D(sin, d.vel, B->vel, 3 * nb));
+  if (up & EP_F_ANGVEL) CK(H2D(sin, d.angvel, B->angvel, 3 * nb));
+  if (up & EP_F_FORCE) CK(H2D(sin, d.force, B->force, 3 * nb));
+  if (up & EP_F_TORQUE) CK(H2D(sin, d.torque, B->torque, 3 * nb));
+  if (up & EP_F_INV_INERTIA_WORLD) CK(H2D(sin, d.iiw, B->inv_inertia_world, 9 * nb));
+  if (up & EP_F_CONSTANTS) {
+    CK(H2D(sin, d.inv_mass, B->inv_mass, nb)); CK(H2D(sin, d.inv_inertia, B->inv_inertia, 3 * nb)); CK(H2D(sin, d.ldp, B->lin_damp_pow, nb)); CK(H2D(sin, d.adp, B->ang_damp_pow, nb));
+    CK(H2D(sin, d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(sin, d.ang_lock, B->ang_lock, 3 * nb));
+  }
   if (pipelined) CK(cudaEventRecord(ctx->ev_in, ctx->cin));
   {
     // Several contexts on one device (sub-batches driven from their own host threads) take turns on the SMs when the
@@ -869,13 +885,14 @@ extern "C" int ep_step_frame(ep_ctx* ctx, ep_bodies* B, ep_contacts* out) {
     if (rc != EP_OK) return rc;
     if (gated) CK(cudaEventRecord(g.ev, st));
   }
-  CK(cudaMemcpyAsync(B->pos, d.pos, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->quat, d.quat, 4 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->vel, d.vel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->angvel, d.angvel, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->force, d.force, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->torque, d.torque, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(B->inv_inertia_world, d.iiw, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  auto D2H = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st); };
+  if (down & EP_F_POS) CK(D2H(B->pos, d.pos, 3 * nb));
+  if (down & EP_F_QUAT) CK(D2H(B->quat, d.quat, 4 * nb));
+  if (down & EP_F_VEL) CK(D2H(B->vel, d.vel, 3 * nb));
+  if (down & EP_F_ANGVEL) CK(D2H(B->angvel, d.angvel, 3 * nb));
+  if (down & EP_F_FORCE) CK(D2H(B->force, d.force, 3 * nb));          // zeros for every non-static body (SolverBody.elm:139-141, 221-223)
+  if (down & EP_F_TORQUE) CK(D2H(B->torque, d.torque, 3 * nb));
+  if (down & EP_F_INV_INERTIA_WORLD) CK(D2H(B->inv_inertia_world, d.iiw, 9 * nb));
   if (out) {
     if (early_out) {       // marshalled in the middle of the step on the copy-out stream (the frame is d.prev by now)
       TRY(copy_out_contacts(ctx, d.prev, out, ctx->cout));
@@ -893,14 +910,15 @@ extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, 
   return EP_OK;
 }
 
-extern "C" int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world, const double* from, const double* direction,
-                          int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal) {
-  if (!ctx || n_rays < 0 || (n_rays > 0 && (!ray_world || !from || !direction || !hit_body || !hit_distance || !hit_point || !hit_normal))) return EP_EINVAL;
+static int raycast_impl(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_ref, const double* from, const double* direction,
+                        int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal, int attached) {
+  if (!ctx || n_rays < 0 || (n_rays > 0 && (!ray_ref || !from || !direction || !hit_body || !hit_distance || !hit_point || !hit_normal))) return EP_EINVAL;
   if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
   if (n_rays == 0) return EP_OK;
   Dev& d = ctx->d;
+  const int limit = attached ? d.n_bodies : d.n_worlds;
   for (int i = 0; i < n_rays; i++)
-    if (ray_world[i] < 0 || ray_world[i] >= d.n_worlds) { ctx->err = "ray_world out of range"; return EP_EINVAL; }
+    if (ray_ref[i] < 0 || ray_ref[i] >= limit) { ctx->err = attached ? "ray_body out of range" : "ray_world out of range"; return EP_EINVAL; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t n = (size_t)n_rays, bytes = n * (4 + 24 + 24 + 4 + 8 + 24 + 24) + 256;
@@ -917,11 +935,13 @@ extern "C" int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world,
   int* d_world = (int*)(d_normal + 3 * n); int* d_hit = d_world + n;
   CK(cudaMemcpyAsync(d_from, from, 24 * n, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_dir, direction, 24 * n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_world, ray_world, 4 * n, cudaMemcpyHostToDevice, st));
-  // worldShapesWithMaterials follow the bodies' CURRENT transforms (SolverBody.elm:212): the placed copies are refreshed
-  // at the start of a step, so refresh them here for the state the last step left
-  if (d.n_pl_all > 0) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
-  k_raycast<<<grid_for(ctx, n_rays, 128, 16), 128, 0, st>>>(d, n_rays, d_world, d_from, d_dir, d_hit, d_dist, d_point, d_normal);
+  CK(cudaMemcpyAsync(d_world, ray_ref, 4 * n, cudaMemcpyHostToDevice, st));
+  // worldShapesWithMaterials follow the bodies' CURRENT transforms (SolverBody.elm:212): the placed copies are refreshed at
+  // the start of a step, so they are refreshed here for the state the last step left -- once: further casts against the
+  // same state (the four wheels of a car, every frame) reuse them
+  if (d.n_pl_all > 0 && !ctx->placed_current) { k_place<<<grid_for(ctx, d.n_pl_all, 256, 16), 256, 0, st>>>(d, d.n_pl_all); ctx->launches++; }
+  ctx->placed_current = true;
+  k_raycast<<<grid_for(ctx, n_rays, 128, 16), 128, 0, st>>>(d, n_rays, d_world, d_from, d_dir, d_hit, d_dist, d_point, d_normal, attached);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(hit_body, d_hit, 4 * n, cudaMemcpyDeviceToHost, st));
@@ -929,6 +949,46 @@ extern "C" int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world,
   CK(cudaMemcpyAsync(hit_point, d_point, 24 * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(hit_normal, d_normal, 24 * n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return EP_OK;
+}
+extern "C" int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world, const double* from, const double* direction,
+                          int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal) {
+  return raycast_impl(ctx, n_rays, ray_world, from, direction, hit_body, hit_distance, hit_point, hit_normal, 0);
+}
+extern "C" int ep_raycast_attached(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_body, const double* local_from, const double* local_direction,
+                                   int32_t* hit_body, double* hit_distance, double* hit_point, double* hit_normal) {
+  return raycast_impl(ctx, n_rays, ray_body, local_from, local_direction, hit_body, hit_distance, hit_point, hit_normal, 1);
+}
+
+// The 22 doubles per body that a step writes (SolverBody.elm:97-225: transform3d 7, velocity 3, angularVelocity 3,
+// invInertiaWorld 9), packed [n_bodies][22] into DEVICE memory of the caller on stream `stream` (NULL: the context's): the
+// send buffer of the one collective of a sharded batch, the final state gather (ncclAllGather), without host staging.
+namespace ep {
+__global__ void k_pack_state(Dev d, double* out) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < d.n_bodies; r += gridDim.x * blockDim.x) {
+    double* o = out + 22 * (size_t)r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[k] = d.pos[3 * (size_t)r + k]; o[7 + k] = d.vel[3 * (size_t)r + k]; o[10 + k] = d.angvel[3 * (size_t)r + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[3 + k] = d.quat[4 * (size_t)r + k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[13 + k] = d.iiw[9 * (size_t)r + k];
+  }
+}
+}  // namespace ep
+extern "C" int ep_pack_state_device(ep_ctx* ctx, void* dst_device, void* stream) {
+  if (!ctx || !dst_device) return EP_EINVAL;
+  if (!ctx->have_worlds) { ctx->err = "no resident worlds"; return EP_ESTATE; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t sx = stream ? (cudaStream_t)stream : ctx->stream;
+  if (ctx->d.n_bodies == 0) return EP_OK;
+  if (sx != ctx->stream) {     // order behind the steps already enqueued on the context's stream
+    CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
+    CK(cudaStreamWaitEvent(sx, ctx->ev_mid, 0));
+  }
+  k_pack_state<<<grid_for(ctx, ctx->d.n_bodies, 256, 16), 256, 0, sx>>>(ctx->d, (double*)dst_device);
+  ctx->launches++;
+  CK(cudaGetLastError());
   return EP_OK;
 }
 

@@ -110,13 +110,23 @@ EPD RayHit ray_capsule(V3 from, V3 dir, const Cap& s) {
   return h;
 }
 
+// attached != 0: ray_world holds BODY rows; the ray is given in the centre-of-mass frame of that body, placed in the world with the
+// body's current transform3d (Transform3d.pointPlaceIn / directionPlaceIn) and never hits its own body -- the RaycastCar pattern
+// (examples/src/RaycastCar/Car.elm:116-128: `Axis3d.placeIn frame`, cast against the bodies without the car)
 __global__ void __launch_bounds__(128) k_raycast(Dev d, int n_rays, const int* ray_world, const double* from, const double* direction,
-                                                  int* hit_body, double* hit_distance, double* hit_point, double* hit_normal) {
+                                                  int* hit_body, double* hit_distance, double* hit_point, double* hit_normal, int attached) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x) {
-    const int w = ray_world[i];
-    const V3 f = ld3(from + 3 * (size_t)i), dir = ld3(direction + 3 * (size_t)i);
+    const int own = attached ? ray_world[i] : -1;
+    const int w = attached ? d.body_world[own] : ray_world[i];
+    V3 f = ld3(from + 3 * (size_t)i), dir = ld3(direction + 3 * (size_t)i);
+    if (attached) {
+      Q4 q; q.x = d.quat[4 * (size_t)own]; q.y = d.quat[4 * (size_t)own + 1]; q.z = d.quat[4 * (size_t)own + 2]; q.w = d.quat[4 * (size_t)own + 3];
+      f = point_place(ld3(d.pos + 3 * (size_t)own), q, f);
+      dir = rotate(q, dir);
+    }
     bool any = false; int bestBody = -1; RayHit best; best.some = false; best.distance = 0; best.point = mk(0, 0, 0); best.normal = mk(0, 0, 0);
     for (int r = d.world_body_off[w]; r < d.world_body_off[w + 1]; r++) {
+      if (r == own) continue;
       RayHit bodyHit; bodyHit.some = false; bodyHit.distance = 0; bodyHit.point = mk(0, 0, 0); bodyHit.normal = mk(0, 0, 0);
       for (int inst = d.inst_off[r]; inst < d.inst_off[r + 1]; inst++) {
         const ShapeRef s = shape_ref(d, inst);

@@ -17,7 +17,7 @@ _LIB = None
 EXPORTS = ("ep_create", "ep_destroy", "ep_last_error", "ep_upload_shapes", "ep_upload_worlds", "ep_step_resident",
            "ep_sync", "ep_download_bodies", "ep_download_contacts", "ep_step", "ep_stats", "ep_stream",
            "ep_profile", "ep_kernel_times", "ep_kernel_name", "ep_configure", "ep_step_frame", "ep_host_alloc",
-           "ep_host_free", "ep_raycast", "ep_apply")
+           "ep_host_free", "ep_raycast", "ep_apply", "ep_raycast_attached", "ep_step_frame_fields", "ep_pack_state_device")
 
 
 class EngineError(RuntimeError):
@@ -127,10 +127,21 @@ class Engine:
                                   C.byref(warm.c) if warm is not None else None,
                                   C.byref(out.c) if out is not None else None, C.c_int32(n_steps)), "ep_step")
 
-    def step_frame(self, bodies, out=None):
-        """ep_step_frame: one frame of the resident batch through host buffers (state in, state + contacts out)."""
-        self._ck(self.lib.ep_step_frame(self.ctx, C.byref(bodies.c), C.byref(out.c) if out is not None else None),
-                 "ep_step_frame")
+    def step_frame(self, bodies, out=None, upload=None, download=None):
+        """ep_step_frame / ep_step_frame_fields: one frame of the resident batch through host buffers (state in, state +
+        contacts out).  `upload` / `download`: abi.EP_F_* masks of the per-body arrays to move (None = every array)."""
+        if upload is None and download is None:
+            self._ck(self.lib.ep_step_frame(self.ctx, C.byref(bodies.c), C.byref(out.c) if out is not None else None), "ep_step_frame")
+            return
+        up = abi.EP_F_ALL if upload is None else upload
+        down = abi.EP_F_ALL if download is None else download
+        self._ck(self.lib.ep_step_frame_fields(self.ctx, C.byref(bodies.c), C.byref(out.c) if out is not None else None,
+                                               C.c_uint32(up), C.c_uint32(down)), "ep_step_frame_fields")
+
+    def pack_state_device(self, dst_ptr, stream=None):
+        """ep_pack_state_device: the 22 output doubles per body into caller-owned DEVICE memory ([n_bodies][22] f64), on `stream`
+        (a cudaStream_t handle; None = the context's): the send buffer of the final NCCL state gather."""
+        self._ck(self.lib.ep_pack_state_device(self.ctx, C.c_void_p(dst_ptr), C.c_void_p(stream) if stream else None), "ep_pack_state_device")
 
     def raycast(self, ray_world, origins, directions):
         """ep_raycast (Physics.raycast, src/Physics.elm:802-841) over the resident worlds.  Returns
@@ -144,6 +155,22 @@ class Engine:
         self._ck(self.lib.ep_raycast(self.ctx, C.c_int32(n), rw.ctypes.data_as(pi), o.ctypes.data_as(pf), dr.ctypes.data_as(pf),
                                      hit.ctypes.data_as(pi), dist.ctypes.data_as(pf), point.ctypes.data_as(pf),
                                      normal.ctypes.data_as(pf)), "ep_raycast")
+        return hit, dist, point, normal
+
+    def raycast_attached(self, ray_body, local_origins, local_directions):
+        """ep_raycast_attached: rays given in the centre-of-mass frame of body rows `ray_body`, placed with the bodies' current
+        transforms on the device, cast against the other bodies of each body's world (the RaycastCar pattern)."""
+        rb = np.ascontiguousarray(ray_body, dtype=np.int32)
+        o = np.ascontiguousarray(local_origins, dtype=np.float64).reshape(-1, 3)
+        dr = np.ascontiguousarray(local_directions, dtype=np.float64).reshape(-1, 3)
+        n = len(rb)
+        if not hasattr(self, "_ray_out") or len(self._ray_out[0]) != n:
+            self._ray_out = (np.zeros(n, np.int32), np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3)))
+        hit, dist, point, normal = self._ray_out
+        pf, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._ck(self.lib.ep_raycast_attached(self.ctx, C.c_int32(n), rb.ctypes.data_as(pi), o.ctypes.data_as(pf), dr.ctypes.data_as(pf),
+                                              hit.ctypes.data_as(pi), dist.ctypes.data_as(pf), point.ctypes.data_as(pf),
+                                              normal.ctypes.data_as(pf)), "ep_raycast_attached")
         return hit, dist, point, normal
 
     def apply(self, kind, body_row, a, b):

@@ -215,6 +215,19 @@ int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_co
  * return.  Contexts of one device may be driven from different host threads concurrently (one thread per context). */
 int ep_step_frame(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out);
 
+/* The same frame moving only the arrays that changed hands.  `upload`: the per-body arrays the caller modified since the
+ * last frame (the resident copy of the others IS what the last frame returned; constants -- inverse mass and inertia, damping
+ * powers, lock masks, bounding radius -- came with ep_upload_worlds).  A simulate loop that only reads the bodies sends nothing
+ * or the dynamic state (EP_F_STATE); one that pushed bodies (src/Physics.elm:857-1017) adds EP_F_FORCE | EP_F_TORQUE on those
+ * frames; one that moved / rotated bodies adds EP_F_INV_INERTIA_WORLD (Physics.elm:291-303 recompute it caller-side).
+ * `download`: the arrays to copy back.  force / torque of every non-static body are zero after a step
+ * (src/Internal/SolverBody.elm:139-141, 221-223) and invInertiaWorld is a function of the returned orientation
+ * (Transform3d.elm:181-205), so EP_F_STATE is everything `Physics.simulate`'s caller cannot derive itself.
+ * ep_step_frame == ep_step_frame_fields(.., EP_F_ALL, EP_F_ALL). */
+enum { EP_F_POS = 1, EP_F_QUAT = 2, EP_F_VEL = 4, EP_F_ANGVEL = 8, EP_F_FORCE = 16, EP_F_TORQUE = 32, EP_F_INV_INERTIA_WORLD = 64,
+       EP_F_CONSTANTS = 128, EP_F_STATE = 15, EP_F_ALL = 255 };
+int ep_step_frame_fields(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out, uint32_t upload, uint32_t download);
+
 /* `Physics.raycast` (src/Physics.elm:802-841) for a batch of rays against the RESIDENT worlds in their current state (after
  * the last step / upload): ray r runs against the bodies of world ray_world[r] in list order; closest hit over every
  * shape of every body (src/Internal/Body.elm:465-489, src/Internal/Shape.elm:132-148), first hit wins ties, point masses
@@ -222,6 +235,21 @@ int ep_step_frame(ep_ctx* ctx, ep_bodies* bodies, ep_contacts* out);
  * hit_normal is normalised (Vec3.normalize).  Host buffers, synchronous. */
 int ep_raycast(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_world, const double* from /*[n][3]*/, const double* direction /*[n][3]*/,
                int32_t* hit_body, double* hit_distance, double* hit_point /*[n][3]*/, double* hit_normal /*[n][3]*/);
+
+/* The same for rays ATTACHED to bodies -- the RaycastCar pattern (examples/src/RaycastCar/Car.elm:116-128: a ray through a point of
+ * the chassis along its down direction, `Axis3d.placeIn frame`, cast against the bodies WITHOUT the car, four per car and frame):
+ * ray r is given in the centre-of-mass frame of global body row ray_body[r] and placed in the world on the device with that
+ * body's current transform3d (Transform3d.pointPlaceIn for the origin, directionPlaceIn for the direction,
+ * src/Internal/Transform3d.elm:134-153, 218-220), so a resident batch needs no state download between steps; it runs against
+ * the other bodies of that body's world (its own body is skipped). */
+int ep_raycast_attached(ep_ctx* ctx, int32_t n_rays, const int32_t* ray_body, const double* local_from /*[n][3]*/, const double* local_direction /*[n][3]*/,
+                        int32_t* hit_body, double* hit_distance, double* hit_point /*[n][3]*/, double* hit_normal /*[n][3]*/);
+
+/* The 22 doubles per body a step writes (src/Internal/SolverBody.elm:97-225: transform3d 7, velocity 3, angularVelocity 3,
+ * invInertiaWorld 9) packed [n_bodies][22] into DEVICE memory of the caller, on `stream` (a cudaStream_t; NULL = the context's
+ * stream), ordered behind the steps already enqueued: the send buffer of the one collective of a batch sharded over several
+ * GPUs -- the final state gather (ncclAllGather over NVLink) -- with no host staging.  Asynchronous. */
+int ep_pack_state_device(ep_ctx* ctx, void* dst_device, void* stream);
 
 /* Between-step body mutators on the RESIDENT state, so that a multi-step batch can push bodies without a host round trip
  * (src/Physics.elm:857-1017 over src/Internal/Body.elm:305-430).  Operation k acts on global body row body_row[k]; operations

@@ -305,6 +305,49 @@ def test_step_frame_host_buffers_lockstep(engine, oracle):
         pool.close()
 
 
+def test_step_frame_fields_masked_lockstep(engine, oracle):
+    """ep_step_frame_fields: only the dynamic state goes up (EP_F_STATE) and comes back, forces / torques only on the frames
+    that pushed bodies, constants never again after ep_upload_worlds -- 60 frames in lock step with the oracle, which is fed
+    every array every frame.  The host copies of the arrays that are not downloaded are reconstructed the way a caller would:
+    force / torque are zero after a step (SolverBody.elm:139-141, 221-223)."""
+    from elm_physics_b200.engine import PinnedPool
+    shapes, bodies, params = scenes.mixed_worlds(6)
+    pool = PinnedPool()
+    try:
+        bo, bg = bodies.copy(), bodies.copy(alloc=pool.empty)
+        engine.upload_shapes(shapes)
+        engine.upload_worlds(bg, params, None)
+        cap = H.contacts_for(bodies)
+        og = abi.Contacts(bodies.n_worlds, cap.group_cap, cap.contact_cap, alloc=pool.empty)
+        wo = None
+        rng = np.random.RandomState(7)
+        for s in range(60):
+            up = abi.EP_F_STATE
+            if s % 7 == 3:
+                rows = rng.randint(0, bodies.n_bodies, 9)
+                push = rng.uniform(-300, 300, (9, 3))
+                for b in (bo, bg):
+                    b.force[rows] += push
+                    b.torque[rows] += 0.1 * push
+                up |= abi.EP_F_FORCE | abi.EP_F_TORQUE
+            oo = H.contacts_for(bodies)
+            oracle.step(shapes, bo, params, wo, oo, 1)
+            engine.step_frame(bg, og, upload=up, download=abi.EP_F_STATE)
+            moving = bodies.kind != abi.EP_STATIC
+            bg.force[moving] = 0.0; bg.torque[moving] = 0.0          # what the library guarantees for every non-static body; not read back
+            H.assert_contacts_equal(oo, og, f"masked step_frame {s}")
+            for name in ("pos", "quat", "vel", "angvel"):
+                assert getattr(bo, name).tobytes() == getattr(bg, name).tobytes(), (s, name)
+            wo = oo
+        # invInertiaWorld was never read back on the way; on request it is the oracle's
+        engine.step_frame(bg, og, upload=0, download=abi.EP_F_ALL)
+        oo = H.contacts_for(bodies)
+        oracle.step(shapes, bo, params, wo, oo, 1)
+        H.assert_bodies_equal(bo, bg, "masked step_frame, full read-back")
+    finally:
+        pool.close()
+
+
 def test_step_frame_contact_points_fields_only(engine):
     """ep_step_frame with only the arrays Physics.contactPoints reads (the other ep_contacts pointers NULL) returns the
     same bodies and, in those arrays, the same bytes as the call that copies every array back; the skipped arrays of the

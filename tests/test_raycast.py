@@ -127,3 +127,66 @@ def test_gpu_body_mutators_match_oracle(oracle):
             H.assert_bodies_equal(bo, bg, f"mutators round {rnd}")
     finally:
         e.close()
+
+
+def _place_rays(pos, quat, local_from, local_dir):
+    """Transform3d.pointPlaceIn (Transform3d.elm:134-153) / directionPlaceIn -> rotate (218-220, 415-432) with numpy, one IEEE
+    operation per reference operation in the reference's order (numpy never fuses), so the result equals the device's."""
+    qx, qy, qz, qw = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+
+    def place(v, origin):                     # Transform3d.pointPlaceIn
+        x, y, z = v[:, 0], v[:, 1], v[:, 2]
+        ix = qw * x + qy * z - qz * y
+        iy = qw * y + qz * x - qx * z
+        iz = qw * z + qx * y - qy * x
+        iw = -qx * x - qy * y - qz * z
+        return np.stack([ix * qw + iw * -qx + iy * -qz - iz * -qy + origin[:, 0],
+                         iy * qw + iw * -qy + iz * -qx - ix * -qz + origin[:, 1],
+                         iz * qw + iw * -qz + ix * -qy - iy * -qx + origin[:, 2]], axis=1)
+
+    def rotate(v):                            # Transform3d.rotate: a DIFFERENT formula from pointPlaceIn (SURVEY 9.3)
+        x, y, z = v[:, 0], v[:, 1], v[:, 2]
+        ix = 2 * (qy * z - qz * y)
+        iy = 2 * (qz * x - qx * z)
+        iz = 2 * (qx * y - qy * x)
+        return np.stack([x + qw * ix + qy * iz - qz * iy, y + qw * iy + qz * ix - qx * iz, z + qw * iz + qx * iy - qy * ix], axis=1)
+    return place(local_from, pos), rotate(local_dir)
+
+
+@pytest.mark.gpu
+def test_gpu_attached_rays_match_oracle(oracle):
+    """ep_raycast_attached (the RaycastCar pattern, examples/src/RaycastCar/Car.elm:116-128): four rays per car given in the
+    chassis frame, placed on the device with the chassis' current transform, cast against the bodies WITHOUT the car.
+    Oracle side: the same rays placed on the host and cast against a copy of the state in which every chassis is moved out of
+    reach (that is what `bodiesWithoutCar` amounts to).  Also: a second cast against the same state reuses the placed shapes."""
+    from elm_physics_b200 import engine as eng
+    shapes, bodies, params = pack.pack_worlds(scenes.car_worlds(12))
+    e = eng.Engine(0)
+    try:
+        e.upload_shapes(shapes)
+        b = bodies.copy()
+        e.upload_worlds(b, params, None)
+        e.step_resident(45)
+        e.sync()
+        e.download_bodies(b)
+        nw = bodies.n_worlds
+        chassis = np.array([int(bodies.world_body_off[w]) + 2 for w in range(nw)], dtype=np.int32)
+        corners = np.array([[-0.9, 1.4, 0.3], [0.9, 1.4, 0.3], [-0.9, -1.4, 0.3], [0.9, -1.4, 0.3]])       # inside the chassis box: the own body must be skipped
+        rb = np.repeat(chassis, 4)
+        lf = np.tile(corners, (nw, 1))
+        ld = np.tile(np.array([[0.0, 0.0, -1.0]]), (4 * nw, 1))
+        launches0 = e.stats()["kernel_launches"]
+        hg = [a.copy() for a in e.raycast_attached(rb, lf, ld)]
+        launches1 = e.stats()["kernel_launches"]
+        hg2 = [a.copy() for a in e.raycast_attached(rb, lf, ld)]
+        assert e.stats()["kernel_launches"] - launches1 == 1 and launches1 - launches0 == 2       # k_place only before the first cast
+        wf, wd = _place_rays(b.pos[rb], b.quat[rb], lf, ld)
+        away = b.copy()
+        away.pos[chassis] += 1.0e6
+        ho = oracle.raycast(shapes, away, np.repeat(np.arange(nw, dtype=np.int32), 4), wf, wd)
+        for k in range(4):
+            assert hg[k].tobytes() == ho[k].tobytes(), k
+            assert hg2[k].tobytes() == hg[k].tobytes(), k
+        assert (hg[0] >= 0).mean() > 0.8 and not np.isin(hg[0], chassis).any()
+    finally:
+        e.close()
