@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""bench.py — body-steps/s of the hot path behind Physics.simulate on BASELINE.json config 3
-(8192 independent worlds x 32 mixed dynamic bodies + a plane, per GPU; worlds sharded by index).
+"""bench.py — body-steps/s of the hot path behind Physics.simulate on BASELINE.json config 3: the batch of 8192
+independent worlds x (32 mixed dynamic bodies + a plane), sharded by world index over the N GPUs (strong scaling: the
+headline; the weak-scaling figure, 8192 worlds per GPU, is reported beside it for N > 1).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement on all host threads
@@ -27,6 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "body_steps_per_sec"
 UNIT = "body-steps/s"
 BODIES_PER_WORLD = 32
+WORKLOAD = "C3: 8192 independent worlds x (32 mixed dynamic bodies + plane), 20 iterations, dt 1/60, sharded by world index"
 
 
 def env_int(name, default):
@@ -160,7 +162,7 @@ def run_reference(args, rank, world_size):
         return
     from elm_physics_b200 import scenes
     cores = host_threads()
-    sample_worlds = min(args.worlds, 64 * cores)
+    sample_worlds = args.worlds                      # the same batch as the GPU arm (same generator, same seeds)
     shapes, bodies, params = scenes.mixed_worlds(sample_worlds)
     import helpers as H
     from elm_physics_b200 import pack
@@ -189,17 +191,17 @@ def run_reference(args, rank, world_size):
 
     for _ in range(args.warmup):
         pass_(1)
-    total = 0.0
-    for _ in range(args.steps):
-        total += pass_(1)
+    times = [pass_(1) for _ in range(args.steps)]
+    total = float(sum(times))
     body_steps = sample_worlds * BODIES_PER_WORLD * args.steps
     value = body_steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "ms_per_step_median": 1e3 * float(np.median(times)),
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3: independent worlds x (32 mixed dynamic bodies + plane), 20 iterations, dt 1/60",
-                   "worlds_per_step": sample_worlds, "bodies_per_world": BODIES_PER_WORLD, "preroll_steps": args.preroll},
+        "config": {"workload": WORKLOAD, "worlds_total": sample_worlds, "bodies_per_world": BODIES_PER_WORLD,
+                   "preroll_steps": args.preroll},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample_worlds} worlds x {args.steps} steps after {args.preroll} pre-roll steps, "
                                    f"{cores} threads (C++ restatement of the Elm path; elm/node absent)"},
@@ -254,7 +256,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--worlds", type=int, default=8192, help="worlds per GPU (weak scaling)")
+    ap.add_argument("--worlds", type=int, default=8192, help="worlds of the whole batch (sharded over the GPUs)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling extra (--worlds per GPU)")
+    ap.add_argument("--no-cars", action="store_true", help="skip the C5 block (65536 car worlds + 4 rays per world per step)")
+    ap.add_argument("--car-worlds", type=int, default=65536)
+    ap.add_argument("--car-steps", type=int, default=20)
     ap.add_argument("--preroll", type=int, default=120, help="untimed steps that drop and pile the bodies first")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-contexts", type=int, default=2, help="sub-batches (contexts + host threads) of the end-to-end measurement")
@@ -300,9 +306,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    W = args.worlds
-    w0, w1 = sharding.shard_range(W * world_size, rank, world_size)          # shard = contiguous world-index range
-    shapes, bodies, params = scenes.mixed_worlds(w1 - w0, first_world=w0)
+    WT = args.worlds                                                         # worlds of the whole batch
+    w0, w1 = sharding.shard_range(WT, rank, world_size)                      # shard = contiguous world-index range
+    W = w1 - w0                                                              # worlds of this rank
+    shapes, bodies, params = scenes.mixed_worlds(W, first_world=w0)
     e = eng.Engine(local_rank)
     e.upload_shapes(shapes)
     e.upload_worlds(bodies, params, None)
@@ -320,20 +327,39 @@ def main():
     work0 = (counts0["contact_iterations"], counts0["joint_row_iterations"])
 
     stream = torch.cuda.ExternalStream(e.stream_handle(), device=torch.device("cuda", local_rank))
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Timing rule: inputs larger than L2 or an L2 flush between timed iterations.  At 8192 worlds per GPU a step streams 2.7 GB
+    # through HBM (no flush needed); a shard of a few thousand worlds or fewer would sit in the 126 MB L2 from step to step,
+    # so its steps are timed one by one with a 256 MB write between them (outside the event brackets).
+    flush_l2 = W < 4096 and not os.environ.get("EP_BENCH_NO_FLUSH")
     sampler = ClockSampler(local_rank)
     launches0 = e.stats()["kernel_launches"]
     barrier()
     torch.cuda.synchronize()
     sampler.start()
-    ev0.record(stream)
-    e.step_resident(args.steps)
-    ev1.record(stream)
-    e.sync()
-    torch.cuda.synchronize()
+    if flush_l2:
+        scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        with torch.cuda.stream(stream):
+            for a, b in evs:
+                scratch.zero_()
+                a.record(stream)
+                e.step_resident(1)
+                b.record(stream)
+        e.sync()
+        torch.cuda.synchronize()
+        my_ms = sum(a.elapsed_time(b) for a, b in evs)
+        del scratch
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        e.step_resident(args.steps)
+        ev1.record(stream)
+        e.sync()
+        torch.cuda.synchronize()
+        my_ms = ev0.elapsed_time(ev1)
     barrier()
     clocks = sampler.stop()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ms = max_over_ranks(my_ms)
     launches = e.stats()["kernel_launches"] - launches0
     end_bodies = bodies.copy()
     e.download_bodies(end_bodies)
@@ -341,19 +367,34 @@ def main():
     e.download_contacts(end_contacts)
     counts = e.stats()
 
-    # the only collective of the path: the final gather of the integrated state (untimed, reported)
-    gather_ms = None
+    # the only collective of the path: the final gather of the integrated state -- ncclAllGather of the 22 output doubles per
+    # body, packed on the device (ep_pack_state_device) straight into the send buffer: no host staging.  Device-timed.
+    gather = None
     if world_size > 1:
-        barrier()
-        t0 = time.perf_counter()
-        full = sharding.gather_body_state(end_bodies, W * world_size, device="cuda")
-        torch.cuda.synchronize()
-        gather_ms = 1e3 * max_over_ranks(time.perf_counter() - t0)
-        assert full["pos"].shape[0] == bodies.n_bodies * world_size
-        del full
+        nb_max = int(max_over_ranks(float(bodies.n_bodies)))
+        send = recv = None
+        cur = torch.cuda.current_stream()
+        times = []
+        for it in range(4):                      # the first pass creates the communicator's channels: untimed
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(cur)
+            recv, send = sharding.gather_state_device(e, nb_max, send=send, recv=None if recv is None else recv.view(-1, 22))
+            g1.record(cur)
+            torch.cuda.synchronize()
+            if it:
+                times.append(max_over_ranks(g0.elapsed_time(g1)))
+        got = recv[rank, :bodies.n_bodies].cpu().numpy()
+        ok = got[:, 0:3].tobytes() == end_bodies.pos.tobytes() and got[:, 13:22].tobytes() == end_bodies.inv_inertia_world.reshape(-1, 9).tobytes()
+        gbytes = world_size * nb_max * 22 * 8
+        gather = {"ms": float(np.median(times)), "bytes_gathered_per_rank": int(gbytes), "GBps_per_rank": gbytes / (np.median(times) * 1e-3) / 1e9,
+                  "how": "ep_pack_state_device + ncclAllGather (torch.distributed.all_gather_into_tensor), device to device, median of 3",
+                  "matches_download": bool(ok)}
+        del send, recv
 
     n_dyn = W * BODIES_PER_WORLD
-    body_steps_all = n_dyn * args.steps * world_size
+    n_dyn_all = WT * BODIES_PER_WORLD
+    body_steps_all = n_dyn_all * args.steps
     value = body_steps_all / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call, one frame per call --------------------------------------
@@ -375,7 +416,7 @@ def main():
         t_e2e += max_over_ranks(time.perf_counter() - t0)
         h2d = sum(getattr(eb, n).nbytes for n, _ in abi.BODY_F64_FIELDS)
         d2h = eb.nbytes_out() + eo.nbytes_out()
-    e2e_single = n_dyn * args.e2e_steps * world_size / t_e2e
+    e2e_single = n_dyn_all * args.e2e_steps / t_e2e
     e2e_parity = None
     if world_size == 1 and not args.no_cpu_baseline:
         # the frames above continue the timed run: check the host-buffer path against the oracle over the same frames
@@ -393,7 +434,7 @@ def main():
     # host that owns several independent world batches would drive one GPU.  This is the headline e2e.
     K = max(1, min(args.e2e_contexts, W))
 
-    def pipelined(fields):
+    def pipelined(fields, up=None, down=None):
         subs = []
         for k in range(K):
             w0k, w1k = sharding.shard_range(W, k, K)
@@ -406,13 +447,13 @@ def main():
             ok = abi.Contacts(bk.n_worlds, capk.group_cap, capk.contact_cap, alloc=pool.empty, fields=fields)
             del capk
             for _ in range(3):
-                ek.step_frame(bk, ok)         # untimed: warm start builds up, host path warms
+                ek.step_frame(bk, ok, up, down)         # untimed: warm start builds up, host path warms
             subs.append((ek, bk, ok))
 
         def frames(sub):
             ek, bk, ok = sub
             for _ in range(args.e2e_steps):
-                ek.step_frame(bk, ok)
+                ek.step_frame(bk, ok, up, down)
 
         barrier()
         ths = [threading.Thread(target=frames, args=(sub,)) for sub in subs]
@@ -422,17 +463,21 @@ def main():
         for t in ths:
             t.join()
         t_pipe = max_over_ranks(time.perf_counter() - t0)
-        h2d = sum(sum(getattr(bk, n).nbytes for n, _ in abi.BODY_F64_FIELDS) for _, bk, _ in subs)
-        d2h = sum(bk.nbytes_out() + ok.nbytes_out() for _, bk, ok in subs)
+        um, dm = (abi.EP_F_ALL if up is None else up), (abi.EP_F_ALL if down is None else down)
+        h2d = sum(sum(getattr(bk, n).nbytes for n, _ in abi.BODY_F64_FIELDS if abi.BODY_FIELD_MASK[n] & um) for _, bk, _ in subs)
+        d2h = sum(sum(getattr(bk, n).nbytes for n in abi.BODY_INOUT if abi.BODY_FIELD_MASK[n] & dm) + ok.nbytes_out() for _, bk, ok in subs)
         for ek, _, _ in subs:
             ek.close()
-        return n_dyn * args.e2e_steps * world_size / t_pipe, h2d, d2h
+        return n_dyn_all * args.e2e_steps / t_pipe, sum_over_ranks(h2d), sum_over_ranks(d2h)
 
     # headline: the host reads back what the public API exposes of a frame -- the integrated bodies and what
     # Physics.contactPoints consumes (src/Physics.elm:1158-1207); the rest of `Contacts` is the next frame's warm start
     # and stays resident.  Beside it: the same with EVERY array of ep_contacts copied back.
-    e2e_value, h2d, d2h = pipelined(abi.CONTACT_POINTS_FIELDS)
-    e2e_full, _, d2h_full = pipelined(None)
+    # Per-body arrays: the dynamic state goes up and comes back (EP_F_STATE: transform, velocities -- 104 B per body each way);
+    # constants stay where ep_upload_worlds put them, forces / torques travel only on frames that applied some (none here) and
+    # are zero after a step, invInertiaWorld follows from the returned orientation (ep_step_frame_fields).
+    e2e_value, h2d, d2h = pipelined(abi.CONTACT_POINTS_FIELDS, abi.EP_F_STATE, abi.EP_F_STATE)
+    e2e_full, h2d_full, d2h_full = pipelined(None)
 
     # the same K steps once more with a CUDA-event pair around every launch (ep_profile): the per-kernel durations behind
     # `roofline` / `kernels`.  Kept out of the pass above because ~60 event records per step cost ~3 % of it.
@@ -449,26 +494,107 @@ def main():
     e.profile(False)
     counts_prof = e.stats()
 
+    # ---- N > 1: the weak-scaling figure beside the headline (every GPU gets a whole 8192-world batch of its own) -----------
+    weak = None
+    if world_size > 1 and not args.no_weak:
+        ws, wb, wp = scenes.mixed_worlds(WT, first_world=rank * WT)
+        ew = eng.Engine(local_rank)
+        ew.upload_shapes(ws)
+        ew.upload_worlds(wb, wp, None)
+        ew.step_resident(args.preroll + args.warmup)
+        ew.sync()
+        wstream = torch.cuda.ExternalStream(ew.stream_handle(), device=torch.device("cuda", local_rank))
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        x0.record(wstream)
+        ew.step_resident(args.steps)
+        x1.record(wstream)
+        ew.sync()
+        torch.cuda.synchronize()
+        wms = max_over_ranks(x0.elapsed_time(x1))
+        weak = {"scaling": "weak", "worlds_per_gpu": WT, "worlds_total": WT * world_size, "ms_per_step": wms / args.steps,
+                "value": WT * world_size * BODIES_PER_WORLD * args.steps / (wms * 1e-3), "unit": UNIT}
+        ew.close()
+        del ws, wb, wp
+
+    # ---- BASELINE config 5: car worlds (chassis + 4 hinged wheels + ramp + 6 hollow crates + tether) sharded like the headline,
+    # with the RaycastCar pattern between the steps: 4 rays per car from the chassis, placed on the device (ep_raycast_attached),
+    # hits copied back to host buffers every step.  Wall clock around the whole loop (the ray results are a host read).
+    cars = None
+    if not args.no_cars:
+        CT = args.car_worlds
+        c0w, c1w = sharding.shard_range(CT, rank, world_size)
+        cs, cb, cp = scenes.car_batch(CT)
+        cb_r, cp_r, _ = scenes.slice_batch(cb, cp, range(c0w, c1w)) if world_size > 1 else (cb, cp, None)
+        del cb, cp
+        ec = eng.Engine(local_rank)
+        ec.upload_shapes(cs)
+        ec.upload_worlds(cb_r, cp_r, None)
+        nwc = cb_r.n_worlds
+        chassis = (cb_r.world_body_off[:nwc] + 2).astype(np.int32)
+        ray_body = np.repeat(chassis, 4)
+        corners = np.array([[-1.0, 1.9, -0.25], [1.0, 1.9, -0.25], [-1.0, -1.9, -0.25], [1.0, -1.9, -0.25]])
+        lf = np.tile(corners, (nwc, 1))
+        ld = np.tile(np.array([[0.0, 0.0, -1.0]]), (4 * nwc, 1))
+        for _ in range(30):
+            ec.step_resident(1)
+            ec.raycast_attached(ray_body, lf, ld)
+        ec.sync()
+        dyn_per_world = int((cb_r.kind[:int(cb_r.world_body_off[1])] == abi.EP_DYNAMIC).sum())
+        barrier()
+        t0 = time.perf_counter()
+        hits = 0
+        for _ in range(args.car_steps):
+            ec.step_resident(1)
+            hit = ec.raycast_attached(ray_body, lf, ld)[0]
+            hits += int((hit >= 0).sum())
+        ec.sync()
+        tc = max_over_ranks(time.perf_counter() - t0)
+        # device time of the steps alone (no rays), same state
+        cstream = torch.cuda.ExternalStream(ec.stream_handle(), device=torch.device("cuda", local_rank))
+        y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        y0.record(cstream)
+        ec.step_resident(args.car_steps)
+        y1.record(cstream)
+        ec.sync()
+        torch.cuda.synchronize()
+        cms = max_over_ranks(y0.elapsed_time(y1))
+        cars = {"workload": "C5: car worlds (chassis compound + 4 hinged wheels + ramp + 6 hollow crates + tether; 5 constraints, 21 joint rows), "
+                            "4 attached rays per world per step, sharded by world index",
+                "worlds_total": CT, "worlds_per_gpu": CT // world_size, "dynamic_bodies_per_world": dyn_per_world, "steps": args.car_steps,
+                "body_steps_per_sec_with_rays": CT * dyn_per_world * args.car_steps / tc,
+                "rays_per_sec": 4.0 * CT * args.car_steps / tc,
+                "ms_per_step_with_rays": 1e3 * tc / args.car_steps,
+                "body_steps_per_sec_steps_only_device_time": CT * dyn_per_world * args.car_steps / (cms * 1e-3),
+                "ms_per_step_steps_only": cms / args.car_steps,
+                "ray_hit_fraction": sum_over_ranks(hits) / (4.0 * CT * args.car_steps),
+                "ray_io": "ep_raycast_attached: host buffers in (13.6 MB per 262144 rays) and out (15.7 MB), synchronous, every step"}
+        ec.close()
+        del cs, cb_r, cp_r
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C3: independent worlds x (32 mixed dynamic bodies + plane), 20 iterations, dt 1/60",
-                   "worlds_per_gpu": W, "bodies_per_world": BODIES_PER_WORLD, "preroll_steps": args.preroll,
-                   "sharding": "contiguous world-index range per rank, no data-path collective",
-                   "l2": "resident state (bodies + contacts + rows) exceeds the 126 MB L2; no flush needed"},
+        "config": {"workload": WORKLOAD, "worlds_total": WT, "worlds_per_gpu": WT // world_size, "bodies_per_world": BODIES_PER_WORLD,
+                   "preroll_steps": args.preroll,
+                   "sharding": "contiguous world-index range per rank, no data-path collective; one ncclAllGather of the final state",
+                   "l2": ("flushed between timed steps (256 MB write outside the per-step event brackets): the shard's state would fit the 126 MB L2"
+                          if flush_l2 else "no flush: a step streams ~0.33 MB per world through HBM (2.7 GB at 8192 worlds, profiles/), far more than the 126 MB L2")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": args.e2e_steps,
-                "call": "ep_step_frame(pinned host buffers): H2D of every per-body array (the bulk of it beside the front kernels), "
-                        "one step warm-started by the resident previous frame, D2H of the integrated state + the contact data "
-                        "Physics.contactPoints reads (pair ids, pre-step body1 frames, contact points; marshalled and copied "
-                        "beside the solver); the batch is driven as %d contexts from %d host threads so that copies and steps "
-                        "of different sub-batches overlap" % (K, K),
-                "contexts": K, "all_contact_arrays_value": e2e_full, "all_contact_arrays_d2h_bytes_per_step": int(d2h_full),
-                "single_context_all_arrays_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
+                "call": "ep_step_frame_fields(pinned host buffers): H2D of the bodies' dynamic state (transform + velocities; pos / quat "
+                        "ahead of the front kernels, the rest beside them), one step warm-started by the resident previous frame, D2H "
+                        "of the integrated state + the contact data Physics.contactPoints reads (pair ids, pre-step body1 frames, "
+                        "contact points; marshalled and copied beside the solver); each rank drives its shard as %d contexts from %d "
+                        "host threads so that copies and steps of different sub-batches overlap" % (K, K),
+                "contexts": K, "every_array_value": e2e_full, "every_array_h2d_bytes_per_step": int(h2d_full),
+                "every_array_d2h_bytes_per_step": int(d2h_full),
+                "single_context_every_array_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
         "gpu_launches": int(launches), "ms_per_step_with_per_kernel_events": ms_profiled / args.steps,
         "clocks": clocks,
-        "final_state_gather_ms": gather_ms,
+        "final_state_gather_ms": gather["ms"] if gather else None, "final_state_gather": gather,
+        "weak_scaling": weak, "cars": cars,
     }
     if rank == 0:
         # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region) ------------
@@ -489,10 +615,11 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         dur_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
         ach = kernel_bytes(dom, c) / (dur_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": TRAFFIC_NCU.get(dom), "peak_source": "measured" if peaks else "fallback",
-                            "avg_launch_ms": dur_ms, "share_of_step": ktimes[dom][0] / total_k if total_k else None}
-        # The solver is not an HBM kernel (each row crosses HBM once per step): its ceiling is the FP64 pipe without FMA
+        hbm_view = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": TRAFFIC_NCU.get(dom), "peak_source": "measured" if peaks else "fallback",
+                    "avg_launch_ms": dur_ms, "share_of_step": ktimes[dom][0] / total_k if total_k else None}
+        line["roofline"] = hbm_view
+        # The solver is not an HBM kernel (each row crosses HBM once per step): its roof is the FP64 pipe without FMA
         # (tools/fp64_peak.cu: profiles/r01_fp64_peak.json) and, in practice, the dependent-issue latency of the PGS chain.
         # Algorithmic fp64 ops: 270 per contact-iteration, 90 per joint-row-iteration, counted on the device.
         ci = counts_prof["contact_iterations"] - counts_p0["contact_iterations"]        # of the profiled pass, like ktimes
@@ -504,10 +631,16 @@ def main():
             pass
         if "k_solve" in ktimes and ktimes["k_solve"][0] > 0:
             tops = (270.0 * ci + 90.0 * ji) / (ktimes["k_solve"][0] * 1e-3) / 1e12
-            line["roofline_fp64"] = {"kernel": "k_solve", "achieved": tops, "peak": fp64_peak, "unit": "T fp64 op/s (no FMA)",
-                                     "frac": tops / fp64_peak, "contact_iterations_per_step": ci / args.steps,
-                                     "mean_iterations_per_contact": ci / max(1.0, args.steps * 0.5 * (counts_p0["contacts"] + counts_prof["contacts"])),
-                                     "peak_source": "tools/fp64_peak.cu measured on this pool's B200 (profiles/r01_fp64_peak.json)"}
+            fp64_view = {"bound": "fp64", "kernel": "k_solve", "achieved": tops, "peak": fp64_peak, "unit": "T fp64 op/s (no FMA)",
+                         "frac": tops / fp64_peak, "contact_iterations_per_step": ci / args.steps,
+                         "mean_iterations_per_contact": ci / max(1.0, args.steps * 0.5 * (counts_p0["contacts"] + counts_prof["contacts"])),
+                         "traffic": TRAFFIC_NCU.get("k_solve"), "avg_launch_ms": ktimes["k_solve"][0] / max(ktimes["k_solve"][1], 1),
+                         "share_of_step": ktimes["k_solve"][0] / total_k if total_k else None,
+                         "peak_source": "tools/fp64_peak.cu measured on this pool's B200 (profiles/r01_fp64_peak.json)"}
+            line["roofline_fp64"] = fp64_view
+            if dom == "k_solve":       # the dominant kernel's roof is the FP64 pipe: that is the headline roofline; the HBM view beside it
+                line["roofline"] = fp64_view
+                line["roofline_hbm"] = hbm_view
         line["kernels"] = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1], "share": v[0] / total_k if total_k else None,
                                "algorithmic_GBps": kernel_bytes(k, c) / (max(v[0], 1e-9) / max(v[1], 1) * 1e-3) / 1e9}
                            for k, v in ktimes.items()}

@@ -45,3 +45,20 @@ def gather_body_state(local, n_worlds_total, device="cpu", group=None):
         full = np.concatenate([r[:counts[k]].cpu().numpy() for k, r in enumerate(recv)], axis=0)
         out[name] = full if width > 1 else full.reshape(-1)
     return out
+
+
+def gather_state_device(engine, n_bodies, group=None, send=None, recv=None):
+    """The final state gather of a sharded batch with no host staging: the 22 doubles per body a step writes (transform3d 7,
+    velocity 3, angular velocity 3, invInertiaWorld 9; src/Internal/SolverBody.elm:97-225) are packed on the device by
+    ep_pack_state_device straight into the send buffer of ONE ncclAllGather (torch.distributed.all_gather_into_tensor on the
+    current CUDA stream).  Every rank must hold the same number of bodies (equal shards) or pass `n_bodies` = the largest
+    shard.  Returns (recv [world_size, n_bodies, 22] on the device, send); pass them back in to reuse the buffers."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    if send is None:
+        send = torch.zeros((n_bodies, 22), dtype=torch.float64, device="cuda")
+        recv = torch.empty((ws * n_bodies, 22), dtype=torch.float64, device="cuda")
+    engine.pack_state_device(send.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv.view(ws, n_bodies, 22), send
