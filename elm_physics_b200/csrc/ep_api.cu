@@ -15,16 +15,9 @@
 
 #include "ep_kernels.cuh"
 #include "ep_solve.cuh"
+#include "ep_solve_quads.cuh"
 #include "ep_output.cuh"
 #include "ep_raycast.cuh"
-
-namespace ep {
-__global__ void k_export_lambda(const RowRec* rows, int n, double* lam, double* t1) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-    lam[c] = rows[c].lamN; t1[3 * c] = rows[c].f1J[3]; t1[3 * c + 1] = rows[c].f1J[4]; t1[3 * c + 2] = rows[c].f1J[5];
-  }
-}
-}  // namespace ep
 
 using namespace ep;
 
@@ -45,7 +38,7 @@ struct ep_ctx {
   int64_t opt[EP_OPT_COUNT] = {0};
   // solver: tiled size classes run on side streams next to the big-island kernel
   static constexpr int kTileBins = 4;
-  static constexpr int kAux = 8;                   // side streams of the solver's concurrent launches
+  static constexpr int kAux = 12;                  // side streams of the solver's concurrent launches
   cudaStream_t aux[kAux] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
   // ep_step_frame's copy streams: the bulk of the H2D runs beside the front kernels, the contact read-back beside the solver
@@ -57,7 +50,13 @@ struct ep_ctx {
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
   int lanes_grid = 0, build_grid = 0;
-  size_t team_smem_max = 48 * 1024;            // device opt-in maximum of dynamic shared memory per CTA (set in ep_create)
+  size_t team_smem_max = 48 * 1024;
+  // quad solver (small batches): launches of k_solve_quads -- classes [lo, hi] with kq islands per warp, shared memory sized
+  // for class hi (ep_solve_quads.cuh) -- and the largest batch (bodies) that takes this family (EP_SOLVER=lanes|quads overrides)
+  struct QuadLaunch { int lo, hi, kq, cap_rows, cap_bodies, cap_groups; size_t smem; int resident; };
+  std::vector<QuadLaunch> quad_plan;
+  int64_t quads_max_bodies = 80000;             // measured crossover on B200: C3 at 2048 worlds (67 k bodies) still wins with quads, 4096 loses
+  int quads_max_world = 64;                     // worlds that can hold an island of hundreds of contacts stay with the lane / team family            // device opt-in maximum of dynamic shared memory per CTA (set in ep_create)
   // per-kernel CUDA-event timing (ep_profile): pending (kernel, start, end) triples resolved at sync
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -165,6 +164,36 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   ctx->team_smem_max = (size_t)std::max(smem_optin, 0);
   ok = ok && cudaFuncSetAttribute(k_solve_team<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_solve_team<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) == cudaSuccess;
+  // Quad solver plan: which classes share a launch and how many islands a warp takes (EP_QUAD_PLAN="lo-hi:kq,..." overrides).
+  // Shared memory of a launch is sized for its largest class: 3 * 2^c row slots, 2^c pair groups, 2^c + 2 bodies per island.
+  {
+    if (getenv("EP_QUADS_MAX_BODIES")) ctx->quads_max_bodies = atoll(getenv("EP_QUADS_MAX_BODIES"));
+    const char* plan = getenv("EP_QUAD_PLAN");
+    std::string ps = plan ? plan : "0-1:8,2-2:8,3-3:8,4-4:4,5-5:2";
+    size_t pos = 0;
+    while (pos < ps.size() && ok) {
+      int lo = 0, hi = 0, kq = 0, used = 0;
+      if (sscanf(ps.c_str() + pos, "%d-%d:%d%n", &lo, &hi, &kq, &used) != 3 || lo < 0 || hi < lo || hi > kLaneBinMax || (kq != 8 && kq != 4 && kq != 2)) { ok = false; break; }
+      ep_ctx::QuadLaunch q{lo, hi, kq, 3 << hi, (1 << hi) + 2, 1 << hi, 0, 0};
+      const void* fn = kq == 8 ? (const void*)k_solve_quads<8> : (kq == 4 ? (const void*)k_solve_quads<4> : (const void*)k_solve_quads<2>);
+      q.smem = kq == 8 ? QuadTile<8>::bytes(q.cap_rows, q.cap_bodies, q.cap_groups) : (kq == 4 ? QuadTile<4>::bytes(q.cap_rows, q.cap_bodies, q.cap_groups) : QuadTile<2>::bytes(q.cap_rows, q.cap_bodies, q.cap_groups));
+      int per_sm = 0;
+      ok = ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+      ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32, q.smem) == cudaSuccess && per_sm >= 1;
+      q.resident = per_sm * ctx->sm_count;
+      ctx->quad_plan.push_back(q);
+      pos += used;
+      if (pos < ps.size() && ps[pos] == ',') pos++;
+    }
+    int covered = 0;
+    for (auto& q : ctx->quad_plan) for (int b = q.lo; b <= q.hi; b++) covered |= 1 << b;
+    ok = ok && covered == (1 << (kLaneBinMax + 1)) - 1 && (int)ctx->quad_plan.size() + 5 <= ep_ctx::kAux;
+    const int optin = (int)ctx->team_smem_max;
+    ok = ok && cudaFuncSetAttribute(k_solve_qteam<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_solve_qteam<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_solve_qteam<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_solve_qteam<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+  }
   if (!ok) { ep_destroy(ctx); return EP_ENODEVICE; }
   *out = ctx;
   return EP_OK;
@@ -249,7 +278,6 @@ extern "C" int ep_upload_shapes(ep_ctx* ctx, const ep_shapes* S) {
 static int alloc_frame(ep_ctx* ctx, FrameBuf& f, const Dev& d) {
   auto& pool = ctx->world_allocs;
   TRY(dev_alloc(ctx, pool, &f.contacts, d.contact_cap));
-  TRY(dev_alloc(ctx, pool, &f.rows, d.contact_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_row1, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_row2, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_cstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_ccount, d.slot_cap));
   TRY(dev_alloc(ctx, pool, &f.slot_jstart, d.slot_cap)); TRY(dev_alloc(ctx, pool, &f.slot_jcount, d.slot_cap));
@@ -435,7 +463,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.isl_key, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nc, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nb, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nj, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_root, nb)); TRY(dev_alloc(ctx, pool, &d.isl_sorted, nb));
   TRY(dev_alloc(ctx, pool, &d.key_cnt, 2 * kKeys));
-  TRY(dev_alloc(ctx, pool, &d.body_iters, nb)); TRY(dev_alloc(ctx, pool, &d.body_mark, nb));
+  TRY(dev_alloc(ctx, pool, &d.body_iters, nb)); TRY(dev_alloc(ctx, pool, &d.body_mark, nb)); TRY(dev_alloc(ctx, pool, &d.body_local, nb));
   CK(cudaMemsetAsync(d.body_iters, 0, std::max(nb, 1) * sizeof(int32_t), ctx->stream));
   TRY(dev_alloc(ctx, pool, &d.tile_top, 1));
   TRY(dev_alloc(ctx, pool, &d.tile_dir, (size_t)nb / 32 + kBins + 1));
@@ -454,7 +482,18 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));
   CK(cudaMemcpyAsync(d.world_min_rem, P->iterations, nw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d.world_n_islands, 0, std::max(nw, 1) * sizeof(int32_t), ctx->stream));
-  TRY(dev_alloc(ctx, pool, &d.jrows, d.jrow_cap));
+  {   // solver family of this batch: quads for small batches (latency-bound shards), lane tiles otherwise
+    const char* sv = getenv("EP_SOLVER");
+    d.quads = sv && !strcmp(sv, "quads") ? 1 : (sv && !strcmp(sv, "lanes") ? 0 : ((nb <= ctx->quads_max_bodies && d.nb_max <= ctx->quads_max_world) ? 1 : 0));
+  }
+  d.rows = nullptr; d.jrows = nullptr; d.qrows = nullptr; d.jqrows = nullptr; d.row_dl = nullptr; d.team_body = nullptr;
+  if (d.quads) {
+    TRY(dev_alloc(ctx, pool, &d.qrows, 3 * (size_t)d.contact_cap)); TRY(dev_alloc(ctx, pool, &d.jqrows, d.jrow_cap));
+    TRY(dev_alloc(ctx, pool, &d.row_dl, 3 * (size_t)d.contact_cap + d.jrow_cap));
+    TRY(dev_alloc(ctx, pool, &d.team_body, 8 * ((size_t)nb + nw + 1)));
+  } else {
+    TRY(dev_alloc(ctx, pool, &d.rows, d.contact_cap)); TRY(dev_alloc(ctx, pool, &d.jrows, d.jrow_cap));
+  }
   // tile images: 37 doubles per contact + 16 per dynamic body, with slack for the max-over-lanes padding of a tile
   d.tile_arena_cap = (int64_t)d.contact_cap * 72 + (int64_t)d.jrow_cap * 24 + (int64_t)nb * 24 + 4096;
   TRY(dev_alloc(ctx, pool, &d.tile_arena, (size_t)d.tile_arena_cap));
@@ -485,9 +524,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     if (ng > d.slot_cap) { ctx->err = "warm-start groups exceed pair capacity"; return EP_ECAPACITY; }
     std::vector<int32_t> row1(ng), row2(ng), cstart(ng), ccount(ng), zero(ng, 0), neg(ng, -1);
     std::vector<ContactRec> crec(std::max(nc, 1));
-    std::vector<RowRec> rrec(std::max(nc, 1));
     memset(crec.data(), 0, crec.size() * sizeof(ContactRec));
-    memset(rrec.data(), 0, rrec.size() * sizeof(RowRec));
     for (int w = 0; w < nw; w++) {
       std::unordered_map<int, int> id2row;
       for (int r = B->world_body_off[w]; r < B->world_body_off[w + 1]; r++) id2row[B->body_id[r]] = r;
@@ -499,8 +536,8 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
         row1[g] = a->second; row2[g] = b->second;
         for (int c = cstart[g]; c < cstart[g] + ccount[g]; c++) {
           crec[c].fk = warm->feature_key[c]; crec[c].sk = warm->shape_key[c]; crec[c].slot = g;
-          rrec[c].lamN = warm->lambda[c];
-          rrec[c].f1J[3] = warm->t1[3 * c]; rrec[c].f1J[4] = warm->t1[3 * c + 1]; rrec[c].f1J[5] = warm->t1[3 * c + 2];
+          crec[c].lam = warm->lambda[c];
+          crec[c].t1[0] = warm->t1[3 * c]; crec[c].t1[1] = warm->t1[3 * c + 1]; crec[c].t1[2] = warm->t1[3 * c + 2];
         }
       }
     }
@@ -514,7 +551,6 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     CK(cudaMemcpyAsync(f.slot_cstart, cstart.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.slot_ccount, ccount.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.contacts, crec.data(), nc * sizeof(ContactRec), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(f.rows, rrec.data(), nc * sizeof(RowRec), cudaMemcpyHostToDevice, ctx->stream));
     k_pair_slots<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(d, f, ng); CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
   }
@@ -649,7 +685,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         k_island_sort<<<grid_for(ctx, d.n_bodies / 2 + 1, 256, 4), 256, 0, st>>>(d); ctx->launches += 2; }
       CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
       { Timed t(ctx, EP_K_EQUATIONS, ctx->aux[0]);
-        k_equations<<<gwide, 128, 0, ctx->aux[0]>>>(d);
+        if (d.quads) k_equations<true><<<gwide, 128, 0, ctx->aux[0]>>>(d); else k_equations<false><<<gwide, 128, 0, ctx->aux[0]>>>(d);
         if (d.n_constraints > 0) { k_joint_equations<<<gwide, 128, 0, ctx->aux[0]>>>(d); ctx->launches++; } }
       CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
       CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
@@ -659,7 +695,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         launch_out_kernels(ctx, d.cur, ctx->cout, 1);
         CK(cudaEventRecord(ctx->ev_out_done, ctx->cout));
       }
-      { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
+      if (!d.quads) { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
     }
     {   // islands by size class, all launches concurrent: classes 0..3 lane-per-island from shared-memory tiles, 4..6 one warp
         // per island, 7.. one CTA per island (level-scheduled, ep_solve.cuh).  EP_K_SOLVE brackets the whole fork/join.
@@ -678,24 +714,53 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         return EP_OK;
       };
       const int tiles_cap = d.n_bodies / 32 + 2;
-      // longest first: CTA-per-island teams, warp-per-island teams, then the lane classes from the largest down
-      // team kernels: shared memory = level-walk chunk (3 x 8T ints) + per-body last level / inverse mass / deltas of the largest world
-      const size_t body_b = (size_t)((d.nb_max + 1) & ~1) * 4 + (size_t)d.nb_max * 56;
-      const bool smemb = body_b + 3 * 8 * 256 * 4 <= std::min<size_t>(200 * 1024, ctx->team_smem_max);
-      const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
-      if (smemb) {
-        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
-        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
+      if (d.quads) {
+        // QUAD family (small batches, ep_solve_quads.cuh), longest first: giant islands (16 warps, rows in place), class 8 (4 warps),
+        // a warp per island for classes 7 and 6, then the quad-per-island classes from the largest down
+        auto team_smem = [](int nw, int cap_bodies, int cap_rows, int cap_groups, bool sb, bool sr) {
+          const int ch = nw == 1 ? 128 : 1024;
+          return (size_t)3 * ch * 4 + (size_t)(ch + 1) * 4 + (sb ? (size_t)cap_bodies * 4 + 16 + (size_t)cap_bodies * 64 : 0) +
+                 (sr ? (size_t)cap_groups * 32 + (size_t)cap_rows * (192 + 8) : 0) + 64;
+        };
+        const int cb = d.nb_max + 2;
+        const size_t need = team_smem(16, cb, 0, 0, true, false);
+        if (need <= ctx->team_smem_max) TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<16, true, false><<<ctx->sm_count, 512, need, sx>>>(d, kBins - 1, kBins - 1, force_resum, cb, 0, 0); }));
+        else TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<16, false, false><<<ctx->sm_count, 512, team_smem(16, 0, 0, 0, false, false), sx>>>(d, kBins - 1, kBins - 1, force_resum, 0, 0, 0); }));
+        const int c8b = (1 << 8) + 2, c8r = 3 << 8, c8g = 1 << 8;
+        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<4, true, true><<<ctx->sm_count, 128, team_smem(4, c8b, c8r, c8g, true, true), sx>>>(d, 8, 8, force_resum, c8b, c8r, c8g); }));
+        for (int c = 7; c > kLaneBinMax; c--) {
+          const int cbod = (1 << c) + 2, crow = 3 << c, cgrp = 1 << c;
+          TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_qteam<1, true, true><<<ctx->sm_count * 4, 32, team_smem(1, cbod, crow, cgrp, true, true), sx>>>(d, c, c, force_resum, cbod, crow, cgrp); }));
+        }
+        for (int i = (int)ctx->quad_plan.size() - 1; i >= 0; i--) {
+          const ep_ctx::QuadLaunch& q = ctx->quad_plan[i];
+          const int grid = std::max(1, std::min(q.resident, d.n_bodies / q.kq + (q.hi - q.lo + 2)));
+          TRY(side(EP_K_SOLVE_LANES_B0 + q.hi, [&](cudaStream_t sx) {
+            if (q.kq == 8) k_solve_quads<8><<<grid, 32, q.smem, sx>>>(d, q.lo, q.hi, q.cap_rows, q.cap_bodies, q.cap_groups);
+            else if (q.kq == 4) k_solve_quads<4><<<grid, 32, q.smem, sx>>>(d, q.lo, q.hi, q.cap_rows, q.cap_bodies, q.cap_groups);
+            else k_solve_quads<2><<<grid, 32, q.smem, sx>>>(d, q.lo, q.hi, q.cap_rows, q.cap_bodies, q.cap_groups);
+          }));
+        }
       } else {
-        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
-        TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
+        // longest first: CTA-per-island teams, warp-per-island teams, then the lane classes from the largest down
+        // team kernels: shared memory = level-walk chunk (3 x 8T ints) + per-body last level / inverse mass / deltas of the largest world
+        const size_t body_b = (size_t)((d.nb_max + 1) & ~1) * 4 + (size_t)d.nb_max * 56;
+        const bool smemb = body_b + 3 * 8 * 256 * 4 <= std::min<size_t>(200 * 1024, ctx->team_smem_max);
+        const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
+        if (smemb) {
+          TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
+          TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
+        } else {
+          TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
+          TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
+        }
+        TRY(side(EP_K_SOLVE_LANES_B5, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5); }));
+        TRY(side(EP_K_SOLVE_LANES_B4, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4); }));
+        TRY(side(EP_K_SOLVE_LANES_B3, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3); }));
+        for (int i = 2; i >= 0; i--)
+          TRY(side(EP_K_SOLVE_LANES_B0 + i, [&](cudaStream_t sx) { k_solve_lanes<2><<<std::min(ctx->head_grid[i], tiles_cap), 32, ctx->tile_smem[i], sx>>>(d, i, i); }));
+        { Timed tt(ctx, EP_K_SOLVE_LANES_INPLACE, st); k_solve_lanes<0><<<std::min(ctx->lanes_grid, tiles_cap / 4 + 1), 128, 0, st>>>(d, 0, kLaneBinMax); }
       }
-      TRY(side(EP_K_SOLVE_LANES_B5, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5); }));
-      TRY(side(EP_K_SOLVE_LANES_B4, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4); }));
-      TRY(side(EP_K_SOLVE_LANES_B3, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3); }));
-      for (int i = 2; i >= 0; i--)
-        TRY(side(EP_K_SOLVE_LANES_B0 + i, [&](cudaStream_t sx) { k_solve_lanes<2><<<std::min(ctx->head_grid[i], tiles_cap), 32, ctx->tile_smem[i], sx>>>(d, i, i); }));
-      { Timed tt(ctx, EP_K_SOLVE_LANES_INPLACE, st); k_solve_lanes<0><<<std::min(ctx->lanes_grid, tiles_cap / 4 + 1), 128, 0, st>>>(d, 0, kLaneBinMax); }
       CK(cudaGetLastError());       // a solver launch that failed must not be followed by the integration of unsolved islands
       for (int i = 0; i < ax; i++) CK(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }

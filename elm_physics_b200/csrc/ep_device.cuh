@@ -13,6 +13,9 @@ struct ContactRec {
   int32_t slot;          // owning pair slot
   double ni[3], pi[3], pj[3];
   double friction, bounciness;
+  double lam;            // normal lambda: the 0.85-scaled seed after k_equations, the solved value after the solver
+  double t1[3];          // friction-1 direction of this frame (= vB of the friction-1 row): with lam, all that the NEXT frame's
+                         // warm start reads of this contact's solution (Solver.elm:320-335)
 };
 
 // `ContactEquations` + `ContactData` (src/Internal/Equation.elm:63-93): three Jacobian rows (wA, vB, wB;
@@ -27,6 +30,25 @@ struct RowRec {
   double dN, dF1, dF2;   // |deltaLambda| of the last iteration, for the canonical-order sum of the team solver
   double nIa[3], nIb[3], f1Ia[3], f1Ib[3], f2Ia[3], f2Ib[3];
 };                       // 58 doubles = 464 B (16 B aligned)
+
+// The same row in the layout of the QUAD solver (ep_solve_quads.cuh), which solves a row with four lanes; lane role q holds
+// one half of one body of the row's pair:
+//   q = 0  body1 linear   a = -vB   c = a        m = invMass1        (vA = -vB, Equation.elm:22-35)
+//   q = 1  body1 angular  a =  wA   c = I1 wA    m = 1
+//   q = 2  body2 linear   a =  vB   c = a        m = invMass2
+//   q = 3  body2 angular  a =  wB   c = I2 wB    m = 1
+// The row's G.W is ((p0 + p1) + p2) + p3 with p_q = (a0 s0 + a1 s1) + a2 s2 over the lane's half s of the solver body --
+// bit for bit the association of Solver.elm:642-646 (negating every product of the first dot negates its rounded sum) --
+// and the lane's update is s += (dlambda m) c, the same operations as applyVelocityBody1/2 (Solver.elm:505-550).
+// Contact c owns rows 3c (normal), 3c+1 (friction 1), 3c+2 (friction 2); joint rows live in their own array.
+struct __align__(16) QRow {
+  double a[3][4];        // [component][role]
+  double c[3][2];        // [component][0: I1 wA, 1: I2 wB]
+  double B, invC;
+  double lam, mu;        // mu: friction rows only (bounds +-mu * lambda of the contact's normal row)
+  int32_t i0, i1, i2, i3;   // free in global memory; the solver's staged copy keeps its row descriptor here
+};
+static_assert(sizeof(QRow) == 192, "QRow is 12 chunks of 16 B");
 
 // `ConstraintEquation` (src/Internal/Equation.elm:503-511); bounds are the constants -1e6 / 1e6.
 struct JointRow { double J[9]; double B, invC, eps, lam; double dl; double Ia[3], Ib[3]; double pad[4]; };   // 24 doubles; dl = |deltaLambda| of the last iteration
@@ -52,7 +74,6 @@ struct OutBuf {
 
 struct FrameBuf {        // double-buffered: the previous frame is the warm-start cache
   ContactRec* contacts;
-  RowRec* rows;
   int32_t* slot_row1;    // pair slots: body rows (body1 = lower gravity-sort position)
   int32_t* slot_row2;
   int32_t* slot_cstart;  // contacts of the slot, solver order
@@ -106,7 +127,16 @@ struct Dev {
   int32_t *sched, *sched_lvl, *lvl_off, *lvl_cur;   // [slot_cap] level schedule of each island's groups (k_solve_team), parallel to isl_groups
   int32_t* world_min_rem;     // [n_worlds] min over islands of remaining iterations
   int32_t* world_n_islands;   // [n_worlds]
-  JointRow* jrows;
+  // rows of this frame (scratch of the step: the next frame reads only ContactRec.lam / t1).  Two solver families, chosen per
+  // batch at ep_upload_worlds (Dev::quads): lane tiles read RowRec / JointRow, the quad solver QRow.
+  int32_t quads;
+  RowRec* rows;               // [contact_cap]                         (lane solver)
+  JointRow* jrows;            // [jrow_cap]
+  QRow* qrows;                // [3 * contact_cap] rows 3c, 3c+1, 3c+2  (quad solver)
+  QRow* jqrows;               // [jrow_cap]
+  double* row_dl;             // [3 * contact_cap + jrow_cap] |deltaLambda| of the last iteration (team of quads: canonical re-sum)
+  double* team_body;          // [(n_bodies + n_worlds + 1)][8] body table of the giant-island quad team when it does not fit shared memory
+  int32_t* body_local;        // [n_bodies] 1-based index of a dynamic body inside its island (0: in no island)
   int32_t* flags;             // [FLAG_COUNT]
   unsigned long long* work;   // [4] cumulative contact-iterations, joint-row-iterations of the solver (roofline denominators), canonical re-sums
   int64_t slot_cap; int32_t contact_cap; int32_t jrow_cap;

@@ -397,6 +397,16 @@ __device__ __forceinline__ Spook spook(double dt) {      // Equation.elm:369-376
   s.eps = 4.0 / (dt * dt * 10000000.0 * (1 + 4 * 3.0));
   return s;
 }
+// a row in the layout of the quad solver (QRow, ep_device.cuh): per lane role the dot coefficients a and the update coefficients c
+__device__ __forceinline__ void store_qrow(QRow& q, const double* J, const double* Ia, const double* Ib, double B, double invC, double lam, double mu) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    q.a[k][0] = -J[3 + k]; q.a[k][1] = J[k]; q.a[k][2] = J[3 + k]; q.a[k][3] = J[6 + k];
+    q.c[k][0] = Ia[k]; q.c[k][1] = Ib[k];
+  }
+  q.B = B; q.invC = invC; q.lam = lam; q.mu = mu;
+  q.i0 = 0; q.i1 = 0; q.i2 = 0; q.i3 = 0;
+}
 __device__ __forceinline__ void joint_row(JointRow& r, double dt, V3 gravity, const BodyE& b1, const BodyE& b2, double velocityB, double eps) {
   r.B = velocityB - (dt * compute_gimf(gravity, b1, b2, r.J));     // computeSolverB 520-522
   r.invC = 1 / (compute_gimgt(b1, b2, r.J) + eps);                 // computeSolverInvC 527-529
@@ -424,46 +434,63 @@ __device__ void rot_row(JointRow& r, double dt, V3 gravity, const Spook& sp, con
 }
 __device__ __forceinline__ int constraint_rows(int kind) { return kind == 0 ? 3 : (kind == 1 ? 5 : (kind == 2 ? 6 : 1)); }
 
-// contactEquations (Equation.elm:364-450) for one contact; lam/ct1 = cached normal lambda and friction-1 direction
-// One row at a time, every field stored as soon as it is known (`r` is the record in global memory): the thread never holds
-// more than one 9-double Jacobian next to the two bodies.
-__device__ __forceinline__ void contact_row(RowRec& r, V3 ni, V3 pi, V3 pj, double bounciness, double friction, double lam, V3 ct1,
-                                            double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2) {
+// contactEquations (Equation.elm:364-450) for one contact; lam/ct1 = cached normal lambda and friction-1 direction.
+// One row at a time, every row stored as soon as it is known (the records live in global memory): the thread never holds
+// more than one 9-double Jacobian next to the two bodies.  Q: rows in the quad solver's layout (three QRow at qrows) instead
+// of the lane solver's RowRec.  Returns the friction-1 direction used.
+template <bool Q>
+__device__ __forceinline__ V3 contact_row(RowRec* rec, QRow* qrows, V3 ni, V3 pi, V3 pj, double bounciness, double friction, double lam, V3 ct1,
+                                          double dt, V3 gravity, const Spook& sp, const BodyE& b1, const BodyE& b2) {
   V3 ri = vsub(pi, b1.x), rj = vsub(pj, b2.x);
   V3 t1, t2; stable_tangents(ct1, ni, t1, t2);
   double J[9], ia[3], ib[3];
   {
     contact_jac(ni, ri, rj, J);
-    r.nB = compute_contact_b(sp.a, sp.b, bounciness, pi, pj, ni, b1, b2, J) - (dt * compute_gimf(gravity, b1, b2, J));
-    r.nInvC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
+    const double B = compute_contact_b(sp.a, sp.b, bounciness, pi, pj, ni, b1, b2, J) - (dt * compute_gimf(gravity, b1, b2, J));
+    const double invC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
     inertia_times(b1.k, J, ia); inertia_times(b2.k, J + 6, ib);
+    if (Q) store_qrow(qrows[0], J, ia, ib, B, invC, lam * kWarmStartFactor, 0.0);
+    else {
+      RowRec& r = *rec;
+      r.nB = B; r.nInvC = invC;
 #pragma unroll
-    for (int k = 0; k < 9; k++) r.nJ[k] = J[k];
+      for (int k = 0; k < 9; k++) r.nJ[k] = J[k];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { r.nIa[k] = ia[k]; r.nIb[k] = ib[k]; }
+      for (int k = 0; k < 3; k++) { r.nIa[k] = ia[k]; r.nIb[k] = ib[k]; }
+    }
   }
   {
     contact_jac(t1, ri, rj, J);
-    r.f1B = (-compute_gw(b1, b2, J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, J));
-    r.f1InvC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
+    const double B = (-compute_gw(b1, b2, J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, J));
+    const double invC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
     inertia_times(b1.k, J, ia); inertia_times(b2.k, J + 6, ib);
+    if (Q) store_qrow(qrows[1], J, ia, ib, B, invC, 0.0, friction);
+    else {
+      RowRec& r = *rec;
+      r.f1B = B; r.f1InvC = invC;
 #pragma unroll
-    for (int k = 0; k < 9; k++) r.f1J[k] = J[k];
+      for (int k = 0; k < 9; k++) r.f1J[k] = J[k];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { r.f1Ia[k] = ia[k]; r.f1Ib[k] = ib[k]; }
+      for (int k = 0; k < 3; k++) { r.f1Ia[k] = ia[k]; r.f1Ib[k] = ib[k]; }
+    }
   }
   {
     contact_jac(t2, ri, rj, J);
-    r.f2B = (-compute_gw(b1, b2, J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, J));
-    r.f2InvC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
+    const double B = (-compute_gw(b1, b2, J) * sp.b) - (dt * compute_gimf(gravity, b1, b2, J));
+    const double invC = 1 / (compute_gimgt(b1, b2, J) + sp.eps);
     inertia_times(b1.k, J, ia); inertia_times(b2.k, J + 6, ib);
+    if (Q) store_qrow(qrows[2], J, ia, ib, B, invC, 0.0, friction);
+    else {
+      RowRec& r = *rec;
+      r.f2B = B; r.f2InvC = invC;
 #pragma unroll
-    for (int k = 0; k < 9; k++) r.f2J[k] = J[k];
+      for (int k = 0; k < 9; k++) r.f2J[k] = J[k];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { r.f2Ia[k] = ia[k]; r.f2Ib[k] = ib[k]; }
+      for (int k = 0; k < 3; k++) { r.f2Ia[k] = ia[k]; r.f2Ib[k] = ib[k]; }
+    }
   }
-  r.mu = friction;
-  r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.dN = 0; r.dF1 = 0; r.dF2 = 0;
+  if (!Q) { RowRec& r = *rec; r.mu = friction; r.lamN = lam * kWarmStartFactor; r.lamF1 = 0; r.lamF2 = 0; r.dN = 0; r.dF1 = 0; r.dF2 = 0; }
+  return t1;
 }
 // addConstraintEquations (Equation.elm:157-361) for the pair (r1, r2) (global body rows; ncon < 0 == flipped registration):
 // rows are emitted per constraint in list order and consed, so the solver order is the reverse of emission:
@@ -512,7 +539,10 @@ __device__ void joint_rows_for_pair(const Dev& d, int r1, int r2, int ncon, cons
         rot_row(tmp[5], dt, gravity, sp, b1, b2, z1, x2);
       }
     }
-    for (int k = 0; k < nr; k++, e++) { tmp[k].dl = 0; tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; tmp[k].pad[3] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
+    for (int k = 0; k < nr; k++, e++) {
+      if (d.quads) store_qrow(d.jqrows[j0 + (E - 1 - e)], tmp[k].J, tmp[k].Ia, tmp[k].Ib, tmp[k].B, tmp[k].invC, 0.0, 0.0);
+      else { tmp[k].dl = 0; tmp[k].pad[0] = 0; tmp[k].pad[1] = 0; tmp[k].pad[2] = 0; tmp[k].pad[3] = 0; d.jrows[j0 + (E - 1 - e)] = tmp[k]; }
+    }
   }
 }
 
@@ -567,6 +597,7 @@ __global__ void __launch_bounds__(256) k_slot_counts(Dev d) {
 }
 
 // k_equations: one thread per contact (contactEquations)
+template <bool Q>
 __global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
   if (d.flags[FLAG_POOL_OVERFLOW]) return;       // contact_src has holes then; ep_sync reports the overflow
   const int ncont = min(d.cur.counters[CNT_CONTACTS], d.contact_cap);
@@ -589,7 +620,6 @@ __global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
     c.pi[0] = rc.pi.x; c.pi[1] = rc.pi.y; c.pi[2] = rc.pi.z;
     c.pj[0] = rc.pj.x; c.pj[1] = rc.pj.y; c.pj[2] = rc.pj.z;
     c.friction = friction; c.bounciness = bounciness;
-    d.cur.contacts[out] = c;
     // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128; Cache.lookup: first match in pairGroup.contacts order == LAST
     // match in solver order (ContactCache.elm:76-87)
     double lam = 0; V3 ct1 = mk(0, 0, 0);
@@ -598,12 +628,14 @@ __global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
       const int pc0 = d.prev.slot_cstart[ps], pcn = d.prev.slot_ccount[ps];
       for (int m = pcn - 1; m >= 0; m--) {
         const ContactRec& p = d.prev.contacts[pc0 + m];
-        if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { const RowRec& pr = d.prev.rows[pc0 + m]; lam = pr.lamN; ct1 = mk(pr.f1J[3], pr.f1J[4], pr.f1J[5]); break; }
+        if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { lam = p.lam; ct1 = mk(p.t1[0], p.t1[1], p.t1[2]); break; }
       }
     }
     const double dt = d.dt[w]; const V3 gravity = ld3(d.gravity + 3 * w);
     const BodyE b1 = load_bodye(d, r1), b2 = load_bodye(d, r2);
-    contact_row(d.cur.rows[out], rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, spook(dt), b1, b2);
+    const V3 t1 = contact_row<Q>(Q ? nullptr : d.rows + out, Q ? d.qrows + 3 * (size_t)out : nullptr, rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, spook(dt), b1, b2);
+    c.lam = lam * kWarmStartFactor; c.t1[0] = t1.x; c.t1[1] = t1.y; c.t1[2] = t1.z;
+    d.cur.contacts[out] = c;
   }
 }
 // addConstraintEquations: one thread per constrained pair (launched only when the batch has constraints)
@@ -632,9 +664,11 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {       // Islands.el
   }
 }
 // island size class: row count (3 per contact + joint rows) on a log2 scale; class kBins-1 runs first
-__device__ __forceinline__ int island_bin(int rows) {
+// The class also bounds the island's pair groups (<= 2^class; hence its dynamic bodies <= 2^class + 1: a component of n dynamic
+// bodies needs n - 1 groups), which is what the quad solver sizes its shared-memory tables by (ep_solve_quads.cuh).
+__device__ __forceinline__ int island_bin(int rows, int groups) {
   int b = 0;
-  while (b < kBins - 1 && rows > (3 << b)) b++;
+  while (b < kBins - 1 && (rows > (3 << b) || groups > (1 << b))) b++;
   return b;
 }
 // Sort key inside a size class, most significant first: row count (16 sub-classes of the class's range: the lanes of a tile
@@ -665,7 +699,7 @@ __global__ void k_islands(Dev d, int use_smem) {
     int* count = use_smem ? s_isl + d.nb_max : d.uf_count + r0;
     int* fill = use_smem ? s_isl + 2 * d.nb_max : d.uf_fill + r0;
     const int s0 = d.cur.cand_base[w], sn = d.cur.cand_n[w];
-    for (int l = tid; l < n; l += nt) { parent[l] = l; count[l] = 0; fill[l] = 0; d.body_mark[r0 + l] = 0; }
+    for (int l = tid; l < n; l += nt) { parent[l] = l; count[l] = 0; fill[l] = 0; d.body_mark[r0 + l] = 0; d.body_local[r0 + l] = 0; }
     if (tid == 0) { s_nisl = 0; s_valid = 0; }
     __syncthreads();
     // Islands.connect for every dynamic-dynamic pair group (Solver.elm:201-206)
@@ -769,7 +803,7 @@ __global__ void k_islands(Dev d, int use_smem) {
     for (int l = tid; l < n; l += nt) {
       if (d.kind[r0 + l] != 2) continue;
       const int c = count[parent[l]];
-      if (c > 0) atomicAdd(&d.isl_nb[c - 1], 1);
+      if (c > 0) d.body_local[r0 + l] = 1 + atomicAdd(&d.isl_nb[c - 1], 1);      // any order: the index only names the body inside its island
     }
     __syncthreads();
     // size class and sort key of each island (k_island_sort)
@@ -777,7 +811,7 @@ __global__ void k_islands(Dev d, int use_smem) {
       if (parent[l] != l || count[l] <= 0) continue;
       const int isl = count[l] - 1;
       const int rows = 3 * d.isl_nc[isl] + d.isl_nj[isl];
-      const int bin = island_bin(rows);
+      const int bin = island_bin(rows, d.isl_cnt[isl]);
       const int key = island_key(bin, rows, d.body_iters[r0 + l], d.isl_cnt[isl]);
       d.isl_key[isl] = key;
       atomicAdd(&d.key_cnt[key], 1);
@@ -918,7 +952,7 @@ __device__ double sweep_nonfriction(const Dev& d, int s, double eps, double tot)
   }
   int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
   for (int k = 0; k < cn; k++) {
-    RowRec& r = d.cur.rows[c0 + k];
+    RowRec& r = d.rows[c0 + k];
     double lam = r.lamN;
     double dl = row_solve(r.nJ, r.nB, r.nInvC, eps, 0.0, kMaxImpulse, lam, k1, k2, s1, s2);
     r.lamN = lam; r.dN = eabs(dl);
@@ -936,7 +970,7 @@ __device__ double sweep_friction(const Dev& d, int s, double eps, double tot) {
   BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
   SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
   for (int k = 0; k < cn; k++) {
-    RowRec& r = d.cur.rows[c0 + k];
+    RowRec& r = d.rows[c0 + k];
     double l1 = r.lamF1, l2 = r.lamF2;
     double a1, a2;
     tot = friction_pair(r.f1J, r.f2J, r.f1B, r.f1InvC, r.f2B, r.f2InvC, eps, r.mu, r.lamN, l1, l2, k1, k2, s1, s2, tot, a1, a2);
@@ -956,7 +990,7 @@ __device__ void warm_group(const Dev& d, int s) {
   SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
   int c0 = d.cur.slot_cstart[s];
   for (int k = 0; k < cn; k++) {
-    const RowRec& r = d.cur.rows[c0 + k];
+    const RowRec& r = d.rows[c0 + k];
     if (r.lamN == 0) continue;                      // Solver.elm:41
     apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
   }

@@ -115,9 +115,8 @@ __global__ void __launch_bounds__(256) k_out_contacts(Dev d, FrameBuf f, int ear
     for (int k = 0; k < 3; k++) { d.out.ni[3 * o + k] = r.ni[k]; d.out.pi[3 * o + k] = r.pi[k]; d.out.pj[3 * o + k] = r.pj[k]; }
     d.out.friction[o] = r.friction; d.out.bounciness[o] = r.bounciness;
     if (early) continue;
-    const RowRec& row = f.rows[c];
-    d.out.lambda[o] = row.lamN;
-    d.out.t1[3 * o] = row.f1J[3]; d.out.t1[3 * o + 1] = row.f1J[4]; d.out.t1[3 * o + 2] = row.f1J[5];
+    d.out.lambda[o] = r.lam;
+    d.out.t1[3 * o] = r.t1[0]; d.out.t1[3 * o + 1] = r.t1[1]; d.out.t1[3 * o + 2] = r.t1[2];
   }
 }
 

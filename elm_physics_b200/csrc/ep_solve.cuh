@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) k_tile_build(Dev d) {
       if (cc >= nc) continue;
       const int rowN = (T.desc2(cc) >> 16) & 0xff;
       // all 58 doubles of the row into registers first (29 independent 16 B loads in flight), then the transposed stores
-      const double2* sp = (const double2*)(d.cur.rows + T.contact_index(cc));
+      const double2* sp = (const double2*)(d.rows + T.contact_index(cc));
       double2 v[29];
 #pragma unroll
       for (int f = 0; f < 29; f++) v[f] = sp[f];
@@ -378,8 +378,7 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   if (R > C) atomicAdd(&d.work[1], (unsigned long long)(R - C) * (iterations - rem));
   // scatter: lambdas back to the slot-order rows (next frame's warm start, Solver.elm:320-335), delta velocities to the bodies
   for (int c = 0; c < C; c++) {
-    RowRec& o = d.cur.rows[T.contact_index(c)];
-    o.lamN = T.nrow((T.desc2(c) >> 16) & 0xff, NR_LAM); o.lamF1 = T.frow(c, FR_L1); o.lamF2 = T.frow(c, FR_L2);
+    d.cur.contacts[T.contact_index(c)].lam = T.nrow((T.desc2(c) >> 16) & 0xff, NR_LAM);      // next frame's warm start (Solver.elm:320-335)
   }
   const int nB = d.isl_nb[isl] + 1;
   for (int b = 1; b < nB; b++) {
@@ -548,7 +547,7 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi,
         if (rc.cn <= 0) continue;
         Pair P; load_pair(rc, P);
         for (int k = 0; k < rc.cn; k++) {
-          const RowRec& r = d.cur.rows[rc.c0 + k];
+          const RowRec& r = d.rows[rc.c0 + k];
           if (r.lamN == 0) continue;                      // Solver.elm:41
           apply_pre(r.lamN, r.nJ, r.nIa, r.nIb, P);
         }
@@ -577,7 +576,7 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi,
             part += eabs(dl);
           }
           if (rc.cn > 0) {
-            RowRec* rows = d.cur.rows + rc.c0;
+            RowRec* rows = d.rows + rc.c0;
             double J[9], ia[3], ib[3], B, invC, lam;
             auto ld = [&](const RowRec& r) {
 #pragma unroll
@@ -612,7 +611,7 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi,
           const TeamRec rc = recs[i];
           if (rc.cn <= 0) continue;
           Pair P; load_pair(rc, P);
-          RowRec* rows = d.cur.rows + rc.c0;
+          RowRec* rows = d.rows + rc.c0;
           for (int k = 0; k < rc.cn; k++) {
             RowRec& r = rows[k];
             if (k + 1 < rc.cn) {        // next row towards L1 while this one computes (464 B = up to five 128 B lines)
@@ -651,12 +650,12 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi,
           for (int gi = 0; gi < gn; gi++) {
             int s = d.isl_groups[g0 + gi];
             for (int k = 0, j0 = d.cur.slot_jstart[s]; k < d.cur.slot_jcount[s]; k++) p1 = p1 + d.jrows[j0 + k].dl;
-            for (int k = 0, c0 = d.cur.slot_cstart[s]; k < d.cur.slot_ccount[s]; k++) p1 = p1 + d.cur.rows[c0 + k].dN;
+            for (int k = 0, c0 = d.cur.slot_cstart[s]; k < d.cur.slot_ccount[s]; k++) p1 = p1 + d.rows[c0 + k].dN;
           }
           double p2 = (gn == 1) ? p1 : 0;
           for (int gi = 0; gi < gn; gi++) {
             int s = d.isl_groups[g0 + gi];
-            for (int k = 0, c0 = d.cur.slot_cstart[s]; k < d.cur.slot_ccount[s]; k++) p2 = p2 + d.cur.rows[c0 + k].dF1 + d.cur.rows[c0 + k].dF2;
+            for (int k = 0, c0 = d.cur.slot_cstart[s]; k < d.cur.slot_ccount[s]; k++) p2 = p2 + d.rows[c0 + k].dF1 + d.rows[c0 + k].dF2;
           }
           double deltaTot = (gn == 1) ? p2 : p1 + p2;
           below = (deltaTot - kSolverTolerance < 0) ? 1 : 0;
@@ -673,6 +672,10 @@ __global__ void __launch_bounds__(T) k_solve_team(Dev d, int bin_lo, int bin_hi,
       atomicMin(&d.world_min_rem[w], rem); d.body_iters[d.isl_root[isl]] = iterations - rem;
       atomicAdd(&d.work[0], (unsigned long long)d.isl_nc[isl] * (iterations - rem));
       if (d.isl_nj[isl]) atomicAdd(&d.work[1], (unsigned long long)d.isl_nj[isl] * (iterations - rem));
+    }
+    for (int i = tid; i < gn; i += T) {      // solved normal lambdas to the contacts: the next frame's warm start (Solver.elm:320-335)
+      const TeamRec rc = recs[i];
+      for (int k = 0; k < rc.cn; k++) d.cur.contacts[rc.c0 + k].lam = d.rows[rc.c0 + k].lamN;
     }
     if (SMEMB) {     // the island's dynamic bodies back to the solver-body array (other islands of the world own other bodies)
       for (int i = tid; i < gn; i += T) {
