@@ -658,17 +658,21 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         k_bp_scan<<<grid_for(ctx, (int64_t)d.n_worlds * 32, 128, 16), 128, 0, st>>>(d);
         k_bp_emit<<<gc, 128, 0, st>>>(d);
         ctx->launches += 2; }
+      static const int np_lanes_env = getenv("EP_NP_LANES") ? atoi(getenv("EP_NP_LANES")) : 0;
+      // small batches (the quad solver's regime): 16 items per warp -- the kernel time is the latency of the heaviest warp, and half-full
+      // warps serialise fewer divergent lanes (0.32 -> 0.28 ms at 1024 worlds; at 8192 worlds full warps are 30 % faster)
+      const int np_lanes = (np_lanes_env == 8 || np_lanes_env == 16 || np_lanes_env == 32 || np_lanes_env == 4) ? np_lanes_env : (d.quads ? 16 : 32);
       static const bool np_serial = getenv("EP_NP_SERIAL") != nullptr;    // profiling aid: one launch per work-item class
       if (np_serial && ctx->profiling) {
         for (int c = 0; c < kClasses; c++) {
           cudaEvent_t a = next_event(ctx), b = next_event(ctx);
           cudaEventRecord(a, st);
-          k_narrowphase<<<gwide, 128, 0, st>>>(d, c);
+          k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, c, np_lanes);
           cudaEventRecord(b, st);
           ctx->np_pending.push_back({c, a, b});
         }
       } else
-      { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide, 128, 0, st>>>(d, -1); }
+      { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes); }
       // k_equations and k_islands both consume k_slot_counts' result and nothing of each other.  The light one (islands: a
       // warp per small world, latency-bound) goes first on the main stream with a grid that leaves CTA slots and registers
       // free, the heavy one (equations, 168 registers) on a side stream beside it.
@@ -722,18 +726,23 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
           return (size_t)3 * ch * 4 + (size_t)(ch + 1) * 4 + (sb ? (size_t)cap_bodies * 4 + 16 + (size_t)cap_bodies * 64 : 0) +
                  (sr ? (size_t)cap_groups * 32 + (size_t)cap_rows * (192 + 8) : 0) + 64;
         };
-        const int cb = d.nb_max + 2;
-        const size_t need = team_smem(16, cb, 0, 0, true, false);
-        if (need <= ctx->team_smem_max) TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<16, true, false><<<ctx->sm_count, 512, need, sx>>>(d, kBins - 1, kBins - 1, force_resum, cb, 0, 0); }));
-        else TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<16, false, false><<<ctx->sm_count, 512, team_smem(16, 0, 0, 0, false, false), sx>>>(d, kBins - 1, kBins - 1, force_resum, 0, 0, 0); }));
-        const int c8b = (1 << 8) + 2, c8r = 3 << 8, c8g = 1 << 8;
-        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<4, true, true><<<ctx->sm_count, 128, team_smem(4, c8b, c8r, c8g, true, true), sx>>>(d, 8, 8, force_resum, c8b, c8r, c8g); }));
-        for (int c = 7; c > kLaneBinMax; c--) {
+        // the two long poles first (they get the high-priority streams): a warp per island for classes 7 and 6
+        static const int team_lo = getenv("EP_TEAM_LO") ? std::max(3, std::min(kLaneBinMax + 1, atoi(getenv("EP_TEAM_LO")))) : kLaneBinMax + 1;
+        for (int c = 7; c >= team_lo; c--) {
           const int cbod = (1 << c) + 2, crow = 3 << c, cgrp = 1 << c;
           TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_qteam<1, true, true><<<ctx->sm_count * 4, 32, team_smem(1, cbod, crow, cgrp, true, true), sx>>>(d, c, c, force_resum, cbod, crow, cgrp); }));
         }
+        // classes 8 and 9 hardly occur in worlds of <= 64 bodies: small grids (each CTA loops over the islands), so that their
+        // large shared-memory footprint never waits for room beside the other launches
+        const int cb = d.nb_max + 2;
+        const size_t need = team_smem(16, cb, 0, 0, true, false);
+        if (need <= ctx->team_smem_max) TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<16, true, false><<<8, 512, need, sx>>>(d, kBins - 1, kBins - 1, force_resum, cb, 0, 0); }));
+        else TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<16, false, false><<<8, 512, team_smem(16, 0, 0, 0, false, false), sx>>>(d, kBins - 1, kBins - 1, force_resum, 0, 0, 0); }));
+        const int c8b = (1 << 8) + 2, c8r = 3 << 8, c8g = 1 << 8;
+        TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_qteam<4, true, true><<<8, 128, team_smem(4, c8b, c8r, c8g, true, true), sx>>>(d, 8, 8, force_resum, c8b, c8r, c8g); }));
         for (int i = (int)ctx->quad_plan.size() - 1; i >= 0; i--) {
           const ep_ctx::QuadLaunch& q = ctx->quad_plan[i];
+          if (q.lo >= team_lo) continue;                       // served by the team-of-quads launches above
           const int grid = std::max(1, std::min(q.resident, d.n_bodies / q.kq + (q.hi - q.lo + 2)));
           TRY(side(EP_K_SOLVE_LANES_B0 + q.hi, [&](cudaStream_t sx) {
             if (q.kq == 8) k_solve_quads<8><<<grid, 32, q.smem, sx>>>(d, q.lo, q.hi, q.cap_rows, q.cap_bodies, q.cap_groups);

@@ -297,18 +297,21 @@ __device__ __forceinline__ ShapeRef shape_ref(const Dev& d, int inst) {
   return s;
 }
 
-__global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls) {
+// L = items per warp (lanes 0..L-1 work): 32 packs the warps full; a smaller L spreads the same items over more warps, which
+// cuts the serialisation of divergent lanes inside a warp -- it pays when there are fewer warps than the GPU has room for
+// (small batches: the kernel time is the latency of its heaviest warp).
+__global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L) {
   TagPt pa[kMaxPoly], pb[kMaxPoly];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   if (d.flags[FLAG_PAIR_OVERFLOW]) return;      // a world's pairs / items did not fit: its items were counted but never emitted
   int ci = 0;                     // position in kClassOrder of the class this warp's chunk belongs to
   const int total = d.np_first[kClasses];
-  for (int chunk = warp; chunk * 32 < total; chunk += nwarps) {
-    while (ci + 1 < kClasses && chunk * 32 >= d.np_first[ci + 1]) ci++;
+  for (int chunk = warp; chunk * L < total; chunk += nwarps) {
+    while (ci + 1 < kClasses && chunk * L >= d.np_first[ci + 1]) ci++;
     const int cls = kClassOrder[ci];
-    const int idx = chunk * 32 + lane;
-    if (idx >= d.np_end[ci] || (only_cls >= 0 && cls != only_cls)) continue;
+    const int idx = chunk * L + lane;
+    if (lane >= L || idx >= d.np_end[ci] || (only_cls >= 0 && cls != only_cls)) continue;
     int4 it = d.items[idx];
     ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
     bool polyOvf = false;
