@@ -177,22 +177,40 @@ __global__ void __launch_bounds__(128) k_bp_count(Dev d) {
 }
 __global__ void __launch_bounds__(128) k_bp_scan(Dev d) {
   const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0) {
     // item array layout: classes in descending expected cost (kClassOrder), each starting at a multiple of 32 (warps are
-    // homogeneous in class), deepest overlaps first inside a class
-    int at = 0;
-    for (int ci = 0; ci < kClasses; ci++) {
+    // homogeneous in class), deepest overlaps first inside a class.  One thread per class loads its depth bins (all loads in
+    // flight at once), one thread chains the 36 class totals, then every class writes its own offsets.
+    __shared__ int s_tot[kClasses], s_at[kClasses + 1];
+    const int ci = threadIdx.x;
+    int cnt[kDepthBins];
+    if (ci < kClasses) {
       const int cls = kClassOrder[ci];
+      int t = 0;
+#pragma unroll
+      for (int db = 0; db < kDepthBins; db++) { cnt[db] = d.cur.counters[CNT_CLASS0 + cls * kDepthBins + db]; t += cnt[db]; }
+      s_tot[ci] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int at = 0;
+      for (int k = 0; k < kClasses; k++) { s_at[k] = at; at = (at + s_tot[k] + 31) & ~31; }
+      s_at[kClasses] = at;
+    }
+    __syncthreads();
+    if (ci < kClasses) {
+      const int cls = kClassOrder[ci];
+      int at = s_at[ci];
       d.np_first[ci] = at;
+#pragma unroll
       for (int db = kDepthBins - 1; db >= 0; db--) {
         const int bin = cls * kDepthBins + db;
         d.cls_off[bin] = at; d.cls_cur[bin] = 0;
-        at += d.cur.counters[CNT_CLASS0 + bin];
+        at += cnt[db];
       }
       d.np_end[ci] = at;
-      at = (at + 31) & ~31;
+      if (ci == 0) d.np_first[kClasses] = s_at[kClasses];
     }
-    d.np_first[kClasses] = at;
   }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int w = warp; w < d.n_worlds; w += nwarps) {
