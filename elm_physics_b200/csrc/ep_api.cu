@@ -672,7 +672,24 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
           ctx->np_pending.push_back({c, a, b});
         }
       } else
-      { Timed t(ctx, EP_K_NARROWPHASE); k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes); }
+      {
+        // large batches: one kernel per module group (8192 worlds: 1.00 -> 0.84 ms); small batches: the single kernel (equal within noise)
+        static const int np_split_env = getenv("EP_NP_SPLIT") ? atoi(getenv("EP_NP_SPLIT")) : -1;
+        const int np_split = np_split_env >= 0 ? np_split_env : (d.quads ? 0 : 1);
+        static const int g12 = getenv("EP_NP_GRID12") ? atoi(getenv("EP_NP_GRID12")) : 1;
+        Timed t(ctx, EP_K_NARROWPHASE);
+        if (!np_split) k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes);
+        else {      // one kernel per module group, side by side: hull-hull on the main stream, capsule-hull and the rest beside it
+          CK(cudaEventRecord(ctx->ev_fork, st));
+          CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0));
+          k_narrowphase_group<0><<<gwide * (32 / np_lanes), 128, 0, st>>>(d, np_lanes);
+          k_narrowphase_group<1><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[0]>>>(d, np_lanes);
+          k_narrowphase_group<2><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[1]>>>(d, np_lanes);
+          CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0])); CK(cudaEventRecord(ctx->ev_join[1], ctx->aux[1]));
+          CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0)); CK(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
+          ctx->launches += 2;
+        }
+      }
       // k_equations and k_islands both consume k_slot_counts' result and nothing of each other.  The light one (islands: a
       // warp per small world, latency-bound) goes first on the main stream with a grid that leaves CTA slots and registers
       // free, the heavy one (equations, 168 registers) on a side stream beside it.

@@ -342,6 +342,40 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L)
   }
 }
 
+// The same work as three kernels, one per GROUP of Collision.* modules (shape_pair_contacts_group), launched side by side:
+// class (lo, hi) of sub-kinds 0 box, 1 convex, 2 plane, 3 sphere, 4 capsule, 5 particle -> group 0 hull-hull (classes 0, 1, 7),
+// group 1 capsule-hull (4, 10), group 2 the rest.  Each instance carries only its modules' code (the one kernel for everything is
+// 26 k SASS lines and stalls on instruction fetch) and only group 0 (and the plane-hull path of group 2) the clip-polygon buffers.
+__host__ __device__ constexpr int np_group_of_class(int cls) { return (cls == 0 || cls == 1 || cls == 7) ? 0 : ((cls == 4 || cls == 10) ? 1 : 2); }
+template <int G>
+__global__ void __launch_bounds__(128) k_narrowphase_group(Dev d, int L) {
+  TagPt pa[G == 1 ? 1 : kMaxPoly], pb[G == 1 ? 1 : kMaxPoly];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (d.flags[FLAG_PAIR_OVERFLOW]) return;
+  int chunk0 = 0;                 // chunks of this group's classes in front of class position ci
+  for (int ci = 0; ci < kClasses; ci++) {
+    if (np_group_of_class(kClassOrder[ci]) != G) continue;
+    const int first = d.np_first[ci], end = d.np_end[ci], nch = (end - first + L - 1) / L;
+    // this warp's chunks of the class: global chunk index g = chunk0 + c, g % nwarps == warp
+    int c = (warp - chunk0 % nwarps + nwarps) % nwarps;
+    for (; c < nch; c += nwarps) {
+      const int idx = first + c * L + lane;
+      if (lane >= L || idx >= end) continue;
+      int4 it = d.items[idx];
+      ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
+      bool polyOvf = false;
+      shape_pair_contacts_group<G>(shape_ref(d, it.y), shape_ref(d, it.z), sink, pa, pb, polyOvf);
+      // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
+      for (int x = 0, y = sink.n - 1; x < y; x++, y--) { RawContact t = sink.buf[x]; sink.buf[x] = sink.buf[y]; sink.buf[y] = t; }
+      if (sink.overflow) d.flags[FLAG_PAIR_OVERFLOW] = 2;
+      if (polyOvf) d.flags[FLAG_POLY_OVERFLOW] = 1;
+      d.raw_cnt[it.w] = sink.n;
+    }
+    chunk0 += nch;
+  }
+}
+
 // ---- k_slot_counts / k_equations / k_joint_equations : rows of every contact and constraint ---------------
 struct BodyK { int kind; double invMass; M33 I; };
 __device__ __forceinline__ BodyK load_bodyk(const Dev& d, int r) {

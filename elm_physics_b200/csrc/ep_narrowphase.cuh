@@ -771,6 +771,43 @@ EPD Sph as_sphere(const ShapeRef& s) { Sph r; r.pos = ld3(s.f); r.r = s.f[3]; re
 EPD Cap as_capsule(const ShapeRef& s) { Cap c; c.pos = ld3(s.f); c.axis = ld3(s.f + 3); c.r = s.f[6]; c.h = s.f[7]; return c; }
 EPD Pln as_plane(const ShapeRef& s) { Pln p; p.pos = ld3(s.f); p.n = ld3(s.f + 3); return p; }
 
+// The same dispatch restricted to one GROUP of modules, so that a kernel instantiated for the group carries only that code (and
+// only the hull-hull group carries the clip-polygon buffers): 0 = convex-convex (ConvexConvex.elm), 1 = capsule-convex
+// (CapsuleConvex.elm), 2 = everything else (plane / sphere / particle against anything, capsule-capsule).
+template <int G>
+EPD void shape_pair_contacts_group(const ShapeRef& a, const ShapeRef& b, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
+  const int key = a.kind * 5 + b.kind;
+  if (G == 0) { if (key == SH_CONVEX * 5 + SH_CONVEX) convex_convex(make_cvx(a.f, a.ib), make_cvx(b.f, b.ib), out, pa, pb, polyOverflow); return; }
+  if (G == 1) {
+    if (key == SH_CONVEX * 5 + SH_CAPSULE) capsule_convex(true, as_capsule(b), make_cvx(a.f, a.ib), out);
+    else if (key == SH_CAPSULE * 5 + SH_CONVEX) capsule_convex(false, as_capsule(a), make_cvx(b.f, b.ib), out);
+    return;
+  }
+  switch (key) {
+    case SH_CONVEX * 5 + SH_PLANE: plane_convex(true, as_plane(b), make_cvx(a.f, a.ib), out, pa, pb, polyOverflow); break;
+    case SH_CONVEX * 5 + SH_SPHERE: sphere_convex(true, as_sphere(b), make_cvx(a.f, a.ib), out); break;
+    case SH_CONVEX * 5 + SH_PARTICLE: particle_convex(true, ld3(b.f), make_cvx(a.f, a.ib), out); break;
+    case SH_PLANE * 5 + SH_CONVEX: plane_convex(false, as_plane(a), make_cvx(b.f, b.ib), out, pa, pb, polyOverflow); break;
+    case SH_PLANE * 5 + SH_SPHERE: plane_sphere(false, as_plane(a), as_sphere(b), out); break;
+    case SH_PLANE * 5 + SH_PARTICLE: plane_point(false, 0, as_plane(a), ld3(b.f), out); break;
+    case SH_PLANE * 5 + SH_CAPSULE: plane_capsule(false, as_plane(a), as_capsule(b), out); break;
+    case SH_SPHERE * 5 + SH_PLANE: plane_sphere(true, as_plane(b), as_sphere(a), out); break;
+    case SH_SPHERE * 5 + SH_CONVEX: sphere_convex(false, as_sphere(a), make_cvx(b.f, b.ib), out); break;
+    case SH_SPHERE * 5 + SH_SPHERE: sphere_sphere(as_sphere(a), as_sphere(b), out); break;
+    case SH_SPHERE * 5 + SH_PARTICLE: sphere_particle(false, as_sphere(a), ld3(b.f), out); break;
+    case SH_SPHERE * 5 + SH_CAPSULE: capsule_sphere(true, as_capsule(b), as_sphere(a), out); break;
+    case SH_PARTICLE * 5 + SH_PLANE: plane_point(true, 0, as_plane(b), ld3(a.f), out); break;
+    case SH_PARTICLE * 5 + SH_CONVEX: particle_convex(false, ld3(a.f), make_cvx(b.f, b.ib), out); break;
+    case SH_PARTICLE * 5 + SH_SPHERE: sphere_particle(true, as_sphere(b), ld3(a.f), out); break;
+    case SH_PARTICLE * 5 + SH_CAPSULE: capsule_particle(true, as_capsule(b), ld3(a.f), out); break;
+    case SH_CAPSULE * 5 + SH_PLANE: plane_capsule(true, as_plane(b), as_capsule(a), out); break;
+    case SH_CAPSULE * 5 + SH_SPHERE: capsule_sphere(false, as_capsule(a), as_sphere(b), out); break;
+    case SH_CAPSULE * 5 + SH_CAPSULE: capsule_capsule(as_capsule(a), as_capsule(b), out); break;
+    case SH_CAPSULE * 5 + SH_PARTICLE: capsule_particle(false, as_capsule(a), ld3(b.f), out); break;
+    default: break;   // plane-plane, particle-particle: NarrowPhase.elm:132-134, 235-237
+  }
+}
+
 EPD void shape_pair_contacts(const ShapeRef& a, const ShapeRef& b, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
   switch (a.kind * 5 + b.kind) {
     case SH_CONVEX * 5 + SH_CONVEX: convex_convex(make_cvx(a.f, a.ib), make_cvx(b.f, b.ib), out, pa, pb, polyOverflow); break;

@@ -15,7 +15,8 @@ METRICS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thr
            "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
            "smsp__cycles_active.avg", "smsp__cycles_active.max"]
 GROUPS = {"k_bp_count": "k_broadphase", "k_bp_scan": "k_broadphase", "k_bp_emit": "k_broadphase", "k_island_sort": "k_islands",
-          "k_slot_counts": "k_islands", "k_solve_team": "k_solve", "k_solve_lanes": "k_solve", "k_joint_equations": "k_equations"}
+          "k_slot_counts": "k_islands", "k_solve_team": "k_solve", "k_solve_lanes": "k_solve", "k_solve_quads": "k_solve",
+          "k_solve_qteam": "k_solve", "k_joint_equations": "k_equations"}
 
 
 def short(name):
@@ -25,6 +26,7 @@ def short(name):
 
 def main():
     rep, table, traffic = sys.argv[1:4]
+    worlds = sys.argv[4] if len(sys.argv) > 4 else "8192"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -47,11 +49,11 @@ def main():
         base = n.split("<")[0]
         g = GROUPS.get(base, base)
         per[g] = per.get(g, 0.0) + num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")
-    json.dump({"source": f"ncu --set full --clock-control none (tools/profile_round.sh), one settled C3 step at 8192 worlds, {table}; "
+    json.dump({"source": f"ncu --set full --clock-control none (tools/profile_round.sh), one settled C3 step at {worlds} worlds, {table}; "
                          "dram__bytes_read.sum + dram__bytes_write.sum per launch",
                "note": "grouped like bench.py's brackets: k_solve = all solver launches of the step, k_broadphase = k_bp_*, "
                        "k_islands = k_slot_counts + k_islands + k_island_sort",
-               "bytes_per_launch_8192_worlds": per}, open(traffic, "w"), indent=1)
+               "bytes_per_launch_%s_worlds" % worlds: per}, open(traffic, "w"), indent=1)
     print(json.dumps(per))
 
 
