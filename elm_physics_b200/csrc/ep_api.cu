@@ -681,13 +681,14 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         if (!np_split) k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes);
         else {      // one kernel per module group, side by side: hull-hull on the main stream, capsule-hull and the rest beside it
           CK(cudaEventRecord(ctx->ev_fork, st));
-          CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0));
+          CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[2], ctx->ev_fork, 0));
           k_narrowphase_group<0><<<gwide * (32 / np_lanes), 128, 0, st>>>(d, np_lanes);
           k_narrowphase_group<1><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[0]>>>(d, np_lanes);
           k_narrowphase_group<2><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[1]>>>(d, np_lanes);
-          CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0])); CK(cudaEventRecord(ctx->ev_join[1], ctx->aux[1]));
-          CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0)); CK(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
-          ctx->launches += 2;
+          k_narrowphase_group<3><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[2]>>>(d, np_lanes);
+          CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0])); CK(cudaEventRecord(ctx->ev_join[1], ctx->aux[1])); CK(cudaEventRecord(ctx->ev_join[2], ctx->aux[2]));
+          CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0)); CK(cudaStreamWaitEvent(st, ctx->ev_join[1], 0)); CK(cudaStreamWaitEvent(st, ctx->ev_join[2], 0));
+          ctx->launches += 3;
         }
       }
       // k_equations and k_islands both consume k_slot_counts' result and nothing of each other.  The light one (islands: a

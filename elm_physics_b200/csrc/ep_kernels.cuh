@@ -343,10 +343,10 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L)
 }
 
 // The same work as three kernels, one per GROUP of Collision.* modules (shape_pair_contacts_group), launched side by side:
-// class (lo, hi) of sub-kinds 0 box, 1 convex, 2 plane, 3 sphere, 4 capsule, 5 particle -> group 0 hull-hull (classes 0, 1, 7),
-// group 1 capsule-hull (4, 10), group 2 the rest.  Each instance carries only its modules' code (the one kernel for everything is
+// class (lo, hi) of sub-kinds 0 box, 1 convex, 2 plane, 3 sphere, 4 capsule, 5 particle -> group 0 hull-hull without boxes (class 7),
+// group 3 box-box / box-hull (0, 1), group 1 capsule-hull (4, 10), group 2 the rest.  Each instance carries only its modules' code (the one kernel for everything is
 // 26 k SASS lines and stalls on instruction fetch) and only group 0 (and the plane-hull path of group 2) the clip-polygon buffers.
-__host__ __device__ constexpr int np_group_of_class(int cls) { return (cls == 0 || cls == 1 || cls == 7) ? 0 : ((cls == 4 || cls == 10) ? 1 : 2); }
+__host__ __device__ constexpr int np_group_of_class(int cls) { return cls == 7 ? 0 : ((cls == 0 || cls == 1) ? 3 : ((cls == 4 || cls == 10) ? 1 : 2)); }
 template <int G>
 __global__ void __launch_bounds__(128) k_narrowphase_group(Dev d, int L) {
   TagPt pa[G == 1 ? 1 : kMaxPoly], pb[G == 1 ? 1 : kMaxPoly];

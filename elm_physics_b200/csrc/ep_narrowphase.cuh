@@ -557,11 +557,17 @@ EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R) {
   return true;
 }
 // addContacts 40-63 with dispatchBestFaces 69-114, clipTwoFaces 204-269
-EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
+// MAY_SCREEN false: an instance for pairs with a box on either side (never screened): it carries neither the fp32 copies nor
+// the screening code
+template <bool MAY_SCREEN>
+EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
   SatResult R;
-  const bool screened = !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
+  const bool screened = MAY_SCREEN && !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
                         c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
-  if (!(screened ? convex_sat_screened(c1, c2, R) : convex_sat(c1, c2, R))) return;
+  bool hit;
+  if (MAY_SCREEN) hit = screened ? convex_sat_screened(c1, c2, R) : convex_sat(c1, c2, R);
+  else hit = convex_sat(c1, c2, R);
+  if (!hit) return;
   const int winIdx = R.winIdx, winSide = R.winSide, winK = R.winK, dir1 = R.dir1, dir2 = R.dir2;
   const bool edgeBeats = R.edgeBeats; const V3 eAxis = R.eAxis;
   if (edgeBeats) {   // addEdgeContact 148-169
@@ -611,6 +617,7 @@ EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa
     out.emit(false, feat(1, id1, id2, src[i].tag, 0), rev, mk(v.x - depth * f1.n.x, v.y - depth * f1.n.y, v.z - depth * f1.n.z), v);
   }
 }
+EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) { convex_convex_t<true>(c1, c2, out, pa, pb, polyOverflow); }
 
 // ---- CapsuleConvex.elm ----------------------------------------------------------------------------
 // testCapsuleConvexAxis 718-749
@@ -773,11 +780,13 @@ EPD Pln as_plane(const ShapeRef& s) { Pln p; p.pos = ld3(s.f); p.n = ld3(s.f + 3
 
 // The same dispatch restricted to one GROUP of modules, so that a kernel instantiated for the group carries only that code (and
 // only the hull-hull group carries the clip-polygon buffers): 0 = convex-convex (ConvexConvex.elm), 1 = capsule-convex
-// (CapsuleConvex.elm), 2 = everything else (plane / sphere / particle against anything, capsule-capsule).
+// (CapsuleConvex.elm), 2 = everything else (plane / sphere / particle against anything, capsule-capsule), 3 = convex-convex
+// with a box on either side (group 0 then holds the general hull pairs only).
 template <int G>
 EPD void shape_pair_contacts_group(const ShapeRef& a, const ShapeRef& b, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
   const int key = a.kind * 5 + b.kind;
-  if (G == 0) { if (key == SH_CONVEX * 5 + SH_CONVEX) convex_convex(make_cvx(a.f, a.ib), make_cvx(b.f, b.ib), out, pa, pb, polyOverflow); return; }
+  if (G == 0) { if (key == SH_CONVEX * 5 + SH_CONVEX) convex_convex_t<true>(make_cvx(a.f, a.ib), make_cvx(b.f, b.ib), out, pa, pb, polyOverflow); return; }
+  if (G == 3) { if (key == SH_CONVEX * 5 + SH_CONVEX) convex_convex_t<false>(make_cvx(a.f, a.ib), make_cvx(b.f, b.ib), out, pa, pb, polyOverflow); return; }
   if (G == 1) {
     if (key == SH_CONVEX * 5 + SH_CAPSULE) capsule_convex(true, as_capsule(b), make_cvx(a.f, a.ib), out);
     else if (key == SH_CAPSULE * 5 + SH_CONVEX) capsule_convex(false, as_capsule(a), make_cvx(b.f, b.ib), out);
