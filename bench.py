@@ -68,7 +68,8 @@ def kernel_bytes(name, c):
 # this workload where the capture was taken on a 2048-world batch; None where no capture exists yet.
 TRAFFIC_NCU = {}
 try:
-    TRAFFIC_NCU = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic_per_launch.json")))["bytes_per_launch_8192_worlds"]
+    TRAFFIC_NCU = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic_per_launch.json")))["bytes_per_launch_8192_worlds"]
+    TRAFFIC_NCU["k_narrowphase"] = TRAFFIC_NCU.get("k_narrowphase", TRAFFIC_NCU.get("k_narrowphase_group"))
 except Exception:  # noqa: BLE001
     pass
 
@@ -616,7 +617,9 @@ def main():
         dur_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
         ach = kernel_bytes(dom, c) / (dur_ms * 1e-3) / 1e9
         hbm_view = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": TRAFFIC_NCU.get(dom), "peak_source": "measured" if peaks else "fallback",
+                    "traffic": (TRAFFIC_NCU.get(dom) * W / 8192.0) if TRAFFIC_NCU.get(dom) else None,
+                    "traffic_source": "profiles/r02_ncu_traffic_per_launch.json (ncu --set full at 8192 worlds), scaled by worlds per GPU / 8192",
+                    "peak_source": "measured" if peaks else "fallback",
                     "avg_launch_ms": dur_ms, "share_of_step": ktimes[dom][0] / total_k if total_k else None}
         line["roofline"] = hbm_view
         # The solver is not an HBM kernel (each row crosses HBM once per step): its roof is the FP64 pipe without FMA
@@ -634,7 +637,7 @@ def main():
             fp64_view = {"bound": "fp64", "kernel": "k_solve", "achieved": tops, "peak": fp64_peak, "unit": "T fp64 op/s (no FMA)",
                          "frac": tops / fp64_peak, "contact_iterations_per_step": ci / args.steps,
                          "mean_iterations_per_contact": ci / max(1.0, args.steps * 0.5 * (counts_p0["contacts"] + counts_prof["contacts"])),
-                         "traffic": TRAFFIC_NCU.get("k_solve"), "avg_launch_ms": ktimes["k_solve"][0] / max(ktimes["k_solve"][1], 1),
+                         "traffic": (TRAFFIC_NCU.get("k_solve") * W / 8192.0) if TRAFFIC_NCU.get("k_solve") else None, "avg_launch_ms": ktimes["k_solve"][0] / max(ktimes["k_solve"][1], 1),
                          "share_of_step": ktimes["k_solve"][0] / total_k if total_k else None,
                          "peak_source": "tools/fp64_peak.cu measured on this pool's B200 (profiles/r01_fp64_peak.json)"}
             line["roofline_fp64"] = fp64_view
