@@ -8,6 +8,7 @@
 #include <string>
 #include <unordered_map>
 #include <mutex>
+#include <chrono>
 #include <vector>
 
 #include "../../include/elm_physics_b200.h"
@@ -49,7 +50,7 @@ struct ep_ctx {
   int tile_grid[kTileBins] = {0, 0, 0, 0};
   int tile_smem[6] = {0, 0, 0, 0, 0, 0};        // dynamic shared memory of the launch that serves each lane class
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
-  int lanes_grid = 0, build_grid = 0;
+  int lanes_grid = 0;
   size_t team_smem_max = 48 * 1024;
   // quad solver (small batches): launches of k_solve_quads -- classes [lo, hi] with kq islands per warp, shared memory sized
   // for class hi (ep_solve_quads.cuh) -- and the largest batch (bodies) that takes this family (EP_SOLVER=lanes|quads overrides)
@@ -70,6 +71,8 @@ struct ep_ctx {
   // ep_raycast scratch (device), grown on demand
   void* ray_buf = nullptr; size_t ray_cap = 0;
   bool placed_current = false;      // the world-placed shape copies match the bodies' current transforms (ep_raycast)
+  // EP_TRACE_FRAME=1: host-side phases of ep_step_frame_fields accumulated per context, printed by ep_destroy (development aid)
+  double tr_us[6] = {0}; int64_t tr_frames = 0;
 };
 
 #define CK(call)                                                                                         \
@@ -137,7 +140,7 @@ extern "C" int ep_create(ep_ctx** out, int device) {
          cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
   // Shared memory of the lane-solver launches, sized for the typical tile of each class: classes 0..2 stage the whole image
   // (stand-in + 2 dynamic bodies, 2^class rows); classes 3..5 stage bodies + descriptors only (2^(class-1)+1 dynamic bodies,
-  // 2^class rows) and stream the rows.  Tiles that need more fall to the next residency mode (k_tile_build).
+  // 2^class rows) and stream the rows.  Tiles that need more fall to the next residency mode (k_solve_lanes).
   for (int i = 0; i < 3; i++) { TileDims t; t.maxB = 3; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_words(t, 32) * 8); }
   for (int i = 3; i < 6; i++) { TileDims t; t.maxB = (1 << (i - 1)) + 2; t.maxR = 1 << i; t.maxC = 1 << i; ctx->tile_smem[i] = (int)(tile_head_words(t, 32) * 8); }
   ok = ok && cudaFuncSetAttribute(k_solve_lanes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->tile_smem[2]) == cudaSuccess;
@@ -152,8 +155,6 @@ extern "C" int ep_create(ep_ctx** out, int device) {
     int per_sm = 0;
     ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<0>, 128, 0) == cudaSuccess && per_sm >= 1;
     ctx->lanes_grid = per_sm * ctx->sm_count;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_build, 128, 0) == cudaSuccess && per_sm >= 1;
-    ctx->build_grid = per_sm * ctx->sm_count;
   }
   // The team kernels' dynamic shared memory depends on the largest world of a batch.  The attribute is per function and per
   // DEVICE, i.e. shared by every context of the process: it is set once, here, to the device's opt-in maximum, and a batch
@@ -203,6 +204,10 @@ extern "C" void ep_destroy(ep_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->tr_frames > 0)
+    fprintf(stderr, "[ep] frame trace, %lld frames, mean us: enqueue H2D %.0f | enqueue step %.0f | enqueue D2H %.0f | (unused %.0f) | totals wait + contact copies + wait %.0f | flags + wait main %.0f\n",
+            (long long)ctx->tr_frames, ctx->tr_us[0] / ctx->tr_frames, ctx->tr_us[1] / ctx->tr_frames, ctx->tr_us[2] / ctx->tr_frames,
+            ctx->tr_us[3] / ctx->tr_frames, ctx->tr_us[4] / ctx->tr_frames, ctx->tr_us[5] / ctx->tr_frames);
   free_pool(ctx->world_allocs);
   free_pool(ctx->shape_allocs);
   if (ctx->ray_buf) cudaFree(ctx->ray_buf);
@@ -463,10 +468,9 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   TRY(dev_alloc(ctx, pool, &d.isl_key, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nc, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nb, nb)); TRY(dev_alloc(ctx, pool, &d.isl_nj, nb));
   TRY(dev_alloc(ctx, pool, &d.isl_root, nb)); TRY(dev_alloc(ctx, pool, &d.isl_sorted, nb));
   TRY(dev_alloc(ctx, pool, &d.key_cnt, 2 * kKeys));
-  TRY(dev_alloc(ctx, pool, &d.body_iters, nb)); TRY(dev_alloc(ctx, pool, &d.body_mark, nb)); TRY(dev_alloc(ctx, pool, &d.body_local, nb));
+  TRY(dev_alloc(ctx, pool, &d.body_iters, nb)); TRY(dev_alloc(ctx, pool, &d.body_local, nb));
   CK(cudaMemsetAsync(d.body_iters, 0, std::max(nb, 1) * sizeof(int32_t), ctx->stream));
   TRY(dev_alloc(ctx, pool, &d.tile_top, 1));
-  TRY(dev_alloc(ctx, pool, &d.tile_dir, (size_t)nb / 32 + kBins + 1));
   for (int i = 0; i < 6; i++) d.tile_smem[i] = ctx->tile_smem[i];
   {
     int64_t icap = std::max<int64_t>(1 << 16, 8 * (int64_t)ni);
@@ -695,6 +699,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
       // warp per small world, latency-bound) goes first on the main stream with a grid that leaves CTA slots and registers
       // free, the heavy one (equations, 168 registers) on a side stream beside it.
       static const int isl_per_sm = getenv("EP_ISL_CTAS") ? atoi(getenv("EP_ISL_CTAS")) : 12;
+
       if (ctx->hook_wait_in) CK(cudaStreamWaitEvent(st, ctx->ev_in, 0));     // velocities, forces, masses: first read by k_equations
       { Timed t(ctx, EP_K_ISLANDS);        // brackets k_slot_counts + k_islands + k_island_sort
         k_slot_counts<<<grid_for(ctx, d.slot_cap, 256, 8), 256, 0, st>>>(d);
@@ -717,7 +722,6 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         launch_out_kernels(ctx, d.cur, ctx->cout, 1);
         CK(cudaEventRecord(ctx->ev_out_done, ctx->cout));
       }
-      if (!d.quads) { Timed t(ctx, EP_K_TILE_BUILD); k_tile_build<<<std::max(1, std::min(ctx->build_grid, d.n_bodies / 128 + 1)), 128, 0, st>>>(d); }
     }
     {   // islands by size class, all launches concurrent: classes 0..3 lane-per-island from shared-memory tiles, 4..6 one warp
         // per island, 7.. one CTA per island (level-scheduled, ep_solve.cuh).  EP_K_SOLVE brackets the whole fork/join.
@@ -781,6 +785,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
           TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
           TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
         }
+        // the lane classes: every warp builds its own tile (bodies, descriptors, rows gathered from k_equations' records) and solves it
         TRY(side(EP_K_SOLVE_LANES_B5, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[5], tiles_cap), 32, ctx->tile_smem[5], sx>>>(d, 5, 5); }));
         TRY(side(EP_K_SOLVE_LANES_B4, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[4], tiles_cap), 32, ctx->tile_smem[4], sx>>>(d, 4, 4); }));
         TRY(side(EP_K_SOLVE_LANES_B3, [&](cudaStream_t sx) { k_solve_lanes<1><<<std::min(ctx->head_grid[3], tiles_cap), 32, ctx->tile_smem[3], sx>>>(d, 0, 3); }));
@@ -930,6 +935,10 @@ extern "C" int ep_step_frame_fields(ep_ctx* ctx, ep_bodies* B, ep_contacts* out,
   cudaStream_t st = ctx->stream;
   const size_t nb = d.n_bodies;
   if (nb == 0) return EP_OK;
+  static const bool trace = getenv("EP_TRACE_FRAME") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_last = now();
+  auto lap = [&](int k) { if (trace) { auto t = now(); ctx->tr_us[k] += std::chrono::duration<double, std::micro>(t - t_last).count(); t_last = t; } };
   // The frame as a pipeline over three streams (EP_FRAME_PIPELINE=0: everything on the main stream):
   //   main     H2D of what the front kernels read (pos, quat, bounding radius) | place .. narrowphase | rows, islands | solver | integrate | D2H of the state
   //   copy-in  H2D of everything else (80 % of the bytes), awaited by the first kernel that reads it (k_equations)
@@ -954,6 +963,7 @@ extern "C" int ep_step_frame_fields(ep_ctx* ctx, ep_bodies* B, ep_contacts* out,
     CK(H2D(sin, d.lin_lock, B->lin_lock, 3 * nb)); CK(H2D(sin, d.ang_lock, B->ang_lock, 3 * nb));
   }
   if (pipelined) CK(cudaEventRecord(ctx->ev_in, ctx->cin));
+  lap(0);
   {
     // Several contexts on one device (sub-batches driven from their own host threads) take turns on the SMs when the
     // contact read-back FOLLOWS the step: the step of a context waits for the step of the context before it, so that it
@@ -977,6 +987,7 @@ extern "C" int ep_step_frame_fields(ep_ctx* ctx, ep_bodies* B, ep_contacts* out,
     if (rc != EP_OK) return rc;
     if (gated) CK(cudaEventRecord(g.ev, st));
   }
+  lap(1);
   auto D2H = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st); };
   if (down & EP_F_POS) CK(D2H(B->pos, d.pos, 3 * nb));
   if (down & EP_F_QUAT) CK(D2H(B->quat, d.quat, 4 * nb));
@@ -985,13 +996,18 @@ extern "C" int ep_step_frame_fields(ep_ctx* ctx, ep_bodies* B, ep_contacts* out,
   if (down & EP_F_FORCE) CK(D2H(B->force, d.force, 3 * nb));          // zeros for every non-static body (SolverBody.elm:139-141, 221-223)
   if (down & EP_F_TORQUE) CK(D2H(B->torque, d.torque, 3 * nb));
   if (down & EP_F_INV_INERTIA_WORLD) CK(D2H(B->inv_inertia_world, d.iiw, 9 * nb));
+  lap(2);
   if (out) {
     if (early_out) {       // marshalled in the middle of the step on the copy-out stream (the frame is d.prev by now)
       TRY(copy_out_contacts(ctx, d.prev, out, ctx->cout));
       TRY(wait_stream(ctx, ctx->cout));
     } else TRY(download_contacts_async(ctx, out));
   }
-  return check_flags(ctx);
+  lap(4);
+  const int rc_flags = check_flags(ctx);
+  lap(5);
+  if (trace) ctx->tr_frames++;
+  return rc_flags;
 }
 
 extern "C" int ep_step(ep_ctx* ctx, ep_bodies* bodies, const ep_params* params, const ep_contacts* warm_in, ep_contacts* out, int32_t n_steps) {

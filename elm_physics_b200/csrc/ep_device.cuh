@@ -158,11 +158,9 @@ struct Dev {
   int32_t* isl_sorted;        // [n_bodies] island indices in work-list order
   int32_t* key_cnt;           // [kKeys] histogram, [kKeys..2*kKeys) scatter cursors
   int32_t* body_iters;        // [n_bodies] iterations the island rooted at this body used last frame (the predictor)
-  int32_t* body_mark;         // [n_bodies] local index of the body inside its island's tile (0 = not yet assigned)
-  // tile images: lane-transposed copies of the islands of a tile (ep_solve.cuh)
+  // tile images of the lane solver that do not fit shared memory (rows of the large lane classes; ep_solve.cuh)
   double* tile_arena; int64_t tile_arena_cap;   // in doubles
   unsigned long long* tile_top;                 // bump pointer (doubles)
-  int4* tile_dir;             // [n_bodies / 32 + kBins] (offset lo, offset hi, maxB | maxR << 16, maxC | residency mode << 28)
   int32_t tile_smem[6];       // bytes of dynamic shared memory of the launch that serves each lane class
   int32_t nb_max;             // largest world (bodies)
   const int32_t* sh_pl_off;   // [n_shapes+1] placement program of each shape template

@@ -651,44 +651,49 @@ __global__ void __launch_bounds__(256) k_slot_counts(Dev d) {
   }
 }
 
-// k_equations: one thread per contact (contactEquations)
+// The identity and geometry of contact `out` of the frame (ContactRec without lam / t1) and its warm-start seed: the cached
+// normal lambda and friction-1 direction of the same (bodyKey, shapeKey, featureKey) in the previous frame, or zeros.
+__device__ __forceinline__ void gather_contact(const Dev& d, int out, ContactRec& c, double& lam, V3& ct1, int& r1, int& r2, int& w) {
+  const int2 src = d.contact_src[out];
+  const int s = src.x;
+  r1 = d.cur.slot_row1[s]; r2 = d.cur.slot_row2[s];
+  w = d.body_world[r1];
+  const int k = src.y / kRawStride - d.cur.slot_item0[s];
+  const int i1b = d.inst_off[r1], i2b = d.inst_off[r2], ns2 = d.inst_off[r2 + 1] - i2b;
+  const int a = i1b + k / ns2, b = i2b + k % ns2;
+  const int sk = (k / ns2 + 1) * 256 + (k % ns2 + 1);     // ContactId.elm:75-77
+  const double f1 = d.inst_friction[a], f2 = d.inst_friction[b], e1 = d.inst_bounciness[a], e2 = d.inst_bounciness[b];
+  const RawContact rc = d.raw[src.y];
+  c.fk = rc.fk; c.sk = sk; c.slot = s;
+  c.ni[0] = rc.ni.x; c.ni[1] = rc.ni.y; c.ni[2] = rc.ni.z;
+  c.pi[0] = rc.pi.x; c.pi[1] = rc.pi.y; c.pi[2] = rc.pi.z;
+  c.pj[0] = rc.pj.x; c.pj[1] = rc.pj.y; c.pj[2] = rc.pj.z;
+  c.friction = sqrt(f1 * f2);                                 // Material.elm:23-25
+  c.bounciness = (e1 + e2 + eabs(e1 - e2)) * 0.5;             // Material.elm:31-33
+  // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128; Cache.lookup: first match in pairGroup.contacts order == LAST
+  // match in solver order (ContactCache.elm:76-87)
+  lam = 0; ct1 = mk(0, 0, 0);
+  const int ps = d.prev.pair_slot[pair_index(d, w, r1, r2)];
+  if (ps >= 0) {
+    const int pc0 = d.prev.slot_cstart[ps], pcn = d.prev.slot_ccount[ps];
+    for (int m = pcn - 1; m >= 0; m--) {
+      const ContactRec& p = d.prev.contacts[pc0 + m];
+      if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { lam = p.lam; ct1 = mk(p.t1[0], p.t1[1], p.t1[2]); break; }
+    }
+  }
+}
+// k_equations: one thread per contact (contactEquations), rows to the per-contact records (RowRec / QRow)
 template <bool Q>
 __global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
   if (d.flags[FLAG_POOL_OVERFLOW]) return;       // contact_src has holes then; ep_sync reports the overflow
   const int ncont = min(d.cur.counters[CNT_CONTACTS], d.contact_cap);
   for (int out = blockIdx.x * blockDim.x + threadIdx.x; out < ncont; out += gridDim.x * blockDim.x) {
-    const int2 src = d.contact_src[out];
-    const int s = src.x;
-    const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-    const int w = d.body_world[r1];
-    const int k = src.y / kRawStride - d.cur.slot_item0[s];
-    const int i1b = d.inst_off[r1], i2b = d.inst_off[r2], ns2 = d.inst_off[r2 + 1] - i2b;
-    const int a = i1b + k / ns2, b = i2b + k % ns2;
-    const int sk = (k / ns2 + 1) * 256 + (k % ns2 + 1);     // ContactId.elm:75-77
-    const double f1 = d.inst_friction[a], f2 = d.inst_friction[b], e1 = d.inst_bounciness[a], e2 = d.inst_bounciness[b];
-    const double friction = sqrt(f1 * f2);                          // Material.elm:23-25
-    const double bounciness = (e1 + e2 + eabs(e1 - e2)) * 0.5;      // Material.elm:31-33
-    const RawContact rc = d.raw[src.y];
-    ContactRec c;
-    c.fk = rc.fk; c.sk = sk; c.slot = s;
-    c.ni[0] = rc.ni.x; c.ni[1] = rc.ni.y; c.ni[2] = rc.ni.z;
-    c.pi[0] = rc.pi.x; c.pi[1] = rc.pi.y; c.pi[2] = rc.pi.z;
-    c.pj[0] = rc.pj.x; c.pj[1] = rc.pj.y; c.pj[2] = rc.pj.z;
-    c.friction = friction; c.bounciness = bounciness;
-    // Cache.getGroup (bodyKey id1 id2), Equation.elm:122-128; Cache.lookup: first match in pairGroup.contacts order == LAST
-    // match in solver order (ContactCache.elm:76-87)
-    double lam = 0; V3 ct1 = mk(0, 0, 0);
-    const int ps = d.prev.pair_slot[pair_index(d, w, r1, r2)];
-    if (ps >= 0) {
-      const int pc0 = d.prev.slot_cstart[ps], pcn = d.prev.slot_ccount[ps];
-      for (int m = pcn - 1; m >= 0; m--) {
-        const ContactRec& p = d.prev.contacts[pc0 + m];
-        if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { lam = p.lam; ct1 = mk(p.t1[0], p.t1[1], p.t1[2]); break; }
-      }
-    }
+    ContactRec c; double lam; V3 ct1; int r1, r2, w;
+    gather_contact(d, out, c, lam, ct1, r1, r2, w);
     const double dt = d.dt[w]; const V3 gravity = ld3(d.gravity + 3 * w);
     const BodyE b1 = load_bodye(d, r1), b2 = load_bodye(d, r2);
-    const V3 t1 = contact_row<Q>(Q ? nullptr : d.rows + out, Q ? d.qrows + 3 * (size_t)out : nullptr, rc.ni, rc.pi, rc.pj, bounciness, friction, lam, ct1, dt, gravity, spook(dt), b1, b2);
+    const V3 t1 = contact_row<Q>(Q ? nullptr : d.rows + out, Q ? d.qrows + 3 * (size_t)out : nullptr, mk(c.ni[0], c.ni[1], c.ni[2]), mk(c.pi[0], c.pi[1], c.pi[2]),
+                                 mk(c.pj[0], c.pj[1], c.pj[2]), c.bounciness, c.friction, lam, ct1, dt, gravity, spook(dt), b1, b2);
     c.lam = lam * kWarmStartFactor; c.t1[0] = t1.x; c.t1[1] = t1.y; c.t1[2] = t1.z;
     d.cur.contacts[out] = c;
   }
@@ -754,7 +759,7 @@ __global__ void k_islands(Dev d, int use_smem) {
     int* count = use_smem ? s_isl + d.nb_max : d.uf_count + r0;
     int* fill = use_smem ? s_isl + 2 * d.nb_max : d.uf_fill + r0;
     const int s0 = d.cur.cand_base[w], sn = d.cur.cand_n[w];
-    for (int l = tid; l < n; l += nt) { parent[l] = l; count[l] = 0; fill[l] = 0; d.body_mark[r0 + l] = 0; d.body_local[r0 + l] = 0; }
+    for (int l = tid; l < n; l += nt) { parent[l] = l; count[l] = 0; fill[l] = 0; d.body_local[r0 + l] = 0; }
     if (tid == 0) { s_nisl = 0; s_valid = 0; }
     __syncthreads();
     // Islands.connect for every dynamic-dynamic pair group (Solver.elm:201-206)
@@ -909,150 +914,16 @@ __global__ void __launch_bounds__(256) k_island_sort(Dev d) {
   }
 }
 
-// ---- k_solve : one thread per island --------------------------------------------------------------------
+// ---- solver-body deltas and the row dot product shared by the island solvers (ep_solve.cuh, ep_solve_quads.cuh) ------
 struct SB { double vX, vY, vZ, wX, wY, wZ; };
 __device__ __forceinline__ SB load_sb(const double* p) { SB s; s.vX = p[0]; s.vY = p[1]; s.vZ = p[2]; s.wX = p[3]; s.wY = p[4]; s.wZ = p[5]; return s; }
 __device__ __forceinline__ void store_sb(double* p, const SB& s) { p[0] = s.vX; p[1] = s.vY; p[2] = s.vZ; p[3] = s.wX; p[4] = s.wY; p[5] = s.wZ; }
-// applyVelocityBody1/2 (Solver.elm:505-550) == applyEquationWarmStart (39-85)
-__device__ __forceinline__ void apply_row(double dl, const double* J, const BodyK& k1, const BodyK& k2, SB& s1, SB& s2) {
-  if (k1.kind == 2) {
-    const M33& I = k1.I; double k = dl * k1.invMass;
-    double vX = s1.vX - k * J[3], vY = s1.vY - k * J[4], vZ = s1.vZ - k * J[5];
-    double wX = s1.wX + (I.m11 * J[0] + I.m12 * J[1] + I.m13 * J[2]) * dl;
-    double wY = s1.wY + (I.m21 * J[0] + I.m22 * J[1] + I.m23 * J[2]) * dl;
-    double wZ = s1.wZ + (I.m31 * J[0] + I.m32 * J[1] + I.m33 * J[2]) * dl;
-    s1.vX = vX; s1.vY = vY; s1.vZ = vZ; s1.wX = wX; s1.wY = wY; s1.wZ = wZ;
-  }
-  if (k2.kind == 2) {
-    const M33& I = k2.I; double k = dl * k2.invMass;
-    double vX = s2.vX + k * J[3], vY = s2.vY + k * J[4], vZ = s2.vZ + k * J[5];
-    double wX = s2.wX + (I.m11 * J[6] + I.m12 * J[7] + I.m13 * J[8]) * dl;
-    double wY = s2.wY + (I.m21 * J[6] + I.m22 * J[7] + I.m23 * J[8]) * dl;
-    double wZ = s2.wZ + (I.m31 * J[6] + I.m32 * J[7] + I.m33 * J[8]) * dl;
-    s2.vX = vX; s2.vY = vY; s2.vZ = vZ; s2.wX = wX; s2.wY = wY; s2.wZ = wZ;
-  }
-}
 __device__ __forceinline__ double gw_lambda(const double* J, const SB& b1, const SB& b2) {
   return -(J[3] * b1.vX + J[4] * b1.vY + J[5] * b1.vZ)
          + (J[0] * b1.wX + J[1] * b1.wY + J[2] * b1.wZ)
          + (J[3] * b2.vX + J[4] * b2.vY + J[5] * b2.vZ)
          + (J[6] * b2.wX + J[7] * b2.wY + J[8] * b2.wZ);
 }
-// One joint / contact-normal row (solveVelocityConstraints 572-619, solveVelocityNormals 625-672): returns deltaLambda
-__device__ __forceinline__ double row_solve(const double* J, double B, double invC, double eps, double lo, double hi, double& lam,
-                                            const BodyK& k1, const BodyK& k2, SB& s1, SB& s2) {
-  double prev = invC * (B - gw_lambda(J, s1, s2) - eps * lam);
-  double dl = (lam + prev - lo < 0) ? lo - lam : ((lam + prev - hi > 0) ? hi - lam : prev);
-  apply_row(dl, J, k1, k2, s1, s2);
-  lam = lam + dl;
-  return dl;
-}
-// One contact's friction pair (solveVelocityFrictions, Solver.elm:678-844): friction1 then friction2, cone +-mu*lambda_n
-__device__ __forceinline__ double friction_pair(const double* e1, const double* e2, double f1B, double f1InvC, double f2B, double f2InvC,
-                                                double eps, double mu, double nl, double& lamF1, double& lamF2,
-                                                const BodyK& k1, const BodyK& k2, SB& s1, SB& s2, double tot, double& a1, double& a2) {
-  const M33 &I1 = k1.I, &I2 = k2.I;
-  double cap1 = mu * nl;
-  double gW1 = gw_lambda(e1, s1, s2);
-  double dPrev1 = f1InvC * (f1B - gW1 - eps * lamF1);
-  double d1 = (lamF1 + dPrev1 + cap1 < 0) ? -cap1 - lamF1 : ((lamF1 + dPrev1 - cap1 > 0) ? cap1 - lamF1 : dPrev1);
-  double k1a = d1 * k1.invMass;
-  double b1vX = s1.vX - k1a * e1[3], b1vY = s1.vY - k1a * e1[4], b1vZ = s1.vZ - k1a * e1[5];
-  double b1wX = s1.wX + (I1.m11 * e1[0] + I1.m12 * e1[1] + I1.m13 * e1[2]) * d1;
-  double b1wY = s1.wY + (I1.m21 * e1[0] + I1.m22 * e1[1] + I1.m23 * e1[2]) * d1;
-  double b1wZ = s1.wZ + (I1.m31 * e1[0] + I1.m32 * e1[1] + I1.m33 * e1[2]) * d1;
-  double k1b = d1 * k2.invMass;
-  double b2vX = s2.vX + k1b * e1[3], b2vY = s2.vY + k1b * e1[4], b2vZ = s2.vZ + k1b * e1[5];
-  double b2wX = s2.wX + (I2.m11 * e1[6] + I2.m12 * e1[7] + I2.m13 * e1[8]) * d1;
-  double b2wY = s2.wY + (I2.m21 * e1[6] + I2.m22 * e1[7] + I2.m23 * e1[8]) * d1;
-  double b2wZ = s2.wZ + (I2.m31 * e1[6] + I2.m32 * e1[7] + I2.m33 * e1[8]) * d1;
-  double cap2 = mu * nl;
-  double gW2 = -(e2[3] * b1vX + e2[4] * b1vY + e2[5] * b1vZ)
-               + (e2[0] * b1wX + e2[1] * b1wY + e2[2] * b1wZ)
-               + (e2[3] * b2vX + e2[4] * b2vY + e2[5] * b2vZ)
-               + (e2[6] * b2wX + e2[7] * b2wY + e2[8] * b2wZ);
-  double dPrev2 = f2InvC * (f2B - gW2 - eps * lamF2);
-  double d2 = (lamF2 + dPrev2 + cap2 < 0) ? -cap2 - lamF2 : ((lamF2 + dPrev2 - cap2 > 0) ? cap2 - lamF2 : dPrev2);
-  if (k1.kind == 2) {
-    double k2a = d2 * k1.invMass;
-    s1.vX = b1vX - k2a * e2[3]; s1.vY = b1vY - k2a * e2[4]; s1.vZ = b1vZ - k2a * e2[5];
-    s1.wX = b1wX + (I1.m11 * e2[0] + I1.m12 * e2[1] + I1.m13 * e2[2]) * d2;
-    s1.wY = b1wY + (I1.m21 * e2[0] + I1.m22 * e2[1] + I1.m23 * e2[2]) * d2;
-    s1.wZ = b1wZ + (I1.m31 * e2[0] + I1.m32 * e2[1] + I1.m33 * e2[2]) * d2;
-  }
-  if (k2.kind == 2) {
-    double k2b = d2 * k2.invMass;
-    s2.vX = b2vX + k2b * e2[3]; s2.vY = b2vY + k2b * e2[4]; s2.vZ = b2vZ + k2b * e2[5];
-    s2.wX = b2wX + (I2.m11 * e2[6] + I2.m12 * e2[7] + I2.m13 * e2[8]) * d2;
-    s2.wY = b2wY + (I2.m21 * e2[6] + I2.m22 * e2[7] + I2.m23 * e2[8]) * d2;
-    s2.wZ = b2wZ + (I2.m31 * e2[6] + I2.m32 * e2[7] + I2.m33 * e2[8]) * d2;
-  }
-  lamF1 = lamF1 + d1;
-  lamF2 = lamF2 + d2;
-  a1 = eabs(d1); a2 = eabs(d2);
-  return tot + a1 + a2;
-}
-// velocityNonFrictionGroup (Solver.elm:850-864): joints (572-619) then contact normals (625-672)
-__device__ double sweep_nonfriction(const Dev& d, int s, double eps, double tot) {
-  int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-  BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
-  SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
-  int j0 = d.cur.slot_jstart[s], jn = d.cur.slot_jcount[s];
-  for (int k = 0; k < jn; k++) {
-    JointRow& r = d.jrows[j0 + k];
-    double lam = r.lam;
-    double dl = row_solve(r.J, r.B, r.invC, r.eps, -kMaxImpulse, kMaxImpulse, lam, k1, k2, s1, s2);
-    r.lam = lam; r.dl = eabs(dl);
-    tot = tot + eabs(dl);
-  }
-  int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
-  for (int k = 0; k < cn; k++) {
-    RowRec& r = d.rows[c0 + k];
-    double lam = r.lamN;
-    double dl = row_solve(r.nJ, r.nB, r.nInvC, eps, 0.0, kMaxImpulse, lam, k1, k2, s1, s2);
-    r.lamN = lam; r.dN = eabs(dl);
-    tot = tot + eabs(dl);
-  }
-  if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
-  if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
-  return tot;
-}
-// velocityFrictionGroup / solveVelocityFrictions (Solver.elm:678-844)
-__device__ double sweep_friction(const Dev& d, int s, double eps, double tot) {
-  int c0 = d.cur.slot_cstart[s], cn = d.cur.slot_ccount[s];
-  if (cn <= 0) return tot;
-  int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-  BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
-  SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
-  for (int k = 0; k < cn; k++) {
-    RowRec& r = d.rows[c0 + k];
-    double l1 = r.lamF1, l2 = r.lamF2;
-    double a1, a2;
-    tot = friction_pair(r.f1J, r.f2J, r.f1B, r.f1InvC, r.f2B, r.f2InvC, eps, r.mu, r.lamN, l1, l2, k1, k2, s1, s2, tot, a1, a2);
-    r.lamF1 = l1; r.lamF2 = l2; r.dF1 = a1; r.dF2 = a2;
-  }
-  if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
-  if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
-  return tot;
-}
-
-// applyContactsWarmStart of one pair group (Solver.elm:102-119): the seeded normal impulses, solver order
-__device__ void warm_group(const Dev& d, int s) {
-  int cn = d.cur.slot_ccount[s];
-  if (cn <= 0) return;
-  int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
-  BodyK k1 = load_bodyk(d, r1), k2 = load_bodyk(d, r2);
-  SB s1 = load_sb(d.sbv + 6 * r1), s2 = load_sb(d.sbv + 6 * r2);
-  int c0 = d.cur.slot_cstart[s];
-  for (int k = 0; k < cn; k++) {
-    const RowRec& r = d.rows[c0 + k];
-    if (r.lamN == 0) continue;                      // Solver.elm:41
-    apply_row(r.lamN, r.nJ, k1, k2, s1, s2);
-  }
-  if (k1.kind == 2) store_sb(d.sbv + 6 * r1, s1);
-  if (k2.kind == 2) store_sb(d.sbv + 6 * r2, s2);
-}
-// islands of size classes [bin_lo, bin_hi], largest class first: the sorted work list holds the classes contiguously in descending order
 __device__ __forceinline__ int class_start(const Dev& d, int bin) {
   int at = 0;
   for (int b = kBins - 1; b > bin; b--) at += d.cur.counters[CNT_BIN0 + b];

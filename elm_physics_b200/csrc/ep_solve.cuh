@@ -5,14 +5,13 @@
 // contact); warm start in reverse group order; sum|dlambda| association of `step` (two sums added) vs `solve2Body` (one
 // running sum).  Two mappings, chosen by island size class (island_bin, ep_kernels.cuh):
 //
-//   classes 0..kLaneBinMax  one LANE per island, one WARP per tile of 32 islands (k_tile_build + k_solve_lanes).  The work
-//       list is sorted by (class, iterations the island used last frame, group count), so the 32 lanes of a tile run about
-//       the same rows for about the same number of iterations.  k_tile_build gathers each tile ONCE into a lane-transposed
-//       image (word k of lane l at [k][l]: every access of the warp is one coalesced 256 B request / conflict-free LDS.64):
-//       Jacobian rows, Spook scalars, lambdas, the islands' dynamic bodies (constants + solver-body delta velocities) and
-//       per-row descriptors (which two bodies a row couples).  k_solve_lanes<L> stages the image in shared memory and iterates
-//       there; HBM sees each row once per step instead of once per iteration.  Large classes put fewer islands in a tile
-//       (class_lanes) so that it still fits.
+//   classes 0..kLaneBinMax  one LANE per island, one WARP per tile of 32 islands (k_solve_lanes).  The work list is sorted
+//       by (class, iterations the island used last frame, group count), so the 32 lanes of a tile run about the same rows
+//       for about the same number of iterations.  The warp gathers its tile ONCE into a lane-transposed image (word k of
+//       lane l at [k][l]: every access of the warp is one coalesced 256 B request / conflict-free LDS.64): Jacobian rows,
+//       Spook scalars, lambdas, the islands' dynamic bodies (constants + solver-body delta velocities) and per-row
+//       descriptors (which two bodies a row couples) -- in shared memory where it fits -- and iterates there; HBM sees
+//       each row once per step instead of once per iteration.
 //   classes above           one CTA per island, the pair groups of one dependency level in parallel (k_solve_team).
 #pragma once
 #include "ep_kernels.cuh"
@@ -93,102 +92,6 @@ __device__ __forceinline__ bool lane_tile(const Dev& d, int gtile, TileRef& r) {
 __device__ __forceinline__ int warp_max(int v) {
   for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
-}
-
-// ---- k_tile_build : one warp per tile, one lane per island ---------------------------------------------------------------
-// Residency of a tile, decided here from the dynamic shared memory of the class's launch (Dev::tile_smem): 2 = whole image
-// staged in shared memory, 1 = bodies + descriptors staged and the rows streamed from L2 one row ahead, 0 = in place.
-__global__ void __launch_bounds__(128) k_tile_build(Dev d) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int gtile = warp;; gtile += nwarps) {
-    TileRef tr;
-    if (!lane_tile(d, gtile, tr)) break;
-    const int L = class_lanes(tr.bin);
-    const int isl = lane < tr.count ? d.isl_sorted[tr.first + lane] : -1;
-    const int g0 = isl >= 0 ? d.isl_off[isl] : 0, gn = isl >= 0 ? d.isl_cnt[isl] : 0;
-    const int nc = isl >= 0 ? d.isl_nc[isl] : 0, nj = isl >= 0 ? d.isl_nj[isl] : 0;
-    TileDims td;
-    td.maxB = warp_max(isl >= 0 ? d.isl_nb[isl] : 0) + 1;
-    td.maxR = warp_max(nc + nj);
-    td.maxC = warp_max(nc);
-    const int64_t words = tile_words(td, L), head = tile_head_words(td, L);
-    int mode = tr.bin <= 2 ? (words * 8 <= d.tile_smem[tr.bin] ? 2 : (head * 8 <= d.tile_smem[3] ? 1 : 0)) : (head * 8 <= d.tile_smem[tr.bin] ? 1 : 0);
-    if (td.maxB >= 256 || td.maxR >= 256) td.maxC = -1;     // cannot happen for classes <= kLaneBinMax (rows <= 96); refuse rather than corrupt
-    unsigned long long off = 0;
-    if (lane == 0) {
-      off = atomicAdd(d.tile_top, (unsigned long long)words);
-      if ((int64_t)(off + words) > d.tile_arena_cap || td.maxC < 0) { d.flags[FLAG_POOL_OVERFLOW] = 2; td.maxC = -1; off = 0; }
-      d.tile_dir[gtile] = make_int4((int)(off & 0xffffffffu), (int)(off >> 32), td.maxB | (td.maxR << 16), (td.maxC & 0xfffffff) | (mode << 28));
-    }
-    off = __shfl_sync(0xffffffffu, off, 0);
-    td.maxC = __shfl_sync(0xffffffffu, td.maxC, 0);
-    if (isl < 0 || td.maxC < 0) continue;
-    TileT<0> T; T.t = td; T.lane = lane; T.Lrt = L;
-    T.bind(d.tile_arena + off, d.tile_arena + off + head);
-    // local body table: 0 = the non-dynamic stand-in, dynamic bodies 1.. in order of first appearance
-    T.body_row(0) = -1;
-#pragma unroll
-    for (int k = 0; k < kBodyF64; k++) T.body(0, k) = 0.0;
-    int nB = 1, r = 0, c = 0;
-    for (int gi = 0; gi < gn; gi++) {
-      const int s = d.isl_groups[g0 + gi];
-      const int rr[2] = {d.cur.slot_row1[s], d.cur.slot_row2[s]};
-      int lb[2];
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int br = rr[e];
-        int m = 0;
-        if (d.kind[br] == 2) {
-          m = d.body_mark[br];
-          if (m == 0) {
-            m = nB++; d.body_mark[br] = m; T.body_row(m) = br;
-            T.body(m, 0) = d.inv_mass[br];
-            const double* sb = d.sbv + 6 * (size_t)br;
-#pragma unroll
-            for (int k = 0; k < 6; k++) T.body(m, 1 + k) = sb[k];
-            T.body(m, 7) = 0.0;
-          }
-        }
-        lb[e] = m;
-      }
-      const int pair = lb[0] | (lb[1] << 8);
-      int first = DESC_GROUP_START;
-      const int j0 = d.cur.slot_jstart[s], jn = d.cur.slot_jcount[s];
-      for (int k = 0; k < jn; k++, r++) {
-        const JointRow& jr = d.jrows[j0 + k];
-        tile_write_jac(T, false, r, 0, jr.J, jr.Ia, jr.Ib);
-        T.nrow(r, NR_B) = jr.B; T.nrow(r, NR_INVC) = jr.invC; T.nrow(r, NR_LAM) = jr.lam;
-        T.desc1(r) = pair | DESC_JOINT | first; first = 0;
-      }
-      const int c0 = d.cur.slot_cstart[s], cn = max(d.cur.slot_ccount[s], 0);
-      for (int k = 0; k < cn; k++, r++, c++) {
-        T.desc1(r) = pair | first; first = 0;
-        T.desc2(c) = pair | (r << 16);
-        T.contact_index(c) = c0 + k;
-      }
-    }
-    // contact rows, all lanes in lock step on the contact index so that every store of the warp covers whole 128 B lines
-    // (a lane-by-lane copy in group order writes the same lines with partial masks: twice the DRAM traffic, measured)
-    for (int cc = 0; cc < td.maxC; cc++) {
-      if (cc >= nc) continue;
-      const int rowN = (T.desc2(cc) >> 16) & 0xff;
-      // all 58 doubles of the row into registers first (29 independent 16 B loads in flight), then the transposed stores
-      const double2* sp = (const double2*)(d.rows + T.contact_index(cc));
-      double2 v[29];
-#pragma unroll
-      for (int f = 0; f < 29; f++) v[f] = sp[f];
-      const double* src = (const double*)v;       // RowRec field offsets in doubles: nJ 0, nB 9, nInvC 10, lamN 11, f1J 12, f2J 21,
-                                                  // f1B 30, f1InvC 31, f2B 32, f2InvC 33, mu 34, lamF1 35, lamF2 36, d* 37-39, nIa 40, nIb 43,
-                                                  // f1Ia 46, f1Ib 49, f2Ia 52, f2Ib 55
-      tile_write_jac(T, false, rowN, 0, src + 0, src + 40, src + 43);
-      T.nrow(rowN, NR_B) = src[9]; T.nrow(rowN, NR_INVC) = src[10]; T.nrow(rowN, NR_LAM) = src[11];
-      tile_write_jac(T, true, cc, FR_E1, src + 12, src + 46, src + 49);
-      tile_write_jac(T, true, cc, FR_E2, src + 21, src + 52, src + 55);
-      T.frow(cc, FR_F1B) = src[30]; T.frow(cc, FR_F1INVC) = src[31]; T.frow(cc, FR_F2B) = src[32]; T.frow(cc, FR_F2INVC) = src[33];
-      T.frow(cc, FR_MU) = src[34]; T.frow(cc, FR_L1) = src[35]; T.frow(cc, FR_L2) = src[36];
-    }
-  }
 }
 
 // Rows of the tile column of this lane, loaded into registers one row AHEAD of their use so that the load latency of
@@ -388,41 +291,135 @@ __device__ __forceinline__ void solve_lane(const Dev& d, const TT& T, int isl) {
   }
 }
 
-// Rows are prefetched one row ahead into registers only where they come from L2 (a staged tile's LDS latency hides behind
-// the FP64 chain by itself, and the registers saved double the warps per SM).
-// One warp per tile.  MODE 2: whole image staged in dynamic shared memory; MODE 1: bodies + descriptors staged, rows read
-// from the image in place (L2) one row ahead; MODE 0: everything in place, four warps per CTA.  Processes the tiles of
-// classes [bin_lo, bin_hi] whose residency (k_tile_build) is MODE.
+// ---- k_solve_lanes : tile build + solve in one kernel, one warp per tile -------------------------------------------------
+// The warp of a tile
+//   (A) walks the pair groups of its 32 islands: body tables (k_islands' body_local numbering; local body 0 is the stand-in),
+//       row descriptors, joint rows copied from k_joint_equations' records,
+//   (B) gathers the rows of every contact from k_equations' per-contact records (RowRec) into the lane-transposed image --
+//       shared memory (MODE 2: whole image; these tiles have no image in HBM at all), or the arena for the row part
+//       (MODE 1: bodies + descriptors in shared memory, rows written once with whole-line stores and streamed back from L2
+//       by the same SM one row ahead; MODE 0: everything in the arena, four warps per CTA),
+//   (C) solves (solve_lane).
+// Residency of a tile follows from the dynamic shared memory of the launch that serves its class (Dev::tile_smem); every
+// launch visits the tiles of its classes and takes those of its own MODE.  Round 1 did (A) and (B) in a kernel of their own
+// (k_tile_build) in front of the solver: 0.29 ms at 8192 worlds during which nothing else ran; inside the solver's warps the
+// gather overlaps the solves of the other tiles (step 2.87 -> 2.82 ms at 8192 worlds, 1.98 -> 1.90 at 4096), and the tiles of
+// classes 0-2 never exist in HBM.  Forming the rows here as well (contactEquations per lane, no RowRec at all) was built,
+// bit-exact, and measured: the 1300 instructions per contact at the solver's occupancy cost what k_equations + k_tile_build
+// cost (2.92 ms), so k_equations stays a thread-per-contact kernel beside k_islands (profiles/r02_solver_notes.md).
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 0 ? 128 : 32) k_solve_lanes(Dev d, int bin_lo, int bin_hi) {
-  extern __shared__ __align__(16) unsigned char tile_smem[];
+__global__ void __launch_bounds__(MODE == 0 ? 128 : 32, MODE == 0 ? 3 : 12) k_solve_lanes(Dev d, int bin_lo, int bin_hi) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (d.flags[FLAG_POOL_OVERFLOW]) return;       // the contact pool overflowed: the frame is void; ep_sync reports it
   int t0 = 0;                     // first global tile of class bin_hi
   for (int b = kLaneBinMax; b > bin_hi; b--) t0 += class_tiles(d, b);
   int nt = 0;
   for (int b = bin_hi; b >= bin_lo; b--) nt += class_tiles(d, b);
   for (int t = warp; t < nt; t += nwarps) {
-    const int gtile = t0 + t;
-    const int4 e = d.tile_dir[gtile];
-    const int mode = (e.w >> 28) & 3;
-    int maxC = e.w & 0xfffffff; if (maxC & 0x8000000) maxC = -1;
-    if (mode != MODE || maxC < 0) continue;
-    TileRef tr; lane_tile(d, gtile, tr);
-    TileT<32> T; T.lane = lane; T.Lrt = 32; T.t.maxB = e.z & 0xffff; T.t.maxR = (e.z >> 16) & 0xffff; T.t.maxC = maxC;
-    double* img = d.tile_arena + (((unsigned long long)(unsigned)e.y << 32) | (unsigned)e.x);
-    const int head = (int)tile_head_words(T.t, 32);
-    if (MODE == 0) {
-      T.bind(img, img + head);
-    } else {
-      double* sm = (double*)tile_smem;
-      const int n = MODE == 2 ? (int)tile_words(T.t, 32) : head;
-      __syncwarp();
-      for (int i = lane; i < n; i += 32) sm[i] = img[i];
-      __syncwarp();
-      T.bind(sm, MODE == 2 ? sm + head : img + head);
+    TileRef tr; lane_tile(d, t0 + t, tr);
+    const int isl = lane < tr.count ? d.isl_sorted[tr.first + lane] : -1;
+    const int g0 = isl >= 0 ? d.isl_off[isl] : 0, gn = isl >= 0 ? d.isl_cnt[isl] : 0;
+    const int nc = isl >= 0 ? d.isl_nc[isl] : 0, nj = isl >= 0 ? d.isl_nj[isl] : 0;
+    TileT<32> T; T.lane = lane; T.Lrt = 32;
+    T.t.maxB = warp_max(isl >= 0 ? d.isl_nb[isl] : 0) + 1;
+    T.t.maxR = warp_max(nc + nj);
+    T.t.maxC = warp_max(nc);
+    const int64_t words = tile_words(T.t, 32), head = tile_head_words(T.t, 32);
+    const int mode = tr.bin <= 2 ? (words * 8 <= d.tile_smem[tr.bin] ? 2 : (head * 8 <= d.tile_smem[3] ? 1 : 0)) : (head * 8 <= d.tile_smem[tr.bin] ? 1 : 0);
+    if (mode != MODE) continue;
+    if (T.t.maxB >= 256 || T.t.maxR >= 256) { if (lane == 0) d.flags[FLAG_POOL_OVERFLOW] = 2; continue; }     // cannot happen for classes <= kLaneBinMax (rows <= 96); refuse rather than corrupt
+    const int64_t need = MODE == 2 ? 0 : (MODE == 1 ? words - head : words);
+    unsigned long long off = 0;
+    if (MODE != 2) {
+      if (lane == 0) {
+        off = atomicAdd(d.tile_top, (unsigned long long)need);
+        if ((int64_t)(off + need) > d.tile_arena_cap) { d.flags[FLAG_POOL_OVERFLOW] = 2; off = ~0ull; }
+      }
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (off == ~0ull) continue;
     }
-    solve_lane<MODE == 1 ? 1 : 0>(d, T, lane < tr.count ? d.isl_sorted[tr.first + lane] : -1);
+    double* sm = (double*)tile_smem;
+    __syncwarp();
+    if (MODE == 2) T.bind(sm, sm + head);
+    else if (MODE == 1) T.bind(sm, d.tile_arena + off);
+    else T.bind(d.tile_arena + off, d.tile_arena + off + head);
+    // ---- (A) body table, descriptors, joint rows -----------------------------------------------------------------------------
+    if (isl >= 0) {
+      T.body_row(0) = -1;
+#pragma unroll
+      for (int k = 0; k < kBodyF64; k++) T.body(0, k) = 0.0;
+    }
+    const int gmax = warp_max(gn);
+    int r = 0, c = 0;
+    for (int gi = 0; gi < gmax; gi++) {
+      if (gi >= gn) continue;
+      const int s = d.isl_groups[g0 + gi];
+      const int r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+      const int lb1 = d.kind[r1] == 2 ? d.body_local[r1] : 0, lb2 = d.kind[r2] == 2 ? d.body_local[r2] : 0;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int lb = e ? lb2 : lb1, br = e ? r2 : r1;
+        if (lb == 0) continue;                       // several groups may write the same body: same values
+        T.body_row(lb) = br;
+        T.body(lb, 0) = d.inv_mass[br];
+#pragma unroll
+        for (int k = 1; k < kBodyF64; k++) T.body(lb, k) = 0.0;       // the solver-body deltas start at zero (SolverBody.elm:28-38)
+      }
+      const int pair = lb1 | (lb2 << 8);
+      int first = DESC_GROUP_START;
+      const int j0 = d.cur.slot_jstart[s], jn = max(d.cur.slot_jcount[s], 0);
+      for (int k = 0; k < jn; k++, r++) {
+        const JointRow& jr = d.jrows[j0 + k];
+        tile_write_jac(T, false, r, 0, jr.J, jr.Ia, jr.Ib);
+        T.nrow(r, NR_B) = jr.B; T.nrow(r, NR_INVC) = jr.invC; T.nrow(r, NR_LAM) = jr.lam;
+        T.desc1(r) = pair | DESC_JOINT | first; first = 0;
+      }
+      const int c0 = d.cur.slot_cstart[s], cn = max(d.cur.slot_ccount[s], 0);
+      for (int k = 0; k < cn; k++, r++, c++) {
+        T.desc1(r) = pair | first; first = 0;
+        T.desc2(c) = pair | (r << 16);
+        T.contact_index(c) = c0 + k;
+      }
+    }
+    __syncwarp();
+    // ---- (B) contact rows, all lanes in lock step on the contact index so that every store of the warp covers whole 128 B lines
+    // where the rows go to the arena (a lane-by-lane copy in group order writes the same lines with partial masks: twice the
+    // DRAM traffic, measured)
+    for (int cc = 0; cc < T.t.maxC; cc++) {
+      if (cc >= nc) continue;
+      const int rowN = (T.desc2(cc) >> 16) & 0xff;
+      // the record in two halves (15 + 14 independent 16 B loads in flight each), then the transposed stores; RowRec field
+      // offsets in doubles: nJ 0, nB 9, nInvC 10, lamN 11, f1J 12, f2J 21, f1B 30, f1InvC 31, f2B 32, f2InvC 33, mu 34,
+      // lamF1 35, lamF2 36, d* 37-39, nIa 40, nIb 43, f1Ia 46, f1Ib 49, f2Ia 52, f2Ib 55
+      const double2* sp = (const double2*)(d.rows + T.contact_index(cc));
+      {
+        double2 v[15];
+#pragma unroll
+        for (int f = 0; f < 15; f++) v[f] = sp[f];
+        const double* src = (const double*)v;       // doubles 0..29
+#pragma unroll
+        for (int k = 0; k < 9; k++) { T.nrow(rowN, k) = src[k]; T.frow(cc, FR_E1 + k) = src[12 + k]; T.frow(cc, FR_E2 + k) = src[21 + k]; }
+        T.nrow(rowN, NR_B) = src[9]; T.nrow(rowN, NR_INVC) = src[10]; T.nrow(rowN, NR_LAM) = src[11];
+      }
+      {
+        double2 v[14];
+#pragma unroll
+        for (int f = 0; f < 14; f++) v[f] = sp[15 + f];
+        const double* src = (const double*)v - 30;  // doubles 30..57
+        T.frow(cc, FR_F1B) = src[30]; T.frow(cc, FR_F1INVC) = src[31]; T.frow(cc, FR_F2B) = src[32]; T.frow(cc, FR_F2INVC) = src[33];
+        T.frow(cc, FR_MU) = src[34]; T.frow(cc, FR_L1) = src[35]; T.frow(cc, FR_L2) = src[36];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          T.nrow(rowN, NR_IA + k) = src[40 + k]; T.nrow(rowN, NR_IB + k) = src[43 + k];
+          T.frow(cc, FR_E1IA + k) = src[46 + k]; T.frow(cc, FR_E1IB + k) = src[49 + k];
+          T.frow(cc, FR_E2IA + k) = src[52 + k]; T.frow(cc, FR_E2IB + k) = src[55 + k];
+        }
+      }
+    }
+    __syncwarp();
+    solve_lane<MODE == 1 ? 1 : 0>(d, T, isl);
   }
 }
 

@@ -8,6 +8,6 @@ for round in 1 2; do for v in "$@"; do
   python ../../tools/time_scene.py $scene 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); k=d['kernels_ms']
-print('$v', 'step %.3f' % d['ms_per_step'], ' '.join('%s %.3f' % (n.replace('k_',''), k[n]) for n in ['k_broadphase','k_narrowphase','k_equations','k_islands','k_tile_build','k_solve']))"
+print('$v', 'step %.3f' % d['ms_per_step'], ' '.join('%s %.3f' % (n.replace('k_',''), k.get(n, 0.0)) for n in ['k_broadphase','k_narrowphase','k_equations','k_islands','k_tile_build','k_solve']))"
 done; done
 cp /tmp/keep.so libelm_physics_b200.so
