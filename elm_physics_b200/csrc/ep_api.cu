@@ -151,6 +151,11 @@ extern "C" int ep_create(ep_ctx** out, int device) {
     else ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<1>, 32, ctx->tile_smem[i]) == cudaSuccess && per_sm >= 1;
     ctx->head_grid[i] = per_sm * ctx->sm_count;
   }
+  if (const char* hg = getenv("EP_HEAD_GRID")) {      // tuning aid: resident CTAs per SM of each lane class, "c0,c1,c2,c3,c4,c5" (0 keeps the occupancy maximum)
+    int v[6] = {0, 0, 0, 0, 0, 0};
+    sscanf(hg, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+    for (int i = 0; i < 6; i++) if (v[i] > 0) ctx->head_grid[i] = std::min(ctx->head_grid[i], v[i] * ctx->sm_count);
+  }
   if (ok) {
     int per_sm = 0;
     ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lanes<0>, 128, 0) == cudaSuccess && per_sm >= 1;
@@ -686,8 +691,12 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         else {      // one kernel per module group, side by side: hull-hull on the main stream, capsule-hull and the rest beside it
           CK(cudaEventRecord(ctx->ev_fork, st));
           CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[2], ctx->ev_fork, 0));
-          k_narrowphase_group<0><<<gwide * (32 / np_lanes), 128, 0, st>>>(d, np_lanes);
-          k_narrowphase_group<1><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[0]>>>(d, np_lanes);
+          static const int l0_env = getenv("EP_NP_LANES_G0") ? atoi(getenv("EP_NP_LANES_G0")) : 0;
+          const int l0 = (l0_env == 4 || l0_env == 8 || l0_env == 16 || l0_env == 32) ? l0_env : np_lanes;
+          k_narrowphase_group<0><<<gwide * (32 / l0), 128, 0, st>>>(d, l0);
+          static const int l1_env = getenv("EP_NP_LANES_G1") ? atoi(getenv("EP_NP_LANES_G1")) : 0;
+          const int l1 = (l1_env == 4 || l1_env == 8 || l1_env == 16 || l1_env == 32) ? l1_env : np_lanes;
+          k_narrowphase_group<1><<<gwide * g12 * (32 / l1), 128, 0, ctx->aux[0]>>>(d, l1);
           k_narrowphase_group<2><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[1]>>>(d, np_lanes);
           k_narrowphase_group<3><<<gwide * g12 * (32 / np_lanes), 128, 0, ctx->aux[2]>>>(d, np_lanes);
           CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0])); CK(cudaEventRecord(ctx->ev_join[1], ctx->aux[1])); CK(cudaEventRecord(ctx->ev_join[2], ctx->aux[2]));
