@@ -486,6 +486,8 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     TRY(dev_alloc(ctx, pool, &d.np_first, kClasses + 1)); TRY(dev_alloc(ctx, pool, &d.np_end, kClasses));
     TRY(dev_alloc(ctx, pool, &d.raw, (size_t)d.item_cap * kRawStride));
     TRY(dev_alloc(ctx, pool, &d.contact_src, (size_t)d.contact_cap));
+    TRY(dev_alloc(ctx, pool, &d.sep_hint, (size_t)d.slot_cap));
+    CK(cudaMemsetAsync(d.sep_hint, 0, (size_t)d.slot_cap * sizeof(int32_t), ctx->stream));
     TRY(dev_alloc(ctx, pool, &d.raw_cnt, d.item_cap));
   }
   TRY(dev_alloc(ctx, pool, &d.world_min_rem, nw)); TRY(dev_alloc(ctx, pool, &d.world_n_islands, nw));

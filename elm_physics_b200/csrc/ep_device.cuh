@@ -147,6 +147,7 @@ struct Dev {
   int32_t *np_first, *np_end; // [kClasses + 1] / [kClasses] item range of every class in kClassOrder order
   struct RawContact* raw;     // [item_cap][kRawStride] contacts of each item, solver order
   int32_t* raw_cnt;           // [item_cap]
+  int32_t* sep_hint;          // [slot_cap] dense (world, i<j body pair) -> separating axis of last frame (ep_kernels.cuh), 0 = none; persistent
   int2* contact_src;          // [contact_cap] (slot, raw contact index) of every contact of the frame (k_slot_counts -> k_equations)
   // solver work list: islands sorted by (size class, predicted iterations, group count), largest / longest first, so that the
   // 32 islands of a lane-per-island tile run about the same number of rows for about the same number of iterations

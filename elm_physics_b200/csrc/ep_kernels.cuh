@@ -111,13 +111,22 @@ __device__ __forceinline__ bool may_contact(const Dev& d, int w, int r0, int n, 
 // How deep the bounding spheres of a candidate pair overlap, 0 (just touching) .. kDepthBins-1: a proxy for the cost of its
 // narrowphase items (separated hulls leave the SAT at an early axis, interpenetrating ones run every axis and the
 // clipping).  Items are ordered by it inside a class so that the lanes of a warp do similar work.  Ordering only.
+// The upper half of the bins holds the pairs that had contacts LAST frame (they will most likely run the whole SAT and the
+// clipping again), the lower half the pairs that had none: those mostly leave at the axis that separated them last frame
+// (ContactSink::hint), so whole warps of them cost one axis.
 constexpr int kDepthBins = 8;
-__device__ __forceinline__ int depth_bin(const Dev& d, int r1, int r2) {
+__device__ __forceinline__ int depth_bin(const Dev& d, int w, int r1, int r2) {
   double rr = d.radius[r1] + d.radius[r2];
   double dx = d.pos[3 * r2] - d.pos[3 * r1], dy = d.pos[3 * r2 + 1] - d.pos[3 * r1 + 1], dz = d.pos[3 * r2 + 2] - d.pos[3 * r1 + 2];
   double q = 1.0 - (dx * dx + dy * dy + dz * dz) / (rr * rr);
-  int b = (int)(q * kDepthBins);
-  return b < 0 ? 0 : (b > kDepthBins - 1 ? kDepthBins - 1 : b);
+  if (d.quads) {                    // small batches: the narrowphase is the latency of its heaviest warp and the lookup only costs the broadphase
+    const int b8 = (int)(q * kDepthBins);
+    return b8 < 0 ? 0 : (b8 > kDepthBins - 1 ? kDepthBins - 1 : b8);
+  }
+  int b = (int)(q * (kDepthBins / 2));
+  b = b < 0 ? 0 : (b > kDepthBins / 2 - 1 ? kDepthBins / 2 - 1 : b);
+  const bool touched = d.prev.pair_slot[pair_index(d, w, r1, r2)] >= 0;
+  return touched ? kDepthBins / 2 + b : b;
 }
 
 // Work-item classes: shape sub-kind = convex box 0, convex other 1, plane 2, sphere 3, capsule 4, particle 5;
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(128) k_bp_count(Dev d) {
       if (may) {
         const int n1 = d.inst_off[r1 + 1] - d.inst_off[r1], n2 = d.inst_off[r2 + 1] - d.inst_off[r2];
         icnt += n1 * n2;
-        const int db = depth_bin(d, r1, r2);
+        const int db = depth_bin(d, w, r1, r2);
         for (int a = 0; a < n1; a++)
           for (int b = 0; b < n2; b++) {
             const int ka = shape_subkind(d, d.inst_off[r1] + a), kb = shape_subkind(d, d.inst_off[r2] + b);
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(128) k_bp_emit(Dev d) {
         may = may_contact(d, w, r0, n, r1, r2);
         ncon = constraints_between(d, r1, r2);
         flag = may || ncon != 0;
-        if (may) { ns2 = d.inst_off[r2 + 1] - d.inst_off[r2]; nit = (d.inst_off[r1 + 1] - d.inst_off[r1]) * ns2; dbin = depth_bin(d, r1, r2); }
+        if (may) { ns2 = d.inst_off[r2 + 1] - d.inst_off[r2]; nit = (d.inst_off[r1 + 1] - d.inst_off[r1]) * ns2; dbin = depth_bin(d, w, r1, r2); }
       }
       unsigned bal = __ballot_sync(0xffffffffu, flag);
       int iscan = nit;                                            // inclusive warp scan of the item counts
@@ -315,6 +324,23 @@ __device__ __forceinline__ ShapeRef shape_ref(const Dev& d, int inst) {
   return s;
 }
 
+// Separating-axis hints (ContactSink::hint / sep) live in a dense table over the (world, i < j body pair)s, like the warm-start
+// index: entry = shape-pair number inside the body pair << 20 | axis id + 1, 0 = none.  Persistent across frames; a pair of
+// compound bodies keeps the hint of one of its shape pairs (the others simply find none).
+__device__ __forceinline__ bool class_has_sat(int cls) { return cls == 0 || cls == 1 || cls == 7 || cls == 4 || cls == 10; }
+__device__ __forceinline__ int hint_index_and_load(const Dev& d, const int4& it, ContactSink& sink, int& kitem) {
+  const int s = it.x, r1 = d.cur.slot_row1[s], r2 = d.cur.slot_row2[s];
+  const int idx = (int)pair_index(d, d.body_world[r1], r1, r2);
+  kitem = it.w - d.cur.slot_item0[s];
+  const int h = d.sep_hint[idx];
+  sink.hint = (h != 0 && (h >> 20) == kitem) ? (h & 0xfffff) - 1 : -1;
+  return idx;
+}
+__device__ __forceinline__ void hint_store(const Dev& d, int idx, int kitem, const ContactSink& sink) {
+  if (sink.sep >= 0 && sink.sep < 0xfffff && kitem < 2048) { if (sink.sep != sink.hint) d.sep_hint[idx] = (kitem << 20) | (sink.sep + 1); }
+  else if (sink.hint >= 0) d.sep_hint[idx] = 0;       // the pair touches now (or the hint no longer separates)
+}
+
 // L = items per warp (lanes 0..L-1 work): 32 packs the warps full; a smaller L spreads the same items over more warps, which
 // cuts the serialisation of divergent lanes inside a warp -- it pays when there are fewer warps than the GPU has room for
 // (small batches: the kernel time is the latency of its heaviest warp).
@@ -333,7 +359,11 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L)
     int4 it = d.items[idx];
     ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
     bool polyOvf = false;
+    const bool sat = class_has_sat(cls);
+    int kitem = 0, hidx = 0;
+    if (sat) hidx = hint_index_and_load(d, it, sink, kitem);
     shape_pair_contacts(shape_ref(d, it.y), shape_ref(d, it.z), sink, pa, pb, polyOvf);
+    if (sat) hint_store(d, hidx, kitem, sink);
     // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
     for (int x = 0, y = sink.n - 1; x < y; x++, y--) { RawContact t = sink.buf[x]; sink.buf[x] = sink.buf[y]; sink.buf[y] = t; }
     if (sink.overflow) d.flags[FLAG_PAIR_OVERFLOW] = 2;
@@ -365,7 +395,10 @@ __global__ void __launch_bounds__(128) k_narrowphase_group(Dev d, int L) {
       int4 it = d.items[idx];
       ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
       bool polyOvf = false;
+      int kitem = 0, hidx = 0;
+      if (G != 2) hidx = hint_index_and_load(d, it, sink, kitem);
       shape_pair_contacts_group<G>(shape_ref(d, it.y), shape_ref(d, it.z), sink, pa, pb, polyOvf);
+      if (G != 2) hint_store(d, hidx, kitem, sink);
       // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
       for (int x = 0, y = sink.n - 1; x < y; x++, y--) { RawContact t = sink.buf[x]; sink.buf[x] = sink.buf[y]; sink.buf[y] = t; }
       if (sink.overflow) d.flags[FLAG_PAIR_OVERFLOW] = 2;

@@ -14,8 +14,13 @@ constexpr int kMaxPairContacts = 24;
 
 struct RawContact { int64_t fk; V3 ni, pi, pj; };
 
+// hint / sep: temporal coherence of the SAT modules (ConvexConvex, CapsuleConvex).  Every axis of the reference's axis set that
+// separates yields the same result -- no contacts -- whichever comes first, so the axis that separated this shape pair LAST frame
+// (hint, -1 = none) is tested first, with exactly the arithmetic the full walk applies to it; a pair that is still apart leaves
+// after one axis instead of walking the axis list up to its first separating one.  sep returns the axis that separated (-1: none).
+// The hint only skips work: a stale or foreign hint names some axis of the set (or none) and the verdict is the same.
 struct ContactSink {
-  RawContact* buf; int n; int cap; bool overflow;
+  RawContact* buf; int n; int cap; bool overflow; int hint = -1; int sep = -1;
   EPD void emit(bool flip, int64_t fk, V3 ni, V3 pi, V3 pj) {      // Contact.flip, Contact.elm:36-43
     if (n >= cap) { overflow = true; return; }
     RawContact c;
@@ -448,7 +453,36 @@ EPD int clip_polygon(V3 pn, double pc, const TagPt* src, int n, TagPt* dst, bool
 }
 struct SatResult { int winIdx, winSide, winK; double dmin; bool edgeBeats; V3 eAxis; int dir1, dir2; };
 // findFaceSAT 420-479 + findEdgeSAT 517-580 (threshold pre-divided by edgeBiasFactor 1.05), every axis in fp64; false = separated
-EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R) {
+// Axis ids of a hull pair (ContactSink::hint / sep): face axes 0 .. ng1 + ng2 - 1 (convex1's groups, then convex2's), edge axis
+// (a, b) = ng1 + ng2 + a * ne2 + b.  sat_axis_separates evaluates ONE axis as the walks below do: true = it separates.
+EPD bool sat_axis_separates(const Cvx& c1, const Cvx& c2, int id) {
+  double dist;
+  if (id < 0) return false;
+  if (id < c1.ng + c2.ng) {
+    const bool first = id < c1.ng;
+    const Cvx& own = first ? c1 : c2;
+    const Cvx& other = first ? c2 : c1;
+    const int k = first ? id : id - c1.ng;
+    const V3 axis = ld3(own.gf(k));
+    double omn, omx, pmn, pmx;
+    face_extent(axis, own, k, omn, omx);
+    project_convex(axis, other, pmn, pmx);
+    return !(first ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist));
+  }
+  const int e = id - c1.ng - c2.ng;
+  if (c2.ne <= 0 || e >= c1.ne * c2.ne) return false;
+  const int a = e / c2.ne, b = e - a * c2.ne;
+  int n1, n2; const int* e1 = c1.edges(a, n1); const int* e2 = c2.edges(b, n2);
+  if (n1 < 2 || n2 < 2) return false;
+  const V3 cr = vcross(vdirection(c1.vert(e1[0]), c1.vert(e1[1])), vdirection(c2.vert(e2[0]), c2.vert(e2[1])));
+  if (valmost0(cr)) return false;
+  const V3 n = vnormalize(cr);
+  double mn1, mx1, mn2, mx2;
+  project_convex(n, c1, mn1, mx1);
+  project_convex(n, c2, mn2, mx2);
+  return !overlap(mn1, mx1, mn2, mx2, dist);
+}
+EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R, int& sep) {
   // face SAT: convex1's groups then convex2's, strict improvement => first wins ties
   R.winIdx = -1; R.winSide = 1; R.winK = 0; R.dmin = kMaxNumber;
   for (int side = 1; side <= 2; side++) {
@@ -461,7 +495,7 @@ EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R) {
       face_extent(axis, own, k, omn, omx);
       project_convex(axis, other, pmn, pmx);
       bool ok = side == 1 ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist);
-      if (!ok) return false;
+      if (!ok) { sep = (side == 1 ? 0 : c1.ng) + k; return false; }
       if (dist - R.dmin < 0) { R.winIdx = nextIdx; R.winSide = side; R.winK = k; R.dmin = dist; }
       nextIdx += own.gi(k)[0] != 0 ? 2 : 1;
     }
@@ -483,7 +517,7 @@ EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R) {
       double mn1, mx1, mn2, mx2, dist;
       project_convex(n, c1, mn1, mx1);
       project_convex(n, c2, mn2, mx2);
-      if (!overlap(mn1, mx1, mn2, mx2, dist)) return false;       // EdgeSeparates
+      if (!overlap(mn1, mx1, mn2, mx2, dist)) { sep = c1.ng + c2.ng + a * c2.ne + b; return false; }       // EdgeSeparates
       if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
     }
   }
@@ -491,7 +525,7 @@ EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R) {
 }
 // The same verdict and the same winners with the axes screened in fp32 first (see above).  For two non-box hulls of at most
 // kScrVerts vertices, 32 face groups and 8 x 8 edge directions.
-EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R) {
+EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R, int& sep) {
   const V3 so = c1.pos();
   Scr s1, s2; double sD = 0;
   scr_build(s1, c1, so, sD); scr_build(s2, c2, so, sD);
@@ -545,7 +579,7 @@ EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R) {
     face_extent(axis, own, k, omn, omx);
     project_convex(axis, other, pmn, pmx);
     const bool ok = first ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist);
-    if (!ok) return false;
+    if (!ok) { sep = j; return false; }
     if (dist - R.dmin < 0) { R.winIdx = idx; R.winSide = first ? 1 : 2; R.winK = k; R.dmin = dist; }
   }
   if (R.winIdx == -1) return false;
@@ -603,7 +637,7 @@ EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R) {
     double mn1, mx1, mn2, mx2, dist;
     project_convex(n, c1, mn1, mx1);
     project_convex(n, c2, mn2, mx2);
-    if (!overlap(mn1, mx1, mn2, mx2, dist)) return false;       // EdgeSeparates
+    if (!overlap(mn1, mx1, mn2, mx2, dist)) { sep = c1.ng + c2.ng + e; return false; }       // EdgeSeparates
     if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
   }
   return true;
@@ -616,9 +650,10 @@ EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* 
   SatResult R;
   const bool screened = MAY_SCREEN && !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
                         c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
+  if (sat_axis_separates(c1, c2, out.hint)) { out.sep = out.hint; return; }      // still apart along last frame's axis
   bool hit;
-  if (MAY_SCREEN) hit = screened ? convex_sat_screened(c1, c2, R) : convex_sat(c1, c2, R);
-  else hit = convex_sat(c1, c2, R);
+  if (MAY_SCREEN) hit = screened ? convex_sat_screened(c1, c2, R, out.sep) : convex_sat(c1, c2, R, out.sep);
+  else hit = convex_sat(c1, c2, R, out.sep);
   if (!hit) return;
   const int winIdx = R.winIdx, winSide = R.winSide, winK = R.winK, dir1 = R.dir1, dir2 = R.dir2;
   const bool edgeBeats = R.edgeBeats; const V3 eAxis = R.eAxis;
@@ -749,22 +784,37 @@ EPD void capsule_convex(bool flip, const Cap& cap, const Cvx& c, ContactSink& ou
   // findSeparatingAxis 494-572: group normals, then closest-point axes of every unique edge
   // (screening these axes in fp32 like convex_sat_screened was measured SLOWER: forming an edge's axis -- closest points
   // of two segments -- costs as much as projecting the hull on it, and the two passes form every axis twice)
+  // axis ids (ContactSink::hint / sep): group normal k = k, edge (g, k) = ng + (g << 8 | k >> 1)
+  auto edge_axis = [&](const int* e, int k, V3& ax) -> bool {      // edgeAxis 575-599; false = the edge yields no axis
+    V3 v1 = c.vert(e[k]), v2 = c.vert(e[k + 1]);
+    V3 pc, pe; closest_segments(ep1, ep2, v1, v2, pc, pe);
+    V3 diff = vsub(pc, pe); double d2 = vlen2(diff);
+    if (d2 - kPrecision > 0) ax = vscale(1 / sqrt(d2), diff);
+    else { V3 cr = vcross(cap.axis, vsub(v2, v1)); if (valmost0(cr)) return false; ax = vnormalize(cr); }
+    return true;
+  };
+  if (out.hint >= 0) {       // still apart along the axis that separated last frame?
+    V3 ax; bool have = false; double dist;
+    if (out.hint < c.ng) { ax = ld3(c.gf(out.hint)); have = true; }
+    else {
+      const int h = out.hint - c.ng, g = h >> 8, k = (h & 0xff) * 2;
+      if (g < c.ne) { int ne; const int* e = c.edges(g, ne); if (k + 1 < ne) have = edge_axis(e, k, ax); }
+    }
+    if (have && !capsule_axis(cap, c, ax, dist)) { out.sep = out.hint; return; }
+  }
   V3 target = mk(0, 0, 0); double dmin = kMaxNumber;
   for (int k = 0; k < c.ng; k++) {
     V3 n = ld3(c.gf(k)); double dist;
-    if (!capsule_axis(cap, c, n, dist)) return;
+    if (!capsule_axis(cap, c, n, dist)) { out.sep = k; return; }
     if (dist - dmin < 0) { target = n; dmin = dist; }
   }
   for (int g = 0; g < c.ne; g++) {
     int ne; const int* e = c.edges(g, ne);
     for (int k = 0; k + 1 < ne; k += 2) {
-      V3 v1 = c.vert(e[k]), v2 = c.vert(e[k + 1]);
-      V3 pc, pe; closest_segments(ep1, ep2, v1, v2, pc, pe);     // edgeAxis 575-599
-      V3 diff = vsub(pc, pe); double d2 = vlen2(diff); V3 ax;
-      if (d2 - kPrecision > 0) ax = vscale(1 / sqrt(d2), diff);
-      else { V3 cr = vcross(cap.axis, vsub(v2, v1)); if (valmost0(cr)) continue; ax = vnormalize(cr); }
+      V3 ax;
+      if (!edge_axis(e, k, ax)) continue;
       double dist;
-      if (!capsule_axis(cap, c, ax, dist)) return;
+      if (!capsule_axis(cap, c, ax, dist)) { if (g < (1 << 20) && k < 512) out.sep = c.ng + (g << 8 | k >> 1); return; }
       if (dist - dmin < 0) { target = ax; dmin = dist; }
     }
   }
