@@ -709,10 +709,26 @@ __device__ __forceinline__ void gather_contact(const Dev& d, int out, ContactRec
   const int ps = d.prev.pair_slot[pair_index(d, w, r1, r2)];
   if (ps >= 0) {
     const int pc0 = d.prev.slot_cstart[ps], pcn = d.prev.slot_ccount[ps];
-    for (int m = pcn - 1; m >= 0; m--) {
-      const ContactRec& p = d.prev.contacts[pc0 + m];
-      if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { lam = p.lam; ct1 = mk(p.t1[0], p.t1[1], p.t1[2]); break; }
+    // the keys of the last (up to) 8 cached contacts in one batch of independent loads (a loop with an early exit serialises one
+    // L2 round trip per candidate), then the match in registers; longer groups continue with the loop
+    int hit = -1;
+    {
+      int64_t fk8[8]; int sk8[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int m = pcn - 1 - j;
+        const ContactRec& p = d.prev.contacts[pc0 + (m >= 0 ? m : 0)];
+        fk8[j] = p.fk; sk8[j] = p.sk;
+      }
+#pragma unroll
+      for (int j = 7; j >= 0; j--) if (pcn - 1 - j >= 0 && (fk8[j] - rc.fk == 0) && (sk8[j] - sk == 0)) hit = pcn - 1 - j;      // ends with the LARGEST matching m
     }
+    if (hit < 0)
+      for (int m = pcn - 9; m >= 0; m--) {
+        const ContactRec& p = d.prev.contacts[pc0 + m];
+        if ((p.fk - rc.fk == 0) && (p.sk - sk == 0)) { hit = m; break; }
+      }
+    if (hit >= 0) { const ContactRec& p = d.prev.contacts[pc0 + hit]; lam = p.lam; ct1 = mk(p.t1[0], p.t1[1], p.t1[2]); }
   }
 }
 // k_equations: one thread per contact (contactEquations), rows to the per-contact records (RowRec / QRow)
