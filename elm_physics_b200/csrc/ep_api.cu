@@ -678,18 +678,31 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         for (int c = 0; c < kClasses; c++) {
           cudaEvent_t a = next_event(ctx), b = next_event(ctx);
           cudaEventRecord(a, st);
-          k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, c, np_lanes);
+          k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, c, np_lanes, 0ull);
           cudaEventRecord(b, st);
           ctx->np_pending.push_back({c, a, b});
         }
       } else
       {
         // large batches: one kernel per module group (8192 worlds: 1.00 -> 0.84 ms); small batches: the single kernel (equal within noise)
-        static const int np_split_env = getenv("EP_NP_SPLIT") ? atoi(getenv("EP_NP_SPLIT")) : -1;
-        const int np_split = np_split_env >= 0 ? np_split_env : (d.quads ? 0 : 1);
+        // EP_NP_MODE: 0 one kernel for every class, 1 one kernel per module group side by side, 2 a quad of lanes per item for the SAT
+        // classes (hull-hull, capsule-hull) beside one kernel for the rest.  Measured on B200 (C3): mode 2 wins up to 4096 worlds per
+        // GPU (k_narrowphase 0.57 -> 0.44 ms at 4096, 0.27 -> 0.245 at 1024), mode 1 at 8192 (0.74 against 0.78)
+        static const int np_mode_env = getenv("EP_NP_MODE") ? atoi(getenv("EP_NP_MODE")) : -1;
+        const int np_mode = (np_mode_env >= 0 && np_mode_env <= 2) ? np_mode_env : (d.n_bodies <= 200000 ? 2 : 1);
+        const int np_split = np_mode == 1;
+        const bool np_quad = np_mode == 2;
         static const int g12 = getenv("EP_NP_GRID12") ? atoi(getenv("EP_NP_GRID12")) : 1;
         Timed t(ctx, EP_K_NARROWPHASE);
-        if (!np_split) k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes);
+        if (np_quad) {
+          CK(cudaEventRecord(ctx->ev_fork, st));
+          CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+          k_narrowphase_quad<<<gwide * 2, 128, 0, ctx->aux[0]>>>(d);
+          k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes, kQuadClasses);
+          CK(cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
+          CK(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+          ctx->launches += 1;
+        } else if (!np_split) k_narrowphase<<<gwide * (32 / np_lanes), 128, 0, st>>>(d, -1, np_lanes, 0ull);
         else {      // one kernel per module group, side by side: hull-hull on the main stream, capsule-hull and the rest beside it
           CK(cudaEventRecord(ctx->ev_fork, st));
           CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(ctx->aux[2], ctx->ev_fork, 0));

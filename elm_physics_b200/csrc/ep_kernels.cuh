@@ -344,7 +344,7 @@ __device__ __forceinline__ void hint_store(const Dev& d, int idx, int kitem, con
 // L = items per warp (lanes 0..L-1 work): 32 packs the warps full; a smaller L spreads the same items over more warps, which
 // cuts the serialisation of divergent lanes inside a warp -- it pays when there are fewer warps than the GPU has room for
 // (small batches: the kernel time is the latency of its heaviest warp).
-__global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L) {
+__global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L, unsigned long long skip_mask) {
   TagPt pa[kMaxPoly], pb[kMaxPoly];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128) k_narrowphase(Dev d, int only_cls, int L)
     while (ci + 1 < kClasses && chunk * L >= d.np_first[ci + 1]) ci++;
     const int cls = kClassOrder[ci];
     const int idx = chunk * L + lane;
-    if (lane >= L || idx >= d.np_end[ci] || (only_cls >= 0 && cls != only_cls)) continue;
+    if (lane >= L || idx >= d.np_end[ci] || (only_cls >= 0 && cls != only_cls) || ((skip_mask >> cls) & 1ull)) continue;
     int4 it = d.items[idx];
     ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
     bool polyOvf = false;
@@ -406,6 +406,47 @@ __global__ void __launch_bounds__(128) k_narrowphase_group(Dev d, int L) {
       d.raw_cnt[it.w] = sink.n;
     }
     chunk0 += nch;
+  }
+}
+
+// Classes 7 (hull-hull without boxes), 10 and 4 (capsule against a hull / a box) with a QUAD of lanes per item (convex_convex_quad,
+// capsule_convex_quad, ep_narrowphase.cuh): 8 items per warp.  For small batches, where the kernel time is the latency of the
+// heaviest warp; beside k_narrowphase(skip_mask = kQuadClasses).
+constexpr unsigned long long kQuadClasses = (1ull << 7) | (1ull << 10) | (1ull << 4);
+__global__ void __launch_bounds__(128) k_narrowphase_quad(Dev d) {
+  TagPt pa[kMaxPoly], pb[kMaxPoly];
+  const int lane = threadIdx.x & 31, q = lane & 3, sub = lane >> 2;
+  const unsigned qm = 0xFu << (lane & ~3);
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (d.flags[FLAG_PAIR_OVERFLOW]) return;
+  int chunk0 = 0;                 // chunks of the quad classes in front of class position ci: the classes' chunks are dealt on over the warps
+  for (int ci = 0; ci < kClasses; ci++) {
+    if (!((kQuadClasses >> kClassOrder[ci]) & 1ull)) continue;
+    const int first = d.np_first[ci], end = d.np_end[ci], nch = (end - first + 7) / 8;
+    int c = (warp - chunk0 % nwarps + nwarps) % nwarps;
+    chunk0 += nch;
+    for (; c < nch; c += nwarps) {
+      const int idx = first + c * 8 + sub;
+      if (idx >= end) continue;                      // the four lanes of a quad together
+      int4 it = d.items[idx];
+      ContactSink sink; sink.buf = d.raw + (size_t)it.w * kRawStride; sink.n = 0; sink.cap = kRawStride; sink.overflow = false;
+      bool polyOvf = false;
+      int kitem = 0;
+      const int hidx = hint_index_and_load(d, it, sink, kitem);
+      sink.hint = __shfl_sync(qm, sink.hint, lane & ~3);          // one value for the quad (the table may change under it)
+      const ShapeRef a = shape_ref(d, it.y), b = shape_ref(d, it.z);
+      if (a.kind == SH_CONVEX && b.kind == SH_CONVEX) convex_convex_quad(make_cvx(a.f, a.ib), make_cvx(b.f, b.ib), sink, pa, pb, polyOvf, q, qm);
+      else if (a.kind == SH_CONVEX && b.kind == SH_CAPSULE) capsule_convex_quad(true, as_capsule(b), make_cvx(a.f, a.ib), sink, q, qm);
+      else if (a.kind == SH_CAPSULE && b.kind == SH_CONVEX) capsule_convex_quad(false, as_capsule(a), make_cvx(b.f, b.ib), sink, q, qm);
+      if (q == 0) {
+        // solver order = reverse emission inside a shape pair (Equation.elm:135-154)
+        for (int x = 0, y = sink.n - 1; x < y; x++, y--) { RawContact t = sink.buf[x]; sink.buf[x] = sink.buf[y]; sink.buf[y] = t; }
+        if (sink.overflow) d.flags[FLAG_PAIR_OVERFLOW] = 2;
+        if (polyOvf) d.flags[FLAG_POLY_OVERFLOW] = 1;
+        d.raw_cnt[it.w] = sink.n;
+        hint_store(d, hidx, kitem, sink);
+      }
+    }
   }
 }
 

@@ -642,19 +642,8 @@ EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R, int& se
   }
   return true;
 }
-// addContacts 40-63 with dispatchBestFaces 69-114, clipTwoFaces 204-269
-// MAY_SCREEN false: an instance for pairs with a box on either side (never screened): it carries neither the fp32 copies nor
-// the screening code
-template <bool MAY_SCREEN>
-EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
-  SatResult R;
-  const bool screened = MAY_SCREEN && !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
-                        c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
-  if (sat_axis_separates(c1, c2, out.hint)) { out.sep = out.hint; return; }      // still apart along last frame's axis
-  bool hit;
-  if (MAY_SCREEN) hit = screened ? convex_sat_screened(c1, c2, R, out.sep) : convex_sat(c1, c2, R, out.sep);
-  else hit = convex_sat(c1, c2, R, out.sep);
-  if (!hit) return;
+// the contacts of a hull pair from the SAT's winners: addEdgeContact 148-169, dispatchBestFaces 69-114, clipTwoFaces 204-269
+EPD void convex_contacts_from_sat(const Cvx& c1, const Cvx& c2, const SatResult& R, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
   const int winIdx = R.winIdx, winSide = R.winSide, winK = R.winK, dir1 = R.dir1, dir2 = R.dir2;
   const bool edgeBeats = R.edgeBeats; const V3 eAxis = R.eAxis;
   if (edgeBeats) {   // addEdgeContact 148-169
@@ -704,7 +693,224 @@ EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* 
     out.emit(false, feat(1, id1, id2, src[i].tag, 0), rev, mk(v.x - depth * f1.n.x, v.y - depth * f1.n.y, v.z - depth * f1.n.z), v);
   }
 }
+// addContacts 40-63 with dispatchBestFaces 69-114, clipTwoFaces 204-269
+// MAY_SCREEN false: an instance for pairs with a box on either side (never screened): it carries neither the fp32 copies nor
+// the screening code
+template <bool MAY_SCREEN>
+EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
+  SatResult R;
+  const bool screened = MAY_SCREEN && !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
+                        c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
+  if (sat_axis_separates(c1, c2, out.hint)) { out.sep = out.hint; return; }      // still apart along last frame's axis
+  bool hit;
+  if (MAY_SCREEN) hit = screened ? convex_sat_screened(c1, c2, R, out.sep) : convex_sat(c1, c2, R, out.sep);
+  else hit = convex_sat(c1, c2, R, out.sep);
+  if (!hit) return;
+  convex_contacts_from_sat(c1, c2, R, out, pa, pb, polyOverflow);
+}
 EPD void convex_convex(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) { convex_convex_t<true>(c1, c2, out, pa, pb, polyOverflow); }
+
+// ---- the screened hull-hull SAT by a QUAD of lanes ---------------------------------------------------------------------------
+// Small batches: the narrowphase is the latency of its heaviest warp -- 16 touching 12-gon cylinder pairs, one per lane, ~0.25 ms.
+// Here four lanes (q = lane & 3, all holding the same item) share one pair:
+//   pass 1 (fp32 screen): the axis pairs are dealt round-robin over the four lanes; every lane keeps its estimates, the threshold
+//          is the minimum over the quad (any upper bound of the smallest true overlap is a valid threshold, see above) and the
+//          survivor masks are OR-ed -- the survivors are a superset of the axes that can matter, as in the one-lane walk;
+//   pass 2 (exact): the survivors in the reference's order, one at a time, each projection split over the four lanes by vertex
+//          (min / max are exact and order-independent, so every lane ends with the very value the one-lane loop computes) and
+//          the overlap / winner logic run identically by all four;
+//   the winners go to lane 0, which forms the contacts (clipping stays serial).
+EPD double quad_min(double v, unsigned qm) {
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) { const double a = __shfl_xor_sync(qm, v, o); v = (v - a > 0) ? a : v; }
+  return v;
+}
+EPD double quad_max(double v, unsigned qm) {
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) { const double a = __shfl_xor_sync(qm, v, o); v = (v - a > 0) ? v : a; }
+  return v;
+}
+// projectConvex 596-610 of a non-box hull, vertices dealt over the quad
+EPD void project_convex_quad(V3 axis, const Cvx& c, int q, unsigned qm, double& mn, double& mx) {
+  mn = kMaxNumber; mx = -kMaxNumber;
+  for (int i = c.nv - 1 - q; i >= 0; i -= 4) {
+    V3 v = c.vert(i);
+    double val = v.x * axis.x + v.y * axis.y + v.z * axis.z;
+    mn = (mn - val > 0) ? val : mn;
+    mx = (mx - val > 0) ? mx : val;
+  }
+  mn = quad_min(mn, qm); mx = quad_max(mx, qm);
+}
+// sat_axis_separates for two non-box hulls, by the quad (the same verdict in all four lanes)
+EPD bool sat_axis_separates_quad(const Cvx& c1, const Cvx& c2, int id, int q, unsigned qm) {
+  double dist;
+  if (id < 0) return false;
+  if (id < c1.ng + c2.ng) {
+    const bool first = id < c1.ng;
+    const Cvx& own = first ? c1 : c2;
+    const Cvx& other = first ? c2 : c1;
+    const int k = first ? id : id - c1.ng;
+    const V3 axis = ld3(own.gf(k));
+    double omn, omx, pmn, pmx;
+    face_extent(axis, own, k, omn, omx);
+    project_convex_quad(axis, other, q, qm, pmn, pmx);
+    return !(first ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist));
+  }
+  const int e = id - c1.ng - c2.ng;
+  if (c2.ne <= 0 || e >= c1.ne * c2.ne) return false;
+  const int a = e / c2.ne, b = e - a * c2.ne;
+  int n1, n2; const int* e1 = c1.edges(a, n1); const int* e2 = c2.edges(b, n2);
+  if (n1 < 2 || n2 < 2) return false;
+  const V3 cr = vcross(vdirection(c1.vert(e1[0]), c1.vert(e1[1])), vdirection(c2.vert(e2[0]), c2.vert(e2[1])));
+  if (valmost0(cr)) return false;
+  const V3 n = vnormalize(cr);
+  double mn1, mx1, mn2, mx2;
+  project_convex_quad(n, c1, q, qm, mn1, mx1);
+  project_convex_quad(n, c2, q, qm, mn2, mx2);
+  return !overlap(mn1, mx1, mn2, mx2, dist);
+}
+EPD bool convex_sat_screened_quad(const Cvx& c1, const Cvx& c2, SatResult& R, int& sep, int q, unsigned qm) {
+  const V3 so = c1.pos();
+  Scr s1, s2; double sD = 0;
+  scr_build(s1, c1, so, sD); scr_build(s2, c2, so, sD);      // every lane its own copy (local memory)
+  const double sE = kScrE * sD + 1.0e-15 * (eabs(so.x) + eabs(so.y) + eabs(so.z)) + 1.0e-12;
+  // ---- face axes, pass 1: pairs of axes of one hull, pair p to lane p & 3
+  unsigned fmask = 0;
+  {
+    double estv[10]; int jv[10]; int cnt = 0; double thr = kMaxNumber;
+    auto face_est = [&](const Cvx& own, int k, V3 axis, float lo, float hi) -> double {
+      double omn, omx;
+      face_extent(axis, own, k, omn, omx);
+      const double on = vdot(axis, so);
+      const double a = omx - ((double)lo + on), b = ((double)hi + on) - omn;
+      return (a - b > 0) ? b : a;
+    };
+    auto keep = [&](int j, double est) {
+      if (cnt < 10) { estv[cnt] = est; jv[cnt] = j; cnt++; } else fmask |= 1u << j;      // cannot overflow (<= 17 pairs); survive rather than drop
+      if (est + sE < thr) thr = est + sE;
+    };
+    int pairNo = 0;
+    for (int side = 0; side < 2; side++) {
+      const Cvx& own = side == 0 ? c1 : c2;
+      const Scr& other = side == 0 ? s2 : s1;
+      const int j0 = side == 0 ? 0 : c1.ng;
+      for (int k = 0; k < own.ng; k += 2, pairNo++) {
+        if ((pairNo & 3) != q) continue;
+        const V3 xa = ld3(own.gf(k));
+        if (k + 1 < own.ng) {
+          const V3 xb = ld3(own.gf(k + 1));
+          float loa, hia, lob, hib; scr_project2(other, xa, xb, loa, hia, lob, hib);
+          keep(j0 + k, face_est(own, k, xa, loa, hia));
+          keep(j0 + k + 1, face_est(own, k + 1, xb, lob, hib));
+        } else {
+          float lo, hi; scr_project(other, xa, lo, hi);
+          keep(j0 + k, face_est(own, k, xa, lo, hi));
+        }
+      }
+    }
+    thr = quad_min(thr, qm);
+    for (int i = 0; i < cnt; i++) if (!(estv[i] - sE > thr)) fmask |= 1u << jv[i];
+    fmask |= __shfl_xor_sync(qm, fmask, 1); fmask |= __shfl_xor_sync(qm, fmask, 2);
+  }
+  // ---- face axes, pass 2: the survivors in fp64, ascending j = the reference's order
+  R.winIdx = -1; R.winSide = 1; R.winK = 0; R.dmin = kMaxNumber;
+  while (fmask) {
+    const int j = __ffs(fmask) - 1; fmask &= fmask - 1;
+    const bool first = j < c1.ng;
+    const Cvx& own = first ? c1 : c2;
+    const Cvx& other = first ? c2 : c1;
+    const int k = first ? j : j - c1.ng;
+    int idx = 1;
+    for (int x = 0; x < k; x++) idx += own.gi(x)[0] != 0 ? 2 : 1;
+    const V3 axis = ld3(own.gf(k));
+    double omn, omx, pmn, pmx, dist;
+    face_extent(axis, own, k, omn, omx);
+    project_convex_quad(axis, other, q, qm, pmn, pmx);
+    const bool ok = first ? overlap(omn, omx, pmn, pmx, dist) : overlap(pmn, pmx, omn, omx, dist);
+    if (!ok) { sep = j; return false; }
+    if (dist - R.dmin < 0) { R.winIdx = idx; R.winSide = first ? 1 : 2; R.winK = k; R.dmin = dist; }
+  }
+  if (R.winIdx == -1) return false;
+  // ---- edge axes, pass 1: axis e = a * ne2 + b, pairs (2p, 2p + 1) to lane p & 3
+  R.edgeBeats = false; R.eAxis = mk(0, 0, 0); R.dir1 = 0; R.dir2 = 0;
+  double emin_ = R.dmin / 1.05;
+  double d1s[3 * 8], d2s[3 * 8]; unsigned ok1 = 0, ok2 = 0;
+  for (int a = 0; a < c1.ne; a++) {
+    int n1; const int* e1 = c1.edges(a, n1);
+    if (n1 < 2) continue;
+    const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
+    d1s[3 * a] = d1.x; d1s[3 * a + 1] = d1.y; d1s[3 * a + 2] = d1.z; ok1 |= 1u << a;
+  }
+  for (int b = 0; b < c2.ne; b++) {
+    int n2; const int* e2 = c2.edges(b, n2);
+    if (n2 < 2) continue;
+    const V3 d2 = vdirection(c2.vert(e2[0]), c2.vert(e2[1]));
+    d2s[3 * b] = d2.x; d2s[3 * b + 1] = d2.y; d2s[3 * b + 2] = d2.z; ok2 |= 1u << b;
+  }
+  unsigned long long emask = 0;
+  {
+    double estv[16]; int ev[16]; int cnt = 0; double thr = emin_;
+    auto edge_est = [&](float lo1, float hi1, float lo2, float hi2) -> double {
+      const double x = (double)hi1 - (double)lo2, y = (double)hi2 - (double)lo1;
+      return (x - y > 0) ? y : x;
+    };
+    auto keep = [&](int e, double est) {
+      if (cnt < 16) { estv[cnt] = est; ev[cnt] = e; cnt++; } else emask |= 1ull << e;     // cannot overflow (<= 32 pairs)
+      if (est + 2 * sE < thr) thr = est + 2 * sE;
+    };
+    auto axis_of = [&](int e, V3& n) -> bool {
+      const int a = e / c2.ne, b = e - a * c2.ne;
+      if (!((ok1 >> a) & 1u) || !((ok2 >> b) & 1u)) return false;
+      const V3 cr = vcross(mk(d1s[3 * a], d1s[3 * a + 1], d1s[3 * a + 2]), mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2]));
+      if (valmost0(cr)) return false;
+      n = vnormalize(cr);
+      return true;
+    };
+    const int ne = c1.ne * c2.ne;
+    for (int e0 = 2 * q; e0 < ne; e0 += 8) {
+      V3 na = mk(0, 0, 0), nb = mk(0, 0, 0);
+      const bool va = axis_of(e0, na), vb = e0 + 1 < ne && axis_of(e0 + 1, nb);
+      if (va && vb) {
+        float l1a, h1a, l1b, h1b, l2a, h2a, l2b, h2b;
+        scr_project2(s1, na, nb, l1a, h1a, l1b, h1b); scr_project2(s2, na, nb, l2a, h2a, l2b, h2b);
+        keep(e0, edge_est(l1a, h1a, l2a, h2a));
+        keep(e0 + 1, edge_est(l1b, h1b, l2b, h2b));
+      } else if (va || vb) {
+        const V3 n = va ? na : nb;
+        float lo1, hi1, lo2, hi2; scr_project(s1, n, lo1, hi1); scr_project(s2, n, lo2, hi2);
+        keep(va ? e0 : e0 + 1, edge_est(lo1, hi1, lo2, hi2));
+      }
+    }
+    thr = quad_min(thr, qm);
+    for (int i = 0; i < cnt; i++) if (!(estv[i] - 2 * sE > thr)) emask |= 1ull << ev[i];
+    unsigned lo = (unsigned)emask, hi = (unsigned)(emask >> 32);
+    lo |= __shfl_xor_sync(qm, lo, 1); lo |= __shfl_xor_sync(qm, lo, 2);
+    hi |= __shfl_xor_sync(qm, hi, 1); hi |= __shfl_xor_sync(qm, hi, 2);
+    emask = ((unsigned long long)hi << 32) | lo;
+  }
+  // ---- edge axes, pass 2
+  while (emask) {
+    const int e = __ffsll((long long)emask) - 1; emask &= emask - 1;
+    const int a = e / c2.ne, b = e - a * c2.ne;
+    const V3 n = vnormalize(vcross(mk(d1s[3 * a], d1s[3 * a + 1], d1s[3 * a + 2]), mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2])));
+    double mn1, mx1, mn2, mx2, dist;
+    project_convex_quad(n, c1, q, qm, mn1, mx1);
+    project_convex_quad(n, c2, q, qm, mn2, mx2);
+    if (!overlap(mn1, mx1, mn2, mx2, dist)) { sep = c1.ng + c2.ng + e; return false; }       // EdgeSeparates
+    if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
+  }
+  return true;
+}
+// one hull pair by the four lanes of a quad; `out` of lane 0 receives the contacts, hint must be the same in all four lanes
+EPD void convex_convex_quad(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow, int q, unsigned qm) {
+  const bool screened = !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
+                        c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
+  if (!screened) { if (q == 0) convex_convex_t<true>(c1, c2, out, pa, pb, polyOverflow); return; }      // the one-lane path
+  if (sat_axis_separates_quad(c1, c2, out.hint, q, qm)) { out.sep = out.hint; return; }
+  SatResult R;
+  if (!convex_sat_screened_quad(c1, c2, R, out.sep, q, qm)) return;
+  if (q == 0) convex_contacts_from_sat(c1, c2, R, out, pa, pb, polyOverflow);
+}
 
 // ---- CapsuleConvex.elm ----------------------------------------------------------------------------
 // testCapsuleConvexAxis 718-749
@@ -777,6 +983,7 @@ EPD void cap_body_contacts(bool flip, int cf, const Cvx& c, bool haveFace, const
     cap_direct(flip, feat(6, k == 0 ? 3 : 4, cf, 0, 0), pt, sep, pen, cap, out);
   }
 }
+EPD void capsule_convex_tail(bool flip, const Cap& cap, const Cvx& c, V3 ep1, V3 ep2, V3 target, ContactSink& out);
 // addContacts 58-190
 EPD void capsule_convex(bool flip, const Cap& cap, const Cvx& c, ContactSink& out) {
   V3 ep1 = mk(cap.pos.x - cap.h * cap.axis.x, cap.pos.y - cap.h * cap.axis.y, cap.pos.z - cap.h * cap.axis.z);
@@ -818,6 +1025,10 @@ EPD void capsule_convex(bool flip, const Cap& cap, const Cvx& c, ContactSink& ou
       if (dist - dmin < 0) { target = ax; dmin = dist; }
     }
   }
+  capsule_convex_tail(flip, cap, c, ep1, ep2, target, out);
+}
+// addContacts 58-190 behind findSeparatingAxis: the contacts along `target`
+EPD void capsule_convex_tail(bool flip, const Cap& cap, const Cvx& c, V3 ep1, V3 ep2, V3 target, ContactSink& out) {
   V3 sep = vdot(vsub(c.pos(), cap.pos), target) > 0 ? vneg(target) : target;
   double pen;
   if (!capsule_axis(cap, c, sep, pen)) return;
@@ -872,6 +1083,70 @@ EPD void capsule_convex(bool flip, const Cap& cap, const Cvx& c, ContactSink& ou
     V3 pc, pe; closest_segments(ep1, ep2, s1, s1, pc, pe);
     cap_direct(flip, feat(6, 5, cf, 0, 0), pc, sep, pen, cap, out);
   }
+}
+
+// ---- CapsuleConvex by a QUAD of lanes: the axes of findSeparatingAxis dealt round-robin over the four lanes -------------------
+// Axis t of the reference's walk (group normals, then every (edge group, edge) in order, t counting the edges that yield no axis
+// as well) goes to lane t & 3, which evaluates it exactly as the one-lane walk does.  A separating axis found by any lane ends the
+// pair (every separating axis means "no contacts"); otherwise the target is the axis of smallest depth, the FIRST one among equals
+// (the walk replaces on strict improvement only) = the lexicographic minimum of (depth, t) over the quad.  Lane 0 then forms the
+// contacts.  hint must be the same in all four lanes.
+EPD void capsule_convex_quad(bool flip, const Cap& cap, const Cvx& c, ContactSink& out, int q, unsigned qm) {
+  V3 ep1 = mk(cap.pos.x - cap.h * cap.axis.x, cap.pos.y - cap.h * cap.axis.y, cap.pos.z - cap.h * cap.axis.z);
+  V3 ep2 = mk(cap.pos.x + cap.h * cap.axis.x, cap.pos.y + cap.h * cap.axis.y, cap.pos.z + cap.h * cap.axis.z);
+  auto edge_axis = [&](const int* e, int k, V3& ax) -> bool {      // edgeAxis 575-599; false = the edge yields no axis
+    V3 v1 = c.vert(e[k]), v2 = c.vert(e[k + 1]);
+    V3 pc, pe; closest_segments(ep1, ep2, v1, v2, pc, pe);
+    V3 diff = vsub(pc, pe); double d2 = vlen2(diff);
+    if (d2 - kPrecision > 0) ax = vscale(1 / sqrt(d2), diff);
+    else { V3 cr = vcross(cap.axis, vsub(v2, v1)); if (valmost0(cr)) return false; ax = vnormalize(cr); }
+    return true;
+  };
+  if (out.hint >= 0) {       // still apart along the axis that separated last frame?  (one lane's work, done by all four alike)
+    V3 ax; bool have = false; double dist;
+    if (out.hint < c.ng) { ax = ld3(c.gf(out.hint)); have = true; }
+    else {
+      const int h = out.hint - c.ng, g = h >> 8, k = (h & 0xff) * 2;
+      if (g < c.ne) { int ne; const int* e = c.edges(g, ne); if (k + 1 < ne) have = edge_axis(e, k, ax); }
+    }
+    if (have && !capsule_axis(cap, c, ax, dist)) { out.sep = out.hint; return; }
+  }
+  V3 target = mk(0, 0, 0); double dmin = kMaxNumber; int tmin = 0x7fffffff;
+  int nedges = 0;
+  for (int g = 0; g < c.ne; g++) { int ne; c.edges(g, ne); nedges += ne >> 1; }
+  const int total = c.ng + nedges;
+  // rounds of four axes, one per lane, and a vote after each: the pair ends at the first round that holds a separating axis
+  // (the one-lane walk stops at its first separating axis; without the vote the other three lanes would walk on to the end)
+  for (int t0 = 0; t0 < total; t0 += 4) {
+    const int t = t0 + q;
+    int sepId = -1;
+    if (t < total) {
+      V3 ax; bool have = true; int id = t;
+      if (t < c.ng) ax = ld3(c.gf(t));
+      else {
+        int te = t - c.ng, g = 0, ne = 0; const int* e = c.edges(0, ne);
+        while (te >= (ne >> 1)) { te -= ne >> 1; g++; e = c.edges(g, ne); }
+        have = edge_axis(e, 2 * te, ax);
+        id = (g < (1 << 20) && te < 256) ? c.ng + (g << 8 | te) : 0x7ffffffe;
+      }
+      if (have) {
+        double dist;
+        if (!capsule_axis(cap, c, ax, dist)) sepId = id;
+        else if (dist - dmin < 0) { target = ax; dmin = dist; tmin = t; }
+      }
+    }
+    unsigned sid = sepId < 0 ? 0xffffffffu : (unsigned)sepId;
+    sid = min(sid, __shfl_xor_sync(qm, sid, 1)); sid = min(sid, __shfl_xor_sync(qm, sid, 2));
+    if (sid != 0xffffffffu) { if (sid < 0x7ffffffeu) out.sep = (int)sid; return; }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {      // lexicographic minimum of (depth, t)
+    const double od = __shfl_xor_sync(qm, dmin, o); const int ot = __shfl_xor_sync(qm, tmin, o);
+    const double ox = __shfl_xor_sync(qm, target.x, o), oy = __shfl_xor_sync(qm, target.y, o), oz = __shfl_xor_sync(qm, target.z, o);
+    const bool take = (od - dmin < 0) || (!(dmin - od < 0) && ot < tmin);
+    if (take) { dmin = od; tmin = ot; target = mk(ox, oy, oz); }
+  }
+  if (q == 0) capsule_convex_tail(flip, cap, c, ep1, ep2, target, out);
 }
 
 // ---- NarrowPhase.elm:86-286 : one (shape1, shape2) cell of the 5x5 matrix ---------------------------
