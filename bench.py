@@ -58,8 +58,8 @@ def kernel_bytes(name, c):
         "k_solve": K * 488 + nd * 56,
         # 512 B per body-step (336 read + 176 written)
         "k_integrate": nb * 512,
-        # round 1's stand-alone tile build (gone: the solver's warps build their own tiles); the slot stays in the ABI's kernel list
-        "k_tile_build": 0,
+        # giant islands on a thread-block cluster (inside k_solve's bracket; its bytes are counted there)
+        "k_solve_cluster": 0,
     }
     return table[name]
 

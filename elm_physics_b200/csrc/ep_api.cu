@@ -17,6 +17,7 @@
 #include "ep_kernels.cuh"
 #include "ep_solve.cuh"
 #include "ep_solve_quads.cuh"
+#include "ep_solve_cluster.cuh"
 #include "ep_output.cuh"
 #include "ep_raycast.cuh"
 
@@ -52,6 +53,7 @@ struct ep_ctx {
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
   int lanes_grid = 0;
   size_t team_smem_max = 48 * 1024;
+  int cluster_nc = 0, cluster_ws = 32, cluster_count = 1, solo_bodies = 1024, cluster_bodies = 512;      // k_solve_cluster: CTAs per cluster (0 = unavailable), window slots per warp, clusters per launch, body table of the SOLO launch
   // quad solver (small batches): launches of k_solve_quads -- classes [lo, hi] with kq islands per warp, shared memory sized
   // for class hi (ep_solve_quads.cuh) -- and the largest batch (bodies) that takes this family (EP_SOLVER=lanes|quads overrides)
   struct QuadLaunch { int lo, hi, kq, cap_rows, cap_bodies, cap_groups; size_t smem; int resident; };
@@ -199,6 +201,31 @@ extern "C" int ep_create(ep_ctx** out, int device) {
     ok = ok && cudaFuncSetAttribute(k_solve_qteam<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_solve_qteam<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_solve_qteam<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+  }
+  // Giant islands (class 9) run on k_solve_cluster (ep_solve_cluster.cuh): SOLO (one CTA, bodies in shared memory) for islands of
+  // <= 1024 pair groups, else a thread-block cluster -- the largest this device co-schedules with the kernel's shared memory,
+  // 16 (non-portable size) or 8 CTAs.  EP_CLUSTER=0 keeps them on k_solve_team<256>; EP_CLUSTER=n forces n; EP_SOLO=0: no SOLO launch.
+  if (ok) {
+    const char* ce = getenv("EP_CLUSTER");
+    const int want = ce ? atoi(ce) : 16;
+    if (getenv("EP_CLUSTER_WS")) ctx->cluster_ws = std::max(0, std::min(32, atoi(getenv("EP_CLUSTER_WS"))));
+    if (getenv("EP_SOLO") && atoi(getenv("EP_SOLO")) == 0) ctx->solo_bodies = 0;
+    const size_t sm = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->cluster_bodies), sm_solo = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->solo_bodies);
+    if (want > 0 && sm_solo <= ctx->team_smem_max &&
+        cudaFuncSetAttribute(k_solve_cluster<kClusterWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&
+        cudaFuncSetAttribute(k_solve_cluster<kClusterWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solo) == cudaSuccess) {
+      cudaFuncSetAttribute(k_solve_cluster<kClusterWarps, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      for (int nc = std::min(want, 16); nc >= 1 && ctx->cluster_nc == 0; nc >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nc); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = sm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_solve_cluster<kClusterWarps, false>, &cfg) == cudaSuccess && ncl >= 1) { ctx->cluster_nc = nc; ctx->cluster_count = std::min(ncl, 4); }
+      }
+      cudaGetLastError();       // a size the device refuses is not an error of the context
+    }
   }
   if (!ok) { ep_destroy(ctx); return EP_ENODEVICE; }
   *out = ctx;
@@ -638,7 +665,7 @@ extern "C" int ep_kernel_times(ep_ctx* ctx, double* ms, int64_t* launches, int32
   return EP_OK;
 }
 extern "C" const char* ep_kernel_name(int32_t k) {
-  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate", "k_tile_build",
+  static const char* names[EP_K_COUNT] = {"k_place", "k_sort", "k_broadphase", "k_narrowphase", "k_equations", "k_islands", "k_solve", "k_integrate", "k_solve_cluster",
                                           "k_solve_lanes_b0", "k_solve_lanes_b1", "k_solve_lanes_b2", "k_solve_lanes_b3", "k_solve_lanes_b4", "k_solve_lanes_b5", "k_solve_lanes_inplace", "k_solve_team_warp", "k_solve_team_cta"};
   return (k >= 0 && k < EP_K_COUNT) ? names[k] : "";
 }
@@ -802,11 +829,28 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         const size_t body_b = (size_t)((d.nb_max + 1) & ~1) * 4 + (size_t)d.nb_max * 56;
         const bool smemb = body_b + 3 * 8 * 256 * 4 <= std::min<size_t>(200 * 1024, ctx->team_smem_max);
         const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
+        // giant islands (class 9) on a thread-block cluster, first: it is the longest chain of the step
+        const int team_hi = ctx->cluster_nc > 0 ? kBins - 2 : kBins - 1;
+        if (ctx->cluster_nc > 0) {
+          TRY(side(EP_K_SOLVE_CLUSTER, [&](cudaStream_t sx) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ctx->cluster_nc * ctx->cluster_count); cfg.blockDim = dim3(kClusterThreads);
+            cfg.dynamicSmemBytes = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->cluster_bodies); cfg.stream = sx;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = ctx->cluster_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_solve_cluster<kClusterWarps, false>, d, kBins - 1, kBins - 1, force_resum, ctx->cluster_ws, ctx->cluster_bodies, ctx->solo_bodies);
+          }));
+          if (ctx->solo_bodies > 0)
+            TRY(side(EP_K_SOLVE_CLUSTER, [&](cudaStream_t sx) {
+              k_solve_cluster<kClusterWarps, true><<<16, kClusterThreads, cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->solo_bodies), sx>>>(d, kBins - 1, kBins - 1, force_resum, ctx->cluster_ws, ctx->solo_bodies, ctx->solo_bodies);
+            }));
+        }
         if (smemb) {
-          TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
+          TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, true><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, team_hi, force_resum); }));
           TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, true><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
         } else {
-          TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, kBins - 1, force_resum); }));
+          TRY(side(EP_K_SOLVE_TEAM_CTA, [&](cudaStream_t sx) { k_solve_team<256, false><<<ctx->sm_count * 2, 256, sm_cta, sx>>>(d, 8, team_hi, force_resum); }));
           TRY(side(EP_K_SOLVE_TEAM_WARP, [&](cudaStream_t sx) { k_solve_team<32, false><<<ctx->sm_count * 16, 32, sm_warp, sx>>>(d, kLaneBinMax + 1, 7, force_resum); }));
         }
         // the lane classes: every warp builds its own tile (bodies, descriptors, rows gathered from k_equations' records) and solves it

@@ -279,7 +279,7 @@ enum { EP_STAT_KERNEL_LAUNCHES = 0, EP_STAT_CANDIDATE_PAIRS = 1, EP_STAT_GROUPS 
  * CUDA events on the context's stream and resets the accumulators; ep_kernel_times synchronises and returns
  * the accumulated milliseconds and launch counts per kernel kind (EP_K_*).  Launch counts are always kept. */
 enum { EP_K_PLACE = 0, EP_K_SORT = 1, EP_K_BROADPHASE = 2, EP_K_NARROWPHASE = 3, EP_K_EQUATIONS = 4, EP_K_ISLANDS = 5,
-       EP_K_SOLVE = 6, EP_K_INTEGRATE = 7, EP_K_TILE_BUILD = 8,
+       EP_K_SOLVE = 6, EP_K_INTEGRATE = 7, EP_K_SOLVE_CLUSTER = 8,   /* giant islands on a thread-block cluster (slot of the former k_tile_build) */
        /* the solver's concurrent launches by island size class (they overlap; EP_K_SOLVE brackets all of them) */
        EP_K_SOLVE_LANES_B0 = 9, EP_K_SOLVE_LANES_B1 = 10, EP_K_SOLVE_LANES_B2 = 11, EP_K_SOLVE_LANES_B3 = 12, EP_K_SOLVE_LANES_B4 = 13,
        EP_K_SOLVE_LANES_B5 = 14, EP_K_SOLVE_LANES_INPLACE = 15, EP_K_SOLVE_TEAM_WARP = 16, EP_K_SOLVE_TEAM_CTA = 17, EP_K_COUNT = 18 };
