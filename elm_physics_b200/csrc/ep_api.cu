@@ -53,7 +53,7 @@ struct ep_ctx {
   int head_grid[6] = {0, 0, 0, 0, 0, 0};         // resident CTAs of the staged launch of each class
   int lanes_grid = 0;
   size_t team_smem_max = 48 * 1024;
-  int cluster_nc = 0, cluster_ws = 32, cluster_count = 1, solo_bodies = 1024, cluster_bodies = 512;      // k_solve_cluster: CTAs per cluster (0 = unavailable), window slots per warp, clusters per launch, body table of the SOLO launch
+  int cluster_nc = 0, cluster_ws = 64, cluster_count = 1, solo_bodies = 1024, cluster_bodies = 512;      // k_solve_cluster: CTAs per cluster (0 = unavailable), window slots per warp, clusters per launch, body table of the SOLO launch
   // quad solver (small batches): launches of k_solve_quads -- classes [lo, hi] with kq islands per warp, shared memory sized
   // for class hi (ep_solve_quads.cuh) -- and the largest batch (bodies) that takes this family (EP_SOLVER=lanes|quads overrides)
   struct QuadLaunch { int lo, hi, kq, cap_rows, cap_bodies, cap_groups; size_t smem; int resident; };
@@ -208,7 +208,7 @@ extern "C" int ep_create(ep_ctx** out, int device) {
   if (ok) {
     const char* ce = getenv("EP_CLUSTER");
     const int want = ce ? atoi(ce) : 16;
-    if (getenv("EP_CLUSTER_WS")) ctx->cluster_ws = std::max(0, std::min(32, atoi(getenv("EP_CLUSTER_WS"))));
+    if (getenv("EP_CLUSTER_WS")) ctx->cluster_ws = std::max(0, std::min(64, atoi(getenv("EP_CLUSTER_WS"))));
     if (getenv("EP_SOLO") && atoi(getenv("EP_SOLO")) == 0) ctx->solo_bodies = 0;
     const size_t sm = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->cluster_bodies), sm_solo = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->solo_bodies);
     if (want > 0 && sm_solo <= ctx->team_smem_max &&
@@ -756,7 +756,7 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         k_slot_counts<<<grid_for(ctx, d.slot_cap, 256, 8), 256, 0, st>>>(d);
         CK(cudaEventRecord(ctx->ev_fork, st));
         // one CTA per world: a warp for small worlds, more for large ones; the union-find arrays sit in shared memory when they fit
-        const int it = d.nb_max <= 64 ? 32 : (d.nb_max <= 512 ? 128 : 256);
+        const int it = d.nb_max <= 64 ? 32 : (d.nb_max <= 512 ? 128 : (d.nb_max <= 1024 ? 256 : 1024));
         const size_t ism = 3 * (size_t)d.nb_max * sizeof(int);
         const int use_smem = ism <= 40 * 1024;
         k_islands<<<std::max(1, std::min(d.n_worlds, ctx->sm_count * isl_per_sm)), it, use_smem ? ism : 0, st>>>(d, use_smem);
@@ -830,8 +830,11 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
         const bool smemb = body_b + 3 * 8 * 256 * 4 <= std::min<size_t>(200 * 1024, ctx->team_smem_max);
         const size_t sm_cta = 3 * 8 * 256 * 4 + (smemb ? body_b : 0), sm_warp = 3 * 8 * 32 * 4 + (smemb ? body_b : 0);
         // giant islands (class 9) on a thread-block cluster, first: it is the longest chain of the step
-        const int team_hi = ctx->cluster_nc > 0 ? kBins - 2 : kBins - 1;
-        if (ctx->cluster_nc > 0) {
+        // (only for batches whose worlds are large enough to hold one: beside the 8192 small worlds of config 3 the two launches --
+        // 64 + 16 CTAs with ~100 KB of shared memory each, first in line -- delayed the lane classes by 0.3 ms although they exit at once)
+        const bool use_cluster = ctx->cluster_nc > 0 && d.nb_max > 64;
+        const int team_hi = use_cluster ? kBins - 2 : kBins - 1;
+        if (use_cluster) {
           TRY(side(EP_K_SOLVE_CLUSTER, [&](cudaStream_t sx) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(ctx->cluster_nc * ctx->cluster_count); cfg.blockDim = dim3(kClusterThreads);

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
   __shared__ int4 s_desc[2][NW][8];     // producer -> consumer, per step parity: (first window slot | -1, row-solves, body 1, body 2) of each quad's group
   __shared__ int s_lvn[2][NW];          // ... and the number of groups of the step's level
   __shared__ int s_wflush[2][NW], s_wdlt[2][NW];      // slots of a window whose results wait for the flush, offset of |dlambda| from lambda
-  __shared__ int s_c0[NW][32];          // producer: first contact of the group whose window slots start at [slot]
+  __shared__ int s_c0[NW][64];          // producer: first contact of the group whose window slots start at [slot]
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, qb = lane & ~3, k = lane >> 2;
   const bool producer = warp >= NW;
@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
     const int r0 = d.world_body_off[w];
     const bool solo_ok = gn <= kSoloGroupsMax && nb + 1 <= solo_bodies;       // the SOLO launch takes these, the cluster launch the others
     if (solo_ok != SOLO) continue;
+#ifdef EP_CL_TRACE
+    const long long tr_i0 = cl_clock();
+#endif
     // bodies in the distributed table (numbered inside the island, 0 = the stand-in of every non-dynamic body), or, when they do
     // not fit, in the global solver-body array (global row, -1)
     const bool tab = nb + 1 <= NC * cap_bodies;
@@ -158,18 +161,18 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
           s_a[i] = walk_ref(d.cur.slot_row1[s]); s_b[i] = walk_ref(d.cur.slot_row2[s]);
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {      // the serial part: one dependent shared-memory round trip per group (the next pair is read ahead)
           int nlev = s_nlev;
+          int a = s_a[0], b = s_b[0];
           for (int i = 0; i < m; i++) {
-            const int a = s_a[i], b = s_b[i];
-            int l = 0;
-            if (a) l = last[a];
-            if (b) l = max(l, last[b]);
+            const int na = s_a[min(i + 1, m - 1)], nb2 = s_b[min(i + 1, m - 1)];
+            const int la = a ? last[a] : 0, lb = b ? last[b] : 0;
+            const int l = max(la, lb);
             s_lv[i] = l;
-            l++;
-            if (a) last[a] = l;
-            if (b) last[b] = l;
-            nlev = max(nlev, l);
+            if (a) last[a] = l + 1;
+            if (b) last[b] = l + 1;
+            nlev = max(nlev, l + 1);
+            a = na; b = nb2;
           }
           s_nlev = nlev;
         }
@@ -197,6 +200,9 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
     if (!SOLO) { cl_arrive(); cl_wait(); }
     const int nlev = SOLO ? s_nlev : cl_ld_s32(cl_map(&s_nlev, 0));
     const bool lsm = nlev <= LCAP;
+#ifdef EP_CL_TRACE
+    const long long tr_i1 = cl_clock();
+#endif
     if (lsm) { for (int l = tid; l <= nlev; l += T) s_loff[l] = l < nlev ? __ldcg(loff + l) : gn; }
     if (tid < 2 * NW) { s_wflush[tid / NW][tid % NW] = 0; s_wdlt[tid / NW][tid % NW] = 0; }
     if (tab) {       // this CTA's share of the body table: body b of the island lives in CTA b mod NC, entry b / NC
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
     const double eps_c = spook(d.dt[w]).eps;
     double part = 0;
 #ifdef EP_CL_TRACE
-    long long tr_rows = 0, tr_body = 0, tr_loop = 0, tr_x = 0, tr_y = 0, tr_z = 0, tr_p1 = 0, tr_p2 = 0, tr_q = 0, tr_a = 0, tr_r0 = 0, tr_r1 = 0, tr_nr = 0;
+    long long tr_rows = 0, tr_body = 0, tr_loop = 0, tr_x = 0, tr_y = 0, tr_z = 0, tr_p1 = 0, tr_p2 = 0, tr_q = 0, tr_a = 0, tr_r0 = 0, tr_r1 = 0, tr_nr = 0, tr_slow = 0;
 #endif
     // the lane's half of a solver body: (v | invMass) for the linear lanes, (w | 1) for the angular ones
     auto load_half = [&](int b, bool need, double& s0, double& s1, double& s2, double& m) {
@@ -420,7 +426,8 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
       const bool fits = stg && incl <= ws;
       const int base = incl - n;
       if (q == 0) s_desc[buf][cw][k] = make_int4(fits ? base : -1, n, rc.b1, rc.b2);
-      const unsigned M = __reduce_or_sync(full, (q == 0 && fits) ? (1u << base) : 0u);
+      const unsigned Ml = __reduce_or_sync(full, (q == 0 && fits && base < 32) ? (1u << base) : 0u);      // slots at which a group starts (ws <= 64)
+      const unsigned Mh = __reduce_or_sync(full, (q == 0 && fits && base >= 32) ? (1u << (base - 32)) : 0u);
       const int tot = __reduce_max_sync(full, fits ? incl : 0);
       if (q == 0 && fits) s_c0[cw][base] = rc.c0;
       if (lane == 0) {
@@ -435,7 +442,8 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
       tr_q = cl_clock();
 #endif
       for (int i = k; i < tot; i += 8) {
-        const int sb = 31 - __clz(M & ((2u << i) - 1u));      // the group this slot belongs to starts at slot sb
+        const unsigned mh = i >= 32 ? (Mh & ((2u << (i - 32)) - 1u)) : 0u, ml = i >= 32 ? Ml : (Ml & ((2u << i) - 1u));
+        const int sb = mh ? 63 - __clz(mh) : 31 - __clz(ml);      // the group this slot belongs to starts at slot sb
         const int x = i - sb;
         const int f = ph == 2 ? (x & 1) : 0;
         const double* R = (const double*)(d.rows + s_c0[cw][sb] + (ph == 2 ? x >> 1 : x));
@@ -547,6 +555,9 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
           run_group_win(ph_c, ds.x >= 0 ? ds.y : 0, q < 2 ? ds.z : ds.w, win + ((size_t)(t & 1) * ws + max(ds.x, 0)) * kSlotBytes);
         else {       // a group of the warp is not in the window: the whole warp solves in place, and what was staged must not be flushed
           if (lane == 0) s_wflush[t & 1][cw] = 0;
+#ifdef EP_CL_TRACE
+          tr_slow++;
+#endif
           run_group(ph_c, rec_at(l_c, slot0));
         }
 #ifdef EP_CL_TRACE
@@ -580,6 +591,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
       t++;
     }
 #ifdef EP_CL_TRACE
+    if (tid == 0 && rank == 0) printf("[cl] build %lld cycles, to loop start %lld, slow-path steps of warp 0: %lld\n", tr_i1 - tr_i0, tr_t0 - tr_i0, tr_slow);
     if (lane == 0 && rank == 0) printf("[cl] isl %d gn %d nlev %d warp %d %s steps %d rows %lld: pre %lld wait %lld work %lld cycles per step; body %lld loop %lld p1 %lld p2 %lld r0 %lld rounds %lld (in %lld steps) per step; total %lld\n", isl, gn, nlev, warp, producer ? "producer" : "consumer", t, tr_rows, tr_pre / max(t, 1), tr_wait / max(t, 1), tr_work / max(t, 1), tr_body / max(t, 1), tr_loop / max(t, 1), tr_p1 / max(t, 1), tr_p2 / max(t, 1), tr_r0 / max(t, 1), tr_r1 / max(t, 1), tr_nr, (long long)(cl_clock() - tr_t0));
 #endif
     if (producer) flush((t + 1) & 1);                 // the last step's results
