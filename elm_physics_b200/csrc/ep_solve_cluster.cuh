@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
   __shared__ int4 s_desc[2][NW][8];     // producer -> consumer, per step parity: (first window slot | -1, row-solves, body 1, body 2) of each quad's group
   __shared__ int s_lvn[2][NW];          // ... and the number of groups of the step's level
   __shared__ int s_wflush[2][NW], s_wdlt[2][NW];      // slots of a window whose results wait for the flush, offset of |dlambda| from lambda
-  __shared__ int s_c0[NW][64];          // producer: first contact of the group whose window slots start at [slot]
+  __shared__ int s_c0[2][NW][64];          // producer: first contact of the group whose window slots start at [slot]
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, qb = lane & ~3, k = lane >> 2;
   const bool producer = warp >= NW;
@@ -220,9 +220,10 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
     }
     __syncthreads();
     auto level_begin = [&](int l) -> int { return lsm ? s_loff[l] : (l < nlev ? __ldcg(loff + l) : gn); };
-    // a group's results reach its row records one step after it was solved (the producer's flush) and its rows are staged one step
-    // before it is solved again: with three levels or more the flush is always a whole step ahead of the staging
-    const bool use_win = nlev >= 3 && ws > 0;
+    // a group's results reach its row records one step after it was solved (the producer's flush) and its rows are read two steps
+    // before it is solved again (the producer's loads run a step ahead of its stores): with four levels or more the flush is always
+    // a whole step ahead of the loads
+    const bool use_win = nlev >= 4 && ws > 0;
     TeamRec none; none.b1 = tab ? 0 : -1; none.b2 = none.b1; none.c0 = 0; none.cn = 0; none.j0 = 0; none.jn = 0; none.pad0 = 0; none.pad1 = 0;
     auto rec_at = [&](int l, int slot) -> TeamRec {
       const int lb = level_begin(l), n = level_begin(l + 1) - lb;
@@ -415,8 +416,43 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
       __syncwarp();
     };
     // ---- producer: the consumer's round-0 groups of one step: window slots in quad order while they fit (groups with joint rows and
-    // what does not fit are solved in place), the rows laid out per lane role, and the consumer's descriptors ------------------------
-    auto produce = [&](int ph, int l, const TeamRec& rc, int buf) {
+    // what does not fit are solved in place), the rows laid out per lane role, and the consumer's descriptors.  In two halves a step
+    // apart: `issue` allots the slots and LOADS the rows into registers (the L2 round trip, ~700 cycles, runs beside the producer's
+    // other work and the barrier), `commit` forms the slots from them and stores slots and descriptors into the window ----------
+    constexpr int PF = 2;                                    // slots per lane that travel in registers (8 PF per warp); more are loaded at commit time
+    struct Pend { int ph, n_lvl, tot, par; unsigned Ml, Mh; int4 desc; int slot[PF]; const double* R[PF]; double v[PF][11]; } pd;
+    pd.ph = 0; pd.n_lvl = 0; pd.tot = 0; pd.par = 0; pd.Ml = 0; pd.Mh = 0; pd.desc = make_int4(-1, 0, 0, 0);
+    // row record and field offsets of window slot i of a step (M: the slots at which a group starts; c0 table of the step)
+    auto slot_src = [&](int ph, unsigned Ml, unsigned Mh, const int* c0tab, int i, int& jb, int& ci, int& li, int& bi, int& ici) -> const double* {
+      const unsigned mh = i >= 32 ? (Mh & ((2u << (i - 32)) - 1u)) : 0u, ml = i >= 32 ? Ml : (Ml & ((2u << i) - 1u));
+      const int sb = mh ? 63 - __clz(mh) : 31 - __clz(ml);      // the group this slot belongs to starts at slot sb
+      const int x = i - sb;
+      const int f = ph == 2 ? (x & 1) : 0;
+      jb = ph == 2 ? (f ? kR_f2J : kR_f1J) : kR_nJ;
+      ci = !angular ? jb + ja : (ph == 2 ? (f ? (q == 1 ? kR_f2Ia : kR_f2Ib) : (q == 1 ? kR_f1Ia : kR_f1Ib)) : (q == 1 ? kR_nIa : kR_nIb));
+      li = ph == 2 ? (f ? kR_lamF2 : kR_lamF1) : kR_lamN;
+      bi = ph == 2 ? (f ? kR_f2B : kR_f1B) : kR_nB; ici = ph == 2 ? (f ? kR_f2InvC : kR_f1InvC) : kR_nInvC;
+      return (const double*)(d.rows + c0tab[sb] + (ph == 2 ? x >> 1 : x));
+    };
+    // every load of a slot is issued before any is used: one L2 round trip (all four lanes read the row's scalars, lane 0 keeps them)
+    auto slot_load = [&](const double* R, int jb, int ci, int li, int bi, int ici, double* v) {
+      v[0] = R[jb + ja]; v[1] = R[jb + ja + 1]; v[2] = R[jb + ja + 2];
+      v[3] = R[ci]; v[4] = R[ci + 1]; v[5] = R[ci + 2];
+      v[6] = R[bi]; v[7] = R[ici]; v[8] = __ldcg(R + li); v[9] = R[kR_mu]; v[10] = __ldcg(R + kR_lamN);
+    };
+    auto slot_store = [&](int ph, unsigned char* wb, int i, const double* v, const double* lamp) {
+      const double a0 = sg * v[0], a1 = sg * v[1], a2 = sg * v[2];
+      const double c0 = angular ? v[3] : a0, c1 = angular ? v[4] : a1, c2 = angular ? v[5] : a2;
+      double2* o = (double2*)(wb + (size_t)i * kSlotBytes + q * 48);
+      o[0] = make_double2(a0, a1); o[1] = make_double2(a2, c0); o[2] = make_double2(c1, c2);
+      const double cap = v[9] * v[10];
+      const double lo = ph == 2 ? -cap : 0.0, hi = ph == 2 ? cap : kMaxImpulse;
+      if (q == 0) {
+        double2* s = (double2*)(wb + (size_t)i * kSlotBytes + kSlotShared);
+        s[0] = make_double2(v[6], v[7]); s[1] = make_double2(v[8], lo); s[2] = make_double2(hi, __longlong_as_double((long long)lamp));
+      }
+    };
+    auto issue = [&](int ph, int l, const TeamRec& rc, int par) {
       const int n = rows_of(ph, rc);
       const bool stg = use_win && n > 0 && !(ph == 1 && rc.jn > 0);
       int incl = (q == 0 && stg) ? n : 0;            // inclusive scan over the quad leaders (lanes 0, 4, .., 28)
@@ -425,62 +461,60 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
       incl = __shfl_sync(full, incl, qb);
       const bool fits = stg && incl <= ws;
       const int base = incl - n;
-      if (q == 0) s_desc[buf][cw][k] = make_int4(fits ? base : -1, n, rc.b1, rc.b2);
-      const unsigned Ml = __reduce_or_sync(full, (q == 0 && fits && base < 32) ? (1u << base) : 0u);      // slots at which a group starts (ws <= 64)
-      const unsigned Mh = __reduce_or_sync(full, (q == 0 && fits && base >= 32) ? (1u << (base - 32)) : 0u);
-      const int tot = __reduce_max_sync(full, fits ? incl : 0);
-      if (q == 0 && fits) s_c0[cw][base] = rc.c0;
-      if (lane == 0) {
-        s_lvn[buf][cw] = level_begin(l + 1) - level_begin(l);
-        s_wflush[buf][cw] = ph == 0 ? 0 : tot;
-        s_wdlt[buf][cw] = ph == 1 ? kR_dN - kR_lamN : kR_dF1 - kR_lamF1;
-      }
+      pd.ph = ph; pd.par = par;
+      pd.desc = make_int4(fits ? base : -1, n, rc.b1, rc.b2);
+      pd.Ml = __reduce_or_sync(full, (q == 0 && fits && base < 32) ? (1u << base) : 0u);      // slots at which a group starts (ws <= 64)
+      pd.Mh = __reduce_or_sync(full, (q == 0 && fits && base >= 32) ? (1u << (base - 32)) : 0u);
+      pd.tot = __reduce_max_sync(full, fits ? incl : 0);
+      pd.n_lvl = level_begin(l + 1) - level_begin(l);
+      if (q == 0 && fits) s_c0[par][cw][base] = rc.c0;
       __syncwarp();
-      unsigned char* wb = win + (size_t)buf * ws * kSlotBytes;
 #ifdef EP_CL_TRACE
-      tr_rows += (tot + 7) / 8;
-      tr_q = cl_clock();
+      tr_rows += (pd.tot + 7) / 8;
 #endif
-      for (int i = k; i < tot; i += 8) {
-        const unsigned mh = i >= 32 ? (Mh & ((2u << (i - 32)) - 1u)) : 0u, ml = i >= 32 ? Ml : (Ml & ((2u << i) - 1u));
-        const int sb = mh ? 63 - __clz(mh) : 31 - __clz(ml);      // the group this slot belongs to starts at slot sb
-        const int x = i - sb;
-        const int f = ph == 2 ? (x & 1) : 0;
-        const double* R = (const double*)(d.rows + s_c0[cw][sb] + (ph == 2 ? x >> 1 : x));
-        const int jb = ph == 2 ? (f ? kR_f2J : kR_f1J) : kR_nJ;
-        const int ci = !angular ? jb + ja : (ph == 2 ? (f ? (q == 1 ? kR_f2Ia : kR_f2Ib) : (q == 1 ? kR_f1Ia : kR_f1Ib)) : (q == 1 ? kR_nIa : kR_nIb));
-        const int li = ph == 2 ? (f ? kR_lamF2 : kR_lamF1) : kR_lamN;
-        // every load of the slot is issued before any is used: one L2 round trip (all four lanes read the row's scalars, lane 0 keeps them)
-        const double j0 = R[jb + ja], j1 = R[jb + ja + 1], j2 = R[jb + ja + 2];
-        const double i0 = R[ci], i1 = R[ci + 1], i2 = R[ci + 2];
-        const double B = R[ph == 2 ? (f ? kR_f2B : kR_f1B) : kR_nB], invC = R[ph == 2 ? (f ? kR_f2InvC : kR_f1InvC) : kR_nInvC];
-        const double lam = __ldcg(R + li), mu = R[kR_mu], ln = __ldcg(R + kR_lamN);
-        const double a0 = sg * j0, a1 = sg * j1, a2 = sg * j2;
-        const double c0 = angular ? i0 : a0, c1 = angular ? i1 : a1, c2 = angular ? i2 : a2;
-        double2* o = (double2*)(wb + (size_t)i * kSlotBytes + q * 48);
-        o[0] = make_double2(a0, a1); o[1] = make_double2(a2, c0); o[2] = make_double2(c1, c2);
-        const double cap = mu * ln;
-        const double lo = ph == 2 ? -cap : 0.0, hi = ph == 2 ? cap : kMaxImpulse;
-        if (q == 0) {
-          double2* s = (double2*)(wb + (size_t)i * kSlotBytes + kSlotShared);
-          s[0] = make_double2(B, invC); s[1] = make_double2(lam, lo); s[2] = make_double2(hi, __longlong_as_double((long long)(R + li)));
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        const int i = k + 8 * j;
+        pd.slot[j] = -1;
+        if (i < pd.tot) {
+          int jb, ci, li, bi, ici;
+          const double* R = slot_src(ph, pd.Ml, pd.Mh, s_c0[par][cw], i, jb, ci, li, bi, ici);
+          slot_load(R, jb, ci, li, bi, ici, pd.v[j]);
+          pd.slot[j] = i; pd.R[j] = R + li;
         }
       }
-#ifdef EP_CL_TRACE
+    };
+    auto commit = [&](int buf) {
+      if (q == 0) s_desc[buf][cw][k] = pd.desc;
+      if (lane == 0) {
+        s_lvn[buf][cw] = pd.n_lvl;
+        s_wflush[buf][cw] = pd.ph == 0 ? 0 : pd.tot;
+        s_wdlt[buf][cw] = pd.ph == 1 ? kR_dN - kR_lamN : kR_dF1 - kR_lamF1;
+      }
+      unsigned char* wb = win + (size_t)buf * ws * kSlotBytes;
+#pragma unroll
+      for (int j = 0; j < PF; j++) if (pd.slot[j] >= 0) slot_store(pd.ph, wb, pd.slot[j], pd.v[j], pd.R[j]);
+      for (int i = k + 8 * PF; i < pd.tot; i += 8) {          // what did not travel in registers
+        int jb, ci, li, bi, ici; double v[11];
+        const double* R = slot_src(pd.ph, pd.Ml, pd.Mh, s_c0[pd.par][cw], i, jb, ci, li, bi, ici);
+        slot_load(R, jb, ci, li, bi, ici, v);
+        slot_store(pd.ph, wb, i, v, R + li);
+      }
       __syncwarp();
-      tr_p2 += cl_clock() - tr_q;
-#endif
     };
     const int iterations = d.iterations[w];
     int remaining = iterations, rem = 0;
     int ph_c = 0, l_c = nlev - 1;                    // the current step (consumer) ...
-    int ph_s = ph_c, l_s = l_c, ph_n = 0, l_n = 0;   // ... the step the producer stages next, and the one after it
-    TeamRec rc_s = none, rc_n = none;
-    if (producer) {                                  // the first step's window and descriptors, in front of the first barrier
-      produce(ph_s, l_s, rec_at(l_s, slot0), 0);
-      advance(ph_s, l_s);
-      rc_s = rec_at(l_s, slot0);
-      ph_n = ph_s; l_n = l_s; advance(ph_n, l_n);
+    int ph_i = ph_c, l_i = l_c, ph_n = 0, l_n = 0;   // ... the step the producer issues next (two ahead of the consumer), and the one after it
+    TeamRec rc_i = none, rc_n = none;
+    if (producer) {                                  // the first step's window and descriptors in front of the first barrier, the second step's rows on their way
+      issue(ph_i, l_i, rec_at(l_i, slot0), 0);
+      commit(0);
+      advance(ph_i, l_i);
+      issue(ph_i, l_i, rec_at(l_i, slot0), 1);
+      advance(ph_i, l_i);
+      rc_i = rec_at(l_i, slot0);
+      ph_n = ph_i; l_n = l_i; advance(ph_n, l_n);
     }
     int t = 0;
     bool decide = false;
@@ -493,7 +527,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
 #ifdef EP_CL_TRACE
       tr_a = cl_clock();
 #endif
-      if (producer) rc_n = rec_at(l_n, slot0);        // in flight until the next step is staged
+      if (producer) rc_n = rec_at(l_n, slot0);        // in flight until the step after the next is issued
       __syncwarp();
 #ifdef EP_CL_TRACE
       tr_b = cl_clock(); tr_pre += tr_b - tr_a;
@@ -539,9 +573,10 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
         remaining--;
       }
       if (producer) {
-        flush((t + 1) & 1);                           // step t-1's results, then that window is staged for step t+1
-        produce(ph_s, l_s, rc_s, (t + 1) & 1);
-        ph_s = ph_n; l_s = l_n; rc_s = rc_n; advance(ph_n, l_n);
+        flush((t + 1) & 1);                           // step t-1's results; then that window receives step t+1, whose rows were loaded a step ago,
+        commit((t + 1) & 1);
+        issue(ph_i, l_i, rc_i, t & 1);                // and the loads of step t+2 start
+        ph_i = ph_n; l_i = l_n; rc_i = rc_n; advance(ph_n, l_n);
       } else {
         // ---- the step: this quad's group of level l_c (round 0) from the window; what is not there and further rounds in place ----
         const int4 ds = s_desc[t & 1][cw][k];
