@@ -667,27 +667,45 @@ def main():
                 for name in abi.BODY_INOUT:
                     exact = exact and getattr(end_bodies, name)[r0:r1].tobytes() == getattr(ch[0], name).tobytes()
             line["parity"] = {"worlds": sample, "steps": args.steps, "bit_exact_vs_oracle": bool(exact)}
-        # ---- second half of BASELINE's metric: ms/step of the 2k-body convex pile (config 4; one world, one GPU) ------
+        # ---- second half of BASELINE's metric: ms/step of the 2k-body convex pile (config 4; one world, one GPU), and config 2
+        # (100 boxes: the 91-box pyramid + a 9-box stack, one world) beside it.  Both are ONE giant island: the thread-block-cluster
+        # solver's case (ep_solve_cluster.cuh).  The restatement's single-thread ms/step from the same settled state rides along.
         if world_size == 1 and not args.no_pile:
-            ps, pb, pp = pack.pack_worlds(scenes.pile_scene(2000))
-            ep = eng.Engine(local_rank)
-            ep.upload_shapes(ps)
-            ep.upload_worlds(pb, pp, None)
-            ep.step_resident(args.pile_preroll)
-            ep.sync()
-            pstream = torch.cuda.ExternalStream(ep.stream_handle(), device=torch.device("cuda", local_rank))
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            q0.record(pstream)
-            ep.step_resident(args.pile_steps)
-            q1.record(pstream)
-            ep.sync()
-            torch.cuda.synchronize()
-            pst = ep.stats()
-            line["pile"] = {"workload": "C4: 2000 convex hulls / compounds dropped into a walled pit, one world, 20 iterations",
-                            "ms_per_step": q0.elapsed_time(q1) / args.pile_steps, "steps": args.pile_steps,
-                            "preroll_steps": args.pile_preroll, "bodies": int(pb.n_bodies), "contacts": pst["contacts"],
-                            "islands": pst["islands"], "unit": "ms/step", "higher_is_better": False}
-            ep.close()
+            def single_world(name, worlds, preroll, steps, cpu_steps):
+                ps, pb, pp = pack.pack_worlds(worlds)
+                ep = eng.Engine(local_rank)
+                ep.upload_shapes(ps)
+                ep.upload_worlds(pb, pp, None)
+                ep.step_resident(preroll)
+                ep.sync()
+                cpu_ms = None
+                if not args.no_cpu_baseline and cpu_steps > 0:      # the checker, timed from the GPU's settled state (bodies + warm-start contacts)
+                    from oracle import binding as oracle_binding
+                    sb = pb.copy()
+                    ep.download_bodies(sb)
+                    sw = abi.Contacts(1, 40 * pb.n_bodies, 64 * pb.n_bodies)
+                    ep.download_contacts(sw)
+                    so = abi.Contacts(1, 40 * pb.n_bodies, 64 * pb.n_bodies)
+                    t0 = time.perf_counter()
+                    oracle_binding.step(ps, sb, pp, sw, so, cpu_steps)
+                    cpu_ms = (time.perf_counter() - t0) * 1e3 / cpu_steps
+                pstream = torch.cuda.ExternalStream(ep.stream_handle(), device=torch.device("cuda", local_rank))
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record(pstream)
+                ep.step_resident(steps)
+                q1.record(pstream)
+                ep.sync()
+                torch.cuda.synchronize()
+                pst = ep.stats()
+                out = {"workload": name, "ms_per_step": q0.elapsed_time(q1) / steps, "steps": steps, "preroll_steps": preroll,
+                       "bodies": int(pb.n_bodies), "contacts": pst["contacts"], "islands": pst["islands"], "unit": "ms/step",
+                       "higher_is_better": False, "cpu_restatement_ms_per_step_1_thread": cpu_ms}
+                ep.close()
+                return out
+            line["pile"] = single_world("C4: 2000 convex hulls / compounds dropped into a walled pit, one world, 20 iterations",
+                                        scenes.pile_scene(2000), args.pile_preroll, args.pile_steps, 5)
+            line["boxes"] = single_world("C2: 100 boxes (91-box pyramid + 9-box stack) on a plane, one world, 20 iterations",
+                                         scenes.boxes_scene(), 300, args.pile_steps, 30)
         emit(line)
     pool.close()
     e.close()

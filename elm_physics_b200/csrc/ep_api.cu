@@ -210,6 +210,7 @@ extern "C" int ep_create(ep_ctx** out, int device) {
     const int want = ce ? atoi(ce) : 16;
     if (getenv("EP_CLUSTER_WS")) ctx->cluster_ws = std::max(0, std::min(64, atoi(getenv("EP_CLUSTER_WS"))));
     if (getenv("EP_SOLO") && atoi(getenv("EP_SOLO")) == 0) ctx->solo_bodies = 0;
+    if (getenv("EP_CLUSTER_BODIES")) ctx->cluster_bodies = std::max(1, std::min(512, atoi(getenv("EP_CLUSTER_BODIES"))));      // test aid: a small table forces the global-array fallback
     const size_t sm = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->cluster_bodies), sm_solo = cluster_smem_bytes(kClusterWarps, ctx->cluster_ws, ctx->solo_bodies);
     if (want > 0 && sm_solo <= ctx->team_smem_max &&
         cudaFuncSetAttribute(k_solve_cluster<kClusterWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&

@@ -40,6 +40,7 @@ __device__ __forceinline__ unsigned cl_id() { unsigned r; asm volatile("mov.u32 
 __device__ __forceinline__ unsigned cl_count() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ long long cl_clock() { long long x; asm volatile("mov.u64 %0, %%clock64;" : "=l"(x) :: "memory"); return x; }
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // shared-memory address of `p` in CTA `rank` of the cluster
 __device__ __forceinline__ unsigned cl_map(const void* p, unsigned rank) {
@@ -121,7 +122,12 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
   const int ja = q == 1 ? 0 : (q == 3 ? 6 : 3);        // J = (wA | vB | wB)
   const bool angular = (q & 1) != 0;
   auto step_wait = [&]() { if (SOLO) __syncthreads(); else cl_wait(); };
-  auto step_arrive = [&]() { if (!SOLO) cl_arrive(); };
+  // The release of barrier.cluster.arrive is MEMBAR.ALL.GPU: it waits for every outstanding memory operation of the warp, LOADS
+  // included.  The consumers need it (their body stores must be visible in the other CTAs).  A producer publishes nothing outside
+  // its CTA during a step -- the window is read by its own consumer, the flushed results by itself -- so it orders its stores with
+  // a CTA-scope fence BEFORE it starts the next step's row loads and arrives relaxed: the loads stay in flight across the barrier
+  // (ncu before: 37 % of all warp samples of the pile's launch sat in the arrive's fence).
+  auto step_arrive = [&]() { if (!SOLO) { if (producer) cl_arrive_relaxed(); else cl_arrive(); } };
   auto all_sync = [&]() { if (SOLO) __syncthreads(); else { cl_arrive(); cl_wait(); } };
   int total = 0;
   for (int b = bin_lo; b <= bin_hi; b++) total += d.cur.counters[CNT_BIN0 + b];
@@ -510,6 +516,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
     if (producer) {                                  // the first step's window and descriptors in front of the first barrier, the second step's rows on their way
       issue(ph_i, l_i, rec_at(l_i, slot0), 0);
       commit(0);
+      __threadfence_block();
       advance(ph_i, l_i);
       issue(ph_i, l_i, rec_at(l_i, slot0), 1);
       advance(ph_i, l_i);
@@ -575,6 +582,7 @@ __global__ void __launch_bounds__(2 * NW * 32, 1) k_solve_cluster(Dev d, int bin
       if (producer) {
         flush((t + 1) & 1);                           // step t-1's results; then that window receives step t+1, whose rows were loaded a step ago,
         commit((t + 1) & 1);
+        __threadfence_block();
         issue(ph_i, l_i, rc_i, t & 1);                // and the loads of step t+2 start
         ph_i = ph_n; l_i = l_n; rc_i = rc_n; advance(ph_n, l_n);
       } else {
