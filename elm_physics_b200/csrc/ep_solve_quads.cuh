@@ -227,44 +227,75 @@ __global__ void __launch_bounds__(32) k_solve_quads(Dev d, int bin_lo, int bin_h
     bool done = !live;
     const double eps = live ? spook(d.dt[w]).eps : 0.0;
     while (__any_sync(full, !done)) {
-      // sweep 1: velocityNonFrictionGroup (Solver.elm:850-864) group by group: joint rows (572-619), then contact normals (625-672)
+      // sweep 1: velocityNonFrictionGroup (Solver.elm:850-864) group by group: joint rows (572-619), then contact normals (625-672).
+      // The row after the current one is read while this one computes, and what does not hang on the solver bodies -- the bounds,
+      // lambda's share of the right-hand side, the two clamped candidates -- exists before G.W does: the chain of a row is the dot,
+      // the shuffles, the sum, two compares and selects, the update (no branch; the quad's first lane stores under a predicate)
       double p1 = 0;
-      for (int i = 0; i < R1max; i++) {
-        const bool on = !done && i < R1;
-        unsigned char* row = T.slot(i);
-        LaneRow r; load_row(row, r);
-        enter(on, r.desc);
-        const double gw = quad_gw(r.a0, r.a1, r.a2);
-        const double lo = (r.desc & DESC_JOINT) ? -kMaxImpulse : 0.0;
-        const double prev = r.invC * (r.B - gw - eps * r.lam);
-        const double dl = (r.lam + prev - lo < 0) ? lo - r.lam : ((r.lam + prev - kMaxImpulse > 0) ? kMaxImpulse - r.lam : prev);
-        if (on) {
+      {
+        auto step1 = [&](int i, const LaneRow& r) {
+          const bool on = !done && i < R1;
+          const double lo = (r.desc & DESC_JOINT) ? -kMaxImpulse : 0.0;
+          const double el = eps * r.lam, dlo = lo - r.lam, dhi = kMaxImpulse - r.lam;
+          enter(on, r.desc);
+          const double gw = quad_gw(r.a0, r.a1, r.a2);
+          const double prev = r.invC * (r.B - gw - el);
+          const double sum = r.lam + prev;
+          const bool under = sum - lo < 0, over = sum - kMaxImpulse > 0;
+          const double dl = under ? dlo : (over ? dhi : prev);
           const double tm = dl * m;
-          s0 = s0 + tm * r.c0; s1 = s1 + tm * r.c1; s2 = s2 + tm * r.c2;
-          if (q == 0) *(double*)(row + offS + KQ * 16) = r.lam + dl;
-          p1 = p1 + eabs(dl);
+          const double n0 = s0 + tm * r.c0, n1 = s1 + tm * r.c1, n2 = s2 + tm * r.c2;
+          s0 = on ? n0 : s0; s1 = on ? n1 : s1; s2 = on ? n2 : s2;
+          if (on && q == 0) *(double*)(T.slot(i) + offS + KQ * 16) = r.lam + dl;
+          p1 = p1 + (on ? fabs(dl) : 0.0);
+        };
+        LaneRow ra, rb;
+        if (R1max > 0) load_row(T.slot(0), ra);
+        int i = 0;
+        for (; i + 1 < R1max; i += 2) {
+          load_row(T.slot(i + 1), rb);
+          step1(i, ra);
+          load_row(T.slot(min(i + 2, R1max - 1)), ra);
+          step1(i + 1, rb);
         }
+        if (i < R1max) step1(i, ra);
       }
       __syncwarp();
       // sweep 2: velocityFrictionGroup (Solver.elm:869-880, 678-844): friction1 then friction2, cone +-mu*lambda_n; solve2Body
       // keeps ONE running sum through both phases (Solver.elm:473-489), step adds two sums (345-358)
       double p2 = (gn == 1) ? p1 : 0;
-      for (int j = 0; j < R2max; j++) {
-        const bool on = !done && j < R2;
-        unsigned char* row = T.slot(cap_rows - 1 - j);
-        LaneRow r; load_row(row, r);
-        const double nl = *(const double*)(T.slot(on ? r.aux : 0) + offS + KQ * 16);      // the normal lambda of this contact: sweep 1 is complete
-        enter(on, r.desc);
-        const double gw = quad_gw(r.a0, r.a1, r.a2);
-        const double cap = r.mu * nl;
-        const double prev = r.invC * (r.B - gw - eps * r.lam);
-        const double dl = (r.lam + prev + cap < 0) ? -cap - r.lam : ((r.lam + prev - cap > 0) ? cap - r.lam : prev);
-        if (on) {
+      {
+        // a friction row and the normal lambda of its contact (sweep 1 is complete)
+        auto load2 = [&](int j, LaneRow& r, double& nl) {
+          load_row(T.slot(cap_rows - 1 - j), r);
+          nl = *(const double*)(T.slot(j < R2 ? r.aux : 0) + offS + KQ * 16);
+        };
+        auto step2 = [&](int j, const LaneRow& r, double nl) {
+          const bool on = !done && j < R2;
+          const double cap = r.mu * nl;
+          const double el = eps * r.lam, dlo = -cap - r.lam, dhi = cap - r.lam;
+          enter(on, r.desc);
+          const double gw = quad_gw(r.a0, r.a1, r.a2);
+          const double prev = r.invC * (r.B - gw - el);
+          const double sum = r.lam + prev;
+          const bool under = sum + cap < 0, over = sum - cap > 0;
+          const double dl = under ? dlo : (over ? dhi : prev);
           const double tm = dl * m;
-          s0 = s0 + tm * r.c0; s1 = s1 + tm * r.c1; s2 = s2 + tm * r.c2;
-          if (q == 0) *(double*)(row + offS + KQ * 16) = r.lam + dl;
-          p2 = p2 + eabs(dl);
+          const double n0 = s0 + tm * r.c0, n1 = s1 + tm * r.c1, n2 = s2 + tm * r.c2;
+          s0 = on ? n0 : s0; s1 = on ? n1 : s1; s2 = on ? n2 : s2;
+          if (on && q == 0) *(double*)(T.slot(cap_rows - 1 - j) + offS + KQ * 16) = r.lam + dl;
+          p2 = p2 + (on ? fabs(dl) : 0.0);
+        };
+        LaneRow ra, rb; double na = 0, nb2 = 0;
+        if (R2max > 0) load2(0, ra, na);
+        int j = 0;
+        for (; j + 1 < R2max; j += 2) {
+          load2(j + 1, rb, nb2);
+          step2(j, ra, na);
+          load2(min(j + 2, R2max - 1), ra, na);
+          step2(j + 1, rb, nb2);
         }
+        if (j < R2max) step2(j, ra, na);
       }
       __syncwarp();
       if (!done) {
@@ -449,13 +480,16 @@ __global__ void __launch_bounds__(NW * 32) k_solve_qteam(Dev d, int bin_lo, int 
       if (sweep == 2) return d.row_dl + 3 * (size_t)(rc.c0 + (x >> 1)) + 1 + (x & 1);
       return x < rc.jn ? jdl + rc.j0 + x : d.row_dl + 3 * (size_t)(rc.c0 + x - rc.jn);
     };
-    struct TRow { double a0, a1, a2, c0, c1, c2, B, invC, lam, mu, nl; QRow* at; };
+    // a row as the lane sees it; everything that does not hang on the solver bodies -- the bounds, lambda's share of the right-hand
+    // side, the two clamped candidates of delta-lambda, the address of |dlambda| -- is formed when the row is fetched, off the chain
+    struct TRow { double a0, a1, a2, c0, c1, c2, B, invC, lam, lo, hi, el, dlo, dhi; QRow* at; double* dlp; };
     auto load_trow = [&](QRow* R, TRow& o) {
       o.a0 = R->a[0][q]; o.a1 = R->a[1][q]; o.a2 = R->a[2][q];
       o.c0 = o.a0; o.c1 = o.a1; o.c2 = o.a2;
       if (angular) { o.c0 = R->c[0][q >> 1]; o.c1 = R->c[1][q >> 1]; o.c2 = R->c[2][q >> 1]; }
       const double2 bi = *(const double2*)&R->B, lm = *(const double2*)&R->lam;
-      o.B = bi.x; o.invC = bi.y; o.lam = lm.x; o.mu = lm.y; o.nl = 0; o.at = R;
+      o.B = bi.x; o.invC = bi.y; o.lam = lm.x; o.lo = lm.y /* mu, until the caller turns it into the bounds */; o.hi = 0; o.at = R; o.dlp = nullptr;
+      o.el = 0; o.dlo = 0; o.dhi = 0;
     };
     QTeamRec none; none.lb1 = 0; none.lb2 = 0; none.c0 = 0; none.cn = 0; none.j0 = 0; none.jn = 0; none.row0 = 0; none.enum_pos = 0;
     // warm start (applyContactsWarmStart, Solver.elm:102-119), levels descending; joint rows and rows with lambda 0 are skipped (41)
@@ -493,26 +527,33 @@ __global__ void __launch_bounds__(NW * 32) k_solve_qteam(Dev d, int bin_lo, int 
             if (nmax == 0) continue;
             const int mine = (q < 2) ? rc.lb1 : rc.lb2;
             double s0, s1, s2, m; load_half(mine, s0, s1, s2, m);
-            // one row: G.W from the quad's four partials (Solver.elm:642-646), clamp, update of this lane's half
+            // one row: G.W from the quad's four partials (Solver.elm:642-646), clamp, update of this lane's half -- without a branch:
+            // selects between candidates that exist before G.W does, a predicated store by the quad's first lane
             auto solve_row = [&](int x, const TRow& r) {
               const bool on = x < n;
               const double p = (r.a0 * s0 + r.a1 * s1) + r.a2 * s2;
               const double p0 = __shfl_sync(full, p, qb), p1 = __shfl_sync(full, p, qb + 1), p2 = __shfl_sync(full, p, qb + 2), p3 = __shfl_sync(full, p, qb + 3);
               const double gw = ((p0 + p1) + p2) + p3;
-              const double cap = r.mu * r.nl;
-              const double lo = sweep == 2 ? -cap : (x < rc.jn ? -kMaxImpulse : 0.0), hi = sweep == 2 ? cap : kMaxImpulse;
-              const double prev = r.invC * (r.B - gw - eps * r.lam);
-              const double dl = (r.lam + prev - lo < 0) ? lo - r.lam : ((r.lam + prev - hi > 0) ? hi - r.lam : prev);
-              if (on) {
-                const double tm = dl * m;
-                s0 = s0 + tm * r.c0; s1 = s1 + tm * r.c1; s2 = s2 + tm * r.c2;
-                if (q == 0) { r.at->lam = r.lam + dl; *dl_ref(rc, sweep, x) = eabs(dl); part += eabs(dl); }
-              }
+              const double prev = r.invC * (r.B - gw - r.el);
+              const double sum = r.lam + prev;
+              const bool under = sum - r.lo < 0, over = sum - r.hi > 0;
+              const double dl = under ? r.dlo : (over ? r.dhi : prev);
+              const double tm = dl * m;
+              const double n0 = s0 + tm * r.c0, n1 = s1 + tm * r.c1, n2 = s2 + tm * r.c2;
+              s0 = on ? n0 : s0; s1 = on ? n1 : s1; s2 = on ? n2 : s2;
+              const double ad = fabs(dl);
+              const bool wr = on && q == 0;
+              part += wr ? ad : 0.0;
+              if (wr) { r.at->lam = r.lam + dl; *r.dlp = ad; }
             };
             // a row and, for a friction row, the normal lambda of its contact (sweep 1 is complete when sweep 2 runs)
             auto fetch = [&](int x, TRow& o) {
               load_trow(row_ptr(rc, sweep, x), o);
-              if (sweep == 2) o.nl = row_ptr(rc, 1, rc.jn + (x >> 1))->lam;
+              const double mu = o.lo;
+              if (sweep == 2) { const double cap = mu * row_ptr(rc, 1, rc.jn + (x >> 1))->lam; o.lo = -cap; o.hi = cap; }
+              else { o.lo = x < rc.jn ? -kMaxImpulse : 0.0; o.hi = kMaxImpulse; }
+              o.el = eps * o.lam; o.dlo = o.lo - o.lam; o.dhi = o.hi - o.lam;
+              o.dlp = dl_ref(rc, sweep, x);
             };
             TRow ra, rb;
             fetch(0, ra);             // a quad without rows reads row 0 of an empty record: a valid address, never used
