@@ -264,7 +264,8 @@ def main():
     ap.add_argument("--car-steps", type=int, default=20)
     ap.add_argument("--preroll", type=int, default=120, help="untimed steps that drop and pile the bodies first")
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-contexts", type=int, default=2, help="sub-batches (contexts + host threads) of the end-to-end measurement")
+    ap.add_argument("--e2e-contexts", type=int, default=0,
+                    help="sub-batches (contexts + host threads) of the end-to-end measurement; 0 = by shard size (2 above 4096 worlds per GPU, else 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pile", action="store_true", help="skip the second half of BASELINE's metric (ms/step of the 2k-body convex pile)")
     ap.add_argument("--pile-preroll", type=int, default=600)
@@ -433,7 +434,9 @@ def main():
     # The same call on K contexts of W/K worlds each, one host thread per context (ctypes releases the GIL): the H2D of one
     # sub-batch, the step of another and the D2H of a third overlap (PCIe is full duplex, two copy engines), which is how a
     # host that owns several independent world batches would drive one GPU.  This is the headline e2e.
-    K = max(1, min(args.e2e_contexts, W))
+    # Measured (gpurun_out/s4/ksweep.txt, B200): a shard of 1024 / 4096 worlds runs 28.7 / 52.8 M body-steps/s as ONE context against
+    # 26.8 / 49.7 M as two (both halves sit on the step's latency floor, so splitting doubles it); at 8192 worlds two contexts win (77 vs 67 M).
+    K = max(1, min(args.e2e_contexts if args.e2e_contexts > 0 else (2 if W > 4096 else 1), W))
 
     def pipelined(fields, up=None, down=None):
         subs = []
@@ -587,8 +590,9 @@ def main():
                 "call": "ep_step_frame_fields(pinned host buffers): H2D of the bodies' dynamic state (transform + velocities; pos / quat "
                         "ahead of the front kernels, the rest beside them), one step warm-started by the resident previous frame, D2H "
                         "of the integrated state + the contact data Physics.contactPoints reads (pair ids, pre-step body1 frames, "
-                        "contact points; marshalled and copied beside the solver); each rank drives its shard as %d contexts from %d "
-                        "host threads so that copies and steps of different sub-batches overlap" % (K, K),
+                        "contact points; marshalled and copied beside the solver); each rank drives its shard as %d context(s) from %d "
+                        "host thread(s) (two above 4096 worlds per GPU, so that copies and steps of different sub-batches overlap; one "
+                        "below, where a half shard would sit on the same latency floor as the whole)" % (K, K),
                 "contexts": K, "every_array_value": e2e_full, "every_array_h2d_bytes_per_step": int(h2d_full),
                 "every_array_d2h_bytes_per_step": int(d2h_full),
                 "single_context_every_array_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
