@@ -285,6 +285,15 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     bind_to_gpu_numa_node(local_rank)
+    # How the host waits for a frame (EP_BLOCKING_SYNC, read once by the library): sleeping on an event costs a wake-up of 30-50 us
+    # per wait, three waits per frame -- 10 % of a 1024-world frame (26.8 -> 29.5 M body-steps/s end to end, gpurun_out/s4) and
+    # nothing at 8192 worlds.  Spin when every driving thread of the box can have four cores to itself; otherwise (many ranks on
+    # few cores) keep the library's default, the sleeping wait that the 8-GPU box of round 1 needed.
+    local_ranks = env_int("LOCAL_WORLD_SIZE", world_size)
+    host_threads = local_ranks * (2 if -(-args.worlds // world_size) > 4096 else 1)
+    if "EP_BLOCKING_SYNC" not in os.environ and 4 * host_threads <= (os.cpu_count() or 1):
+        os.environ["EP_BLOCKING_SYNC"] = "0"
+    host_wait = "spin" if os.environ.get("EP_BLOCKING_SYNC") == "0" else "sleep"
     if world_size > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
@@ -592,7 +601,8 @@ def main():
                         "of the integrated state + the contact data Physics.contactPoints reads (pair ids, pre-step body1 frames, "
                         "contact points; marshalled and copied beside the solver); each rank drives its shard as %d context(s) from %d "
                         "host thread(s) (two above 4096 worlds per GPU, so that copies and steps of different sub-batches overlap; one "
-                        "below, where a half shard would sit on the same latency floor as the whole)" % (K, K),
+                        "below, where a half shard would sit on the same latency floor as the whole); host waits: %s" % (K, K, host_wait),
+                "host_wait": host_wait,
                 "contexts": K, "every_array_value": e2e_full, "every_array_h2d_bytes_per_step": int(h2d_full),
                 "every_array_d2h_bytes_per_step": int(d2h_full),
                 "single_context_every_array_value": e2e_single, "bit_exact_vs_oracle_32_worlds": e2e_parity},
