@@ -316,6 +316,7 @@ EPD void sphere_convex(bool flip, const Sph& s, const Cvx& c, ContactSink& out) 
 // =>  <= 15 * 2^-24 * D < 9e-7 D per value, < 2e-6 D per overlap (a difference of two values).  kScrE doubles that.
 // Screening only skips work: every value that is USED is the exact fp64 one.
 constexpr int kScrVerts = 32;
+constexpr int kScrEdges = 24;     // edge directions per hull the screened SAT takes (a 12-gon cone has 18); axes go through it 64 at a time
 constexpr double kScrE = 4.0e-6;
 struct Scr { float4 r[kScrVerts]; int nv; };      // (x, y, z, -) per vertex: one 16 B local load each
 EPD void scr_build(Scr& s, const Cvx& c, V3 o, double& D) {
@@ -524,7 +525,7 @@ EPD bool convex_sat(const Cvx& c1, const Cvx& c2, SatResult& R, int& sep) {
   return true;
 }
 // The same verdict and the same winners with the axes screened in fp32 first (see above).  For two non-box hulls of at most
-// kScrVerts vertices, 32 face groups and 8 x 8 edge directions.
+// kScrVerts vertices, 32 face groups and kScrEdges edge directions each.
 EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R, int& sep) {
   const V3 so = c1.pos();
   Scr s1, s2; double sD = 0;
@@ -586,59 +587,69 @@ EPD bool convex_sat_screened(const Cvx& c1, const Cvx& c2, SatResult& R, int& se
   // ---- edge axes, pass 1: axis e = a * ne2 + b
   R.edgeBeats = false; R.eAxis = mk(0, 0, 0); R.dir1 = 0; R.dir2 = 0;
   double emin_ = R.dmin / 1.05;
-  double d2s[3 * 8]; unsigned ok2 = 0;
+  double d2s[3 * kScrEdges]; unsigned ok2 = 0;
   for (int b = 0; b < c2.ne; b++) {
     int n2; const int* e2 = c2.edges(b, n2);
     if (n2 < 2) continue;
     const V3 d2 = vdirection(c2.vert(e2[0]), c2.vert(e2[1]));
     d2s[3 * b] = d2.x; d2s[3 * b + 1] = d2.y; d2s[3 * b + 2] = d2.z; ok2 |= 1u << b;
   }
-  unsigned long long emask = 0; thr = emin_;
-  {
-    auto edge_est = [&](float lo1, float hi1, float lo2, float hi2) -> double {
-      const double x = (double)hi1 - (double)lo2, y = (double)hi2 - (double)lo1;
-      return (x - y > 0) ? y : x;
-    };
-    auto apply = [&](int e, double est) {
-      if (!(est - 2 * sE > thr)) emask |= 1ull << e;
-      if (est + 2 * sE < thr) thr = est + 2 * sE;
-    };
-    for (int a = 0; a < c1.ne; a++) {
-      int n1; const int* e1 = c1.edges(a, n1);
-      if (n1 < 2) continue;
-      const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
-      // the valid axes of this row two at a time (each vertex of a copy is loaded once per pair); estimates applied in ascending b
-      int pb = -1; V3 pn = mk(0, 0, 0);                 // a valid axis waiting for a partner
-      for (int b = 0; b < c2.ne; b++) {
-        if (!((ok2 >> b) & 1u)) continue;
-        const V3 cr = vcross(d1, mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2]));
-        if (valmost0(cr)) continue;
-        const V3 n = vnormalize(cr);
-        if (pb < 0) { pb = b; pn = n; continue; }
-        float l1a, h1a, l1b, h1b, l2a, h2a, l2b, h2b;
-        scr_project2(s1, pn, n, l1a, h1a, l1b, h1b); scr_project2(s2, pn, n, l2a, h2a, l2b, h2b);
-        apply(a * c2.ne + pb, edge_est(l1a, h1a, l2a, h2a));
-        apply(a * c2.ne + b, edge_est(l1b, h1b, l2b, h2b));
-        pb = -1;
-      }
-      if (pb >= 0) {
-        float lo1, hi1, lo2, hi2; scr_project(s1, pn, lo1, hi1); scr_project(s2, pn, lo2, hi2);
-        apply(a * c2.ne + pb, edge_est(lo1, hi1, lo2, hi2));
+  // The rows of convex1's directions go through the two passes in blocks of at most 64 axes (the survivor mask): pass 2 of a
+  // block runs before pass 1 of the next, so the survivors still come in the reference's order, and every threshold in use (the
+  // exact running minimum, or a screened estimate + its error bound) is an upper bound of the final minimum as before.
+  thr = emin_;
+  const int rows = 64 / c2.ne;                           // >= 2 (ne <= kScrEdges)
+  for (int a0 = 0; a0 < c1.ne; a0 += rows) {
+    const int a1 = min(c1.ne, a0 + rows);
+    unsigned long long emask = 0;
+    {
+      auto edge_est = [&](float lo1, float hi1, float lo2, float hi2) -> double {
+        const double x = (double)hi1 - (double)lo2, y = (double)hi2 - (double)lo1;
+        return (x - y > 0) ? y : x;
+      };
+      auto apply = [&](int e, double est) {
+        if (!(est - 2 * sE > thr)) emask |= 1ull << e;
+        if (est + 2 * sE < thr) thr = est + 2 * sE;
+      };
+      for (int a = a0; a < a1; a++) {
+        int n1; const int* e1 = c1.edges(a, n1);
+        if (n1 < 2) continue;
+        const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
+        const int bit0 = (a - a0) * c2.ne;
+        // the valid axes of this row two at a time (each vertex of a copy is loaded once per pair); estimates applied in ascending b
+        int pb = -1; V3 pn = mk(0, 0, 0);                 // a valid axis waiting for a partner
+        for (int b = 0; b < c2.ne; b++) {
+          if (!((ok2 >> b) & 1u)) continue;
+          const V3 cr = vcross(d1, mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2]));
+          if (valmost0(cr)) continue;
+          const V3 n = vnormalize(cr);
+          if (pb < 0) { pb = b; pn = n; continue; }
+          float l1a, h1a, l1b, h1b, l2a, h2a, l2b, h2b;
+          scr_project2(s1, pn, n, l1a, h1a, l1b, h1b); scr_project2(s2, pn, n, l2a, h2a, l2b, h2b);
+          apply(bit0 + pb, edge_est(l1a, h1a, l2a, h2a));
+          apply(bit0 + b, edge_est(l1b, h1b, l2b, h2b));
+          pb = -1;
+        }
+        if (pb >= 0) {
+          float lo1, hi1, lo2, hi2; scr_project(s1, pn, lo1, hi1); scr_project(s2, pn, lo2, hi2);
+          apply(bit0 + pb, edge_est(lo1, hi1, lo2, hi2));
+        }
       }
     }
-  }
-  // ---- edge axes, pass 2
-  while (emask) {
-    const int e = __ffsll((long long)emask) - 1; emask &= emask - 1;
-    const int a = e / c2.ne, b = e - a * c2.ne;
-    int n1; const int* e1 = c1.edges(a, n1);
-    const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
-    const V3 n = vnormalize(vcross(d1, mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2])));
-    double mn1, mx1, mn2, mx2, dist;
-    project_convex(n, c1, mn1, mx1);
-    project_convex(n, c2, mn2, mx2);
-    if (!overlap(mn1, mx1, mn2, mx2, dist)) { sep = c1.ng + c2.ng + e; return false; }       // EdgeSeparates
-    if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
+    // ---- edge axes, pass 2
+    while (emask) {
+      const int bit = __ffsll((long long)emask) - 1; emask &= emask - 1;
+      const int a = a0 + bit / c2.ne, b = bit % c2.ne;
+      int n1; const int* e1 = c1.edges(a, n1);
+      const V3 d1 = vdirection(c1.vert(e1[0]), c1.vert(e1[1]));
+      const V3 n = vnormalize(vcross(d1, mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2])));
+      double mn1, mx1, mn2, mx2, dist;
+      project_convex(n, c1, mn1, mx1);
+      project_convex(n, c2, mn2, mx2);
+      if (!overlap(mn1, mx1, mn2, mx2, dist)) { sep = c1.ng + c2.ng + a * c2.ne + b; return false; }       // EdgeSeparates
+      if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
+    }
+    if (emin_ < thr) thr = emin_;
   }
   return true;
 }
@@ -700,7 +711,7 @@ template <bool MAY_SCREEN>
 EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
   SatResult R;
   const bool screened = MAY_SCREEN && !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
-                        c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
+                        c1.ng + c2.ng <= 32 && c1.ne <= kScrEdges && c2.ne <= kScrEdges && c1.ne > 0 && c2.ne > 0;
   if (sat_axis_separates(c1, c2, out.hint)) { out.sep = out.hint; return; }      // still apart along last frame's axis
   bool hit;
   if (MAY_SCREEN) hit = screened ? convex_sat_screened(c1, c2, R, out.sep) : convex_sat(c1, c2, R, out.sep);
@@ -834,7 +845,7 @@ EPD bool convex_sat_screened_quad(const Cvx& c1, const Cvx& c2, SatResult& R, in
   // ---- edge axes, pass 1: axis e = a * ne2 + b, pairs (2p, 2p + 1) to lane p & 3
   R.edgeBeats = false; R.eAxis = mk(0, 0, 0); R.dir1 = 0; R.dir2 = 0;
   double emin_ = R.dmin / 1.05;
-  double d1s[3 * 8], d2s[3 * 8]; unsigned ok1 = 0, ok2 = 0;
+  double d1s[3 * kScrEdges], d2s[3 * kScrEdges]; unsigned ok1 = 0, ok2 = 0;
   for (int a = 0; a < c1.ne; a++) {
     int n1; const int* e1 = c1.edges(a, n1);
     if (n1 < 2) continue;
@@ -847,6 +858,10 @@ EPD bool convex_sat_screened_quad(const Cvx& c1, const Cvx& c2, SatResult& R, in
     const V3 d2 = vdirection(c2.vert(e2[0]), c2.vert(e2[1]));
     d2s[3 * b] = d2.x; d2s[3 * b + 1] = d2.y; d2s[3 * b + 2] = d2.z; ok2 |= 1u << b;
   }
+  // 64 axes (one survivor mask) at a time, pass 2 of a block before pass 1 of the next: see convex_sat_screened
+  const int ne = c1.ne * c2.ne;
+  for (int base = 0; base < ne; base += 64) {
+  const int lim = min(ne, base + 64);
   unsigned long long emask = 0;
   {
     double estv[16]; int ev[16]; int cnt = 0; double thr = emin_;
@@ -866,19 +881,18 @@ EPD bool convex_sat_screened_quad(const Cvx& c1, const Cvx& c2, SatResult& R, in
       n = vnormalize(cr);
       return true;
     };
-    const int ne = c1.ne * c2.ne;
-    for (int e0 = 2 * q; e0 < ne; e0 += 8) {
+    for (int e0 = base + 2 * q; e0 < lim; e0 += 8) {
       V3 na = mk(0, 0, 0), nb = mk(0, 0, 0);
-      const bool va = axis_of(e0, na), vb = e0 + 1 < ne && axis_of(e0 + 1, nb);
+      const bool va = axis_of(e0, na), vb = e0 + 1 < lim && axis_of(e0 + 1, nb);
       if (va && vb) {
         float l1a, h1a, l1b, h1b, l2a, h2a, l2b, h2b;
         scr_project2(s1, na, nb, l1a, h1a, l1b, h1b); scr_project2(s2, na, nb, l2a, h2a, l2b, h2b);
-        keep(e0, edge_est(l1a, h1a, l2a, h2a));
-        keep(e0 + 1, edge_est(l1b, h1b, l2b, h2b));
+        keep(e0 - base, edge_est(l1a, h1a, l2a, h2a));
+        keep(e0 + 1 - base, edge_est(l1b, h1b, l2b, h2b));
       } else if (va || vb) {
         const V3 n = va ? na : nb;
         float lo1, hi1, lo2, hi2; scr_project(s1, n, lo1, hi1); scr_project(s2, n, lo2, hi2);
-        keep(va ? e0 : e0 + 1, edge_est(lo1, hi1, lo2, hi2));
+        keep((va ? e0 : e0 + 1) - base, edge_est(lo1, hi1, lo2, hi2));
       }
     }
     thr = quad_min(thr, qm);
@@ -890,7 +904,7 @@ EPD bool convex_sat_screened_quad(const Cvx& c1, const Cvx& c2, SatResult& R, in
   }
   // ---- edge axes, pass 2
   while (emask) {
-    const int e = __ffsll((long long)emask) - 1; emask &= emask - 1;
+    const int e = base + __ffsll((long long)emask) - 1; emask &= emask - 1;
     const int a = e / c2.ne, b = e - a * c2.ne;
     const V3 n = vnormalize(vcross(mk(d1s[3 * a], d1s[3 * a + 1], d1s[3 * a + 2]), mk(d2s[3 * b], d2s[3 * b + 1], d2s[3 * b + 2])));
     double mn1, mx1, mn2, mx2, dist;
@@ -899,12 +913,13 @@ EPD bool convex_sat_screened_quad(const Cvx& c1, const Cvx& c2, SatResult& R, in
     if (!overlap(mn1, mx1, mn2, mx2, dist)) { sep = c1.ng + c2.ng + e; return false; }       // EdgeSeparates
     if (dist - emin_ < 0) { R.edgeBeats = true; R.eAxis = n; R.dir1 = a + 1; R.dir2 = b + 1; emin_ = dist; }
   }
+  }
   return true;
 }
 // one hull pair by the four lanes of a quad; `out` of lane 0 receives the contacts, hint must be the same in all four lanes
 EPD void convex_convex_quad(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow, int q, unsigned qm) {
   const bool screened = !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
-                        c1.ng + c2.ng <= 32 && c1.ne <= 8 && c2.ne <= 8;
+                        c1.ng + c2.ng <= 32 && c1.ne <= kScrEdges && c2.ne <= kScrEdges && c1.ne > 0 && c2.ne > 0;
   if (!screened) { if (q == 0) convex_convex_t<true>(c1, c2, out, pa, pb, polyOverflow); return; }      // the one-lane path
   if (sat_axis_separates_quad(c1, c2, out.hint, q, qm)) { out.sep = out.hint; return; }
   SatResult R;
