@@ -415,10 +415,13 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   // world-placed shape blocks + placement work items (moving bodies first)
   const int ns = (int)ctx->h_sh_kind.size();
   std::vector<int64_t> woff(ni);
+  std::vector<int32_t> inst_sub(std::max(ni, 1));
   int64_t wtotal = 0;
   for (int k = 0; k < ni; k++) {
     int s = B->inst_shape[k];
     if (s < 0 || s >= ns) { ctx->err = "shape index out of range"; return EP_EINVAL; }
+    const int kind = ctx->h_sh_kind[s];
+    inst_sub[k] = kind == SH_CONVEX ? (ctx->h_sh_i32[ctx->h_sh_i32_off[s]] != 0 ? 0 : 1) : kind + 1;
     woff[k] = wtotal;
     wtotal += ctx->h_sh_f64_off[s + 1] - ctx->h_sh_f64_off[s];
   }
@@ -443,6 +446,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
   }
   d.n_pl_moving = n_moving; d.n_pl_all = (int)pl_inst.size();
   TRY(dev_upload(ctx, pool, &d.inst_woff, woff.data(), ni));
+  TRY(dev_upload(ctx, pool, &d.inst_sub, inst_sub.data(), ni));
   TRY(dev_upload_rw(ctx, pool, &d.wf64, wf.data(), wf.size()));
   TRY(dev_upload(ctx, pool, &d.pl_inst, pl_inst.data(), pl_inst.size()));
   TRY(dev_upload(ctx, pool, &d.pl_code, pl_code.data(), pl_code.size()));

@@ -101,6 +101,7 @@ struct Dev {
   double *pos, *quat, *vel, *angvel, *force, *torque, *iiw;
   const double *inv_mass, *inv_inertia, *ldp, *adp, *lin_lock, *ang_lock, *radius;
   const int32_t* inst_off; const int32_t* inst_shape; const int32_t* inst_body;
+  const int32_t* inst_sub;    // [n_insts] narrowphase sub-kind of the instance's shape (box 0, other hull 1, plane 2, sphere 3, capsule 4, particle 5): fixed per batch
   const double* inst_friction; const double* inst_bounciness;
   const int64_t* inst_woff;   // world-placed f64 block of each instance (same layout as its template)
   double* wf64;

@@ -131,10 +131,9 @@ __device__ __forceinline__ int depth_bin(const Dev& d, int w, int r1, int r2) {
 
 // Work-item classes: shape sub-kind = convex box 0, convex other 1, plane 2, sphere 3, capsule 4, particle 5;
 // class = lo * 6 + hi of the unordered pair, so every lane of a warp in k_narrowphase runs the same Collision.* module.
-__device__ __forceinline__ int shape_subkind(const Dev& d, int inst) {
-  int sh = d.inst_shape[inst], k = d.sh_kind[sh];
-  return k == SH_CONVEX ? (d.sh_i32[d.sh_i32_off[sh]] != 0 ? 0 : 1) : k + 1;
-}
+// (one load: the table is filled by ep_upload_worlds from sh_kind / the hull's box flag -- three dependent loads per shape, and a
+// pair of compound bodies walks ns1 x ns2 shape pairs in k_bp_count and again in k_bp_emit)
+__device__ __forceinline__ int shape_subkind(const Dev& d, int inst) { return d.inst_sub[inst]; }
 __device__ __forceinline__ int item_class(int ka, int kb) { return ka < kb ? ka * 6 + kb : kb * 6 + ka; }
 // classes in descending expected cost: the work list starts the long items first
 __constant__ int kClassOrder[kClasses] = {7, 1, 10, 0, 4, 9, 8, 3, 2, 22, 28, 21, 16, 11, 5, 29, 17, 23, 35, 14, 15, 20, 6, 12, 13, 18, 19, 24, 25, 26, 27, 30, 31, 32, 33, 34};
