@@ -545,10 +545,14 @@ def main():
         ec.upload_worlds(cb_r, cp_r, None)
         nwc = cb_r.n_worlds
         chassis = (cb_r.world_body_off[:nwc] + 2).astype(np.int32)
-        ray_body = np.repeat(chassis, 4)
         corners = np.array([[-1.0, 1.9, -0.25], [1.0, 1.9, -0.25], [-1.0, -1.9, -0.25], [1.0, -1.9, -0.25]])
-        lf = np.tile(corners, (nwc, 1))
-        ld = np.tile(np.array([[0.0, 0.0, -1.0]]), (4 * nwc, 1))
+        # the host side of the casts on page-locked memory, like the frame buffers of the e2e leg (pageable arrays go through the
+        # driver's staging buffer at a fifth of the PCIe rate: 3.1 ms per 262144 rays)
+        ray_body, lf, ld = pool.empty(4 * nwc, np.int32), pool.empty((4 * nwc, 3), np.float64), pool.empty((4 * nwc, 3), np.float64)
+        ray_body[:] = np.repeat(chassis, 4)
+        lf[:] = np.tile(corners, (nwc, 1))
+        ld[:] = np.array([0.0, 0.0, -1.0])
+        ec.ray_alloc = pool.empty
         for _ in range(30):
             ec.step_resident(1)
             ec.raycast_attached(ray_body, lf, ld)
@@ -581,7 +585,7 @@ def main():
                 "body_steps_per_sec_steps_only_device_time": CT * dyn_per_world * args.car_steps / (cms * 1e-3),
                 "ms_per_step_steps_only": cms / args.car_steps,
                 "ray_hit_fraction": sum_over_ranks(hits) / (4.0 * CT * args.car_steps),
-                "ray_io": "ep_raycast_attached: host buffers in (13.6 MB per 262144 rays) and out (15.7 MB), synchronous, every step"}
+                "ray_io": "ep_raycast_attached: pinned host buffers in (13.6 MB per 262144 rays) and out (15.7 MB), synchronous, every step"}
         ec.close()
         del cs, cb_r, cp_r
 
