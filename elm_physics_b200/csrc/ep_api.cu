@@ -694,7 +694,11 @@ extern "C" int ep_step_resident(ep_ctx* ctx, int32_t n_steps) {
     {
       CK(cudaMemsetAsync(d.cur.pair_slot, 0xFF, (size_t)d.slot_cap * sizeof(int32_t), st));
       if (d.n_pl_moving > 0) { Timed t(ctx, EP_K_PLACE); k_place<<<grid_for(ctx, d.n_pl_moving, 256, 16), 256, 0, st>>>(d, d.n_pl_moving); }
-      { Timed t(ctx, EP_K_SORT); k_sort<<<gw, d.nb_max <= 128 ? 128 : (d.nb_max <= 512 ? 256 : 1024), 0, st>>>(d); }
+      { Timed t(ctx, EP_K_SORT);
+        if (d.nb_max > 256 && (size_t)d.nb_max * sizeof(double) <= 48 * 1024) {      // large worlds: several CTAs per world
+          const int parts = (d.nb_max + 127) / 128;
+          k_sort_wide<<<(int)std::min<int64_t>((int64_t)d.n_worlds * parts, (int64_t)ctx->sm_count * 64), 128, (size_t)d.nb_max * sizeof(double), st>>>(d, parts);
+        } else k_sort<<<gw, d.nb_max <= 128 ? 128 : (d.nb_max <= 512 ? 256 : 1024), 0, st>>>(d); }
       { Timed t(ctx, EP_K_BROADPHASE);
         const int gc = std::max(1, std::min(d.n_chunks, ctx->sm_count * 16));
         k_bp_count<<<gc, 128, 0, st>>>(d);

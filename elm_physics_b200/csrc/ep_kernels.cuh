@@ -66,6 +66,37 @@ __global__ void k_sort(Dev d) {
   }
 }
 
+// The same sort for worlds of hundreds to thousands of bodies (config 4: one world of 2005 -- the one-CTA rank sort above walks
+// 2005 keys per body on ONE SM, 0.18 ms): the ranks of different bodies are independent, so `parts` CTAs share a world, 128 bodies
+// each, every CTA with its own copy of the world's keys in shared memory (same expression, same bits).
+__global__ void __launch_bounds__(128) k_sort_wide(Dev d, int parts) {
+  extern __shared__ double s_key[];
+  for (int wp = blockIdx.x; wp < d.n_worlds * parts; wp += gridDim.x) {
+    const int w = wp / parts, part = wp - w * parts;
+    const int r0 = d.world_body_off[w], n = d.world_body_off[w + 1] - r0;
+    if (part * 128 >= n) continue;                  // the whole CTA together
+    const V3 g = ld3(d.gravity + 3 * w);
+    for (int j = threadIdx.x; j < n; j += 128) {
+      const V3 p = ld3(d.pos + 3 * (r0 + j));
+      s_key[j] = -(p.x * g.x + p.y * g.y + p.z * g.z);
+    }
+    __syncthreads();
+    const int i = part * 128 + threadIdx.x;
+    if (i < n) {
+      const double a = s_key[i];
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
+        const double b = s_key[j];
+        const bool lt = b - a < 0, gt = b - a > 0;          // Physics.elm:563-571
+        rank += (lt || (!gt && j < i)) ? 1 : 0;
+      }
+      d.sorted[r0 + rank] = r0 + i;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- k_broadphase -------------------------------------------------------------------------------------
 __device__ __forceinline__ void pair_from_index(int64_t p, int n, int& i, int& j) {
   if (n <= 1024) {      // everything below is exact in fp32 / int32 (t*t, 8p < 2^23); the two loops fix a sqrt off by one
