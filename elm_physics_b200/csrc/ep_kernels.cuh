@@ -868,6 +868,17 @@ __device__ __forceinline__ int island_key(int bin, int rows, int pred_iters, int
 __device__ __forceinline__ int uf_root(volatile int* parent, int x) {
   for (;;) { int p = parent[x]; if (p == x) return x; x = p; }
 }
+// The same with path halving, for the union phase only: a non-root never becomes a root again and the CAS below only ever
+// changes roots, so pointing x at its grandparent (still an ancestor) races with nothing that matters; the component's root stays
+// its minimum id.  Without it the one giant island of config 4 (1900 bodies linked by minimum id) grows chains hundreds of
+// hops deep and every find walks them (k_islands 0.36 ms, most of it here).  NOT for the flatten pass, whose result must be a root.
+__device__ __forceinline__ int uf_root_halving(volatile int* parent, int x) {
+  for (;;) {
+    const int p = parent[x]; if (p == x) return x;
+    const int gp = parent[p]; if (gp == p) return p;
+    parent[x] = gp; x = gp;
+  }
+}
 __global__ void k_islands(Dev d, int use_smem) {
   extern __shared__ int s_isl[];           // [3][nb_max] parent / count / fill when the largest world fits
   __shared__ int s_scan[33];
@@ -891,7 +902,7 @@ __global__ void k_islands(Dev d, int use_smem) {
       if (d.kind[ra] != 2 || d.kind[rb] != 2) continue;
       int a = ra - r0, b = rb - r0;
       for (;;) {
-        a = uf_root(parent, a); b = uf_root(parent, b);
+        a = uf_root_halving(parent, a); b = uf_root_halving(parent, b);
         if (a == b) break;
         const int ia = d.body_id[r0 + a], ib = d.body_id[r0 + b];
         const int win = (ia - ib < 0) ? a : b, lose = (ia - ib < 0) ? b : a;
