@@ -710,7 +710,10 @@ EPD void convex_contacts_from_sat(const Cvx& c1, const Cvx& c2, const SatResult&
 template <bool MAY_SCREEN>
 EPD void convex_convex_t(const Cvx& c1, const Cvx& c2, ContactSink& out, TagPt* pa, TagPt* pb, bool& polyOverflow) {
   SatResult R;
-  const bool screened = MAY_SCREEN && !c1.box && !c2.box && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
+  // (a box against another hull is screened too: the fp32 copy of its eight placed corners bounds the exact centre +- extent
+  // projection of pass 2 like any other hull's -- the corners and the axes come from the same transform, rounding apart; two boxes
+  // have 15 axes and are not worth the copies)
+  const bool screened = MAY_SCREEN && !(c1.box && c2.box) && c1.nv <= kScrVerts && c2.nv <= kScrVerts && c1.nv > 0 && c2.nv > 0 &&
                         c1.ng + c2.ng <= 32 && c1.ne <= kScrEdges && c2.ne <= kScrEdges && c1.ne > 0 && c2.ne > 0;
   if (sat_axis_separates(c1, c2, out.hint)) { out.sep = out.hint; return; }      // still apart along last frame's axis
   bool hit;
