@@ -290,8 +290,8 @@ def main():
     # nothing at 8192 worlds.  Spin when every driving thread of the box can have four cores to itself; otherwise (many ranks on
     # few cores) keep the library's default, the sleeping wait that the 8-GPU box of round 1 needed.
     local_ranks = env_int("LOCAL_WORLD_SIZE", world_size)
-    host_threads = local_ranks * (2 if -(-args.worlds // world_size) > 4096 else 1)
-    if "EP_BLOCKING_SYNC" not in os.environ and 4 * host_threads <= (os.cpu_count() or 1):
+    driving_threads = local_ranks * (2 if -(-args.worlds // world_size) > 4096 else 1)
+    if "EP_BLOCKING_SYNC" not in os.environ and 4 * driving_threads <= (os.cpu_count() or 1):
         os.environ["EP_BLOCKING_SYNC"] = "0"
     host_wait = "spin" if os.environ.get("EP_BLOCKING_SYNC") == "0" else "sleep"
     if world_size > 1:
