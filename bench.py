@@ -229,6 +229,19 @@ def emit(line):
     _REAL_STDOUT.flush()
 
 
+def e2e_contexts_for(worlds_per_gpu, requested=0):
+    """Sub-batches (contexts + host threads) one rank drives its shard with in the end-to-end leg: `requested` if given, else two
+    above 4096 worlds per GPU and one below (profiles/r02_e2e_contexts_sweep.txt); never more than the shard has worlds."""
+    k = requested if requested > 0 else (2 if worlds_per_gpu > 4096 else 1)
+    return max(1, min(k, worlds_per_gpu))
+
+
+def host_waits_spin(worlds_total, world_size, local_ranks, cpu_count):
+    """Spin in the host waits of a frame when every driving thread of the box can have four cores to itself."""
+    per_gpu = -(-worlds_total // max(world_size, 1))
+    return 4 * local_ranks * e2e_contexts_for(per_gpu) <= cpu_count
+
+
 def bind_to_gpu_numa_node(device_index):
     """Run this rank (and the pinned buffers it allocates: first touch) on the CPUs next to its GPU, so that the host<->device
     copies of an 8-GPU box do not cross the socket interconnect.  Best effort; EP_BENCH_NO_BIND=1 disables."""
@@ -290,8 +303,7 @@ def main():
     # nothing at 8192 worlds.  Spin when every driving thread of the box can have four cores to itself; otherwise (many ranks on
     # few cores) keep the library's default, the sleeping wait that the 8-GPU box of round 1 needed.
     local_ranks = env_int("LOCAL_WORLD_SIZE", world_size)
-    driving_threads = local_ranks * (2 if -(-args.worlds // world_size) > 4096 else 1)
-    if "EP_BLOCKING_SYNC" not in os.environ and 4 * driving_threads <= (os.cpu_count() or 1):
+    if "EP_BLOCKING_SYNC" not in os.environ and host_waits_spin(args.worlds, world_size, local_ranks, os.cpu_count() or 1):
         os.environ["EP_BLOCKING_SYNC"] = "0"
     host_wait = "spin" if os.environ.get("EP_BLOCKING_SYNC") == "0" else "sleep"
     if world_size > 1:
@@ -445,7 +457,7 @@ def main():
     # host that owns several independent world batches would drive one GPU.  This is the headline e2e.
     # Measured (gpurun_out/s4/ksweep.txt, B200): a shard of 1024 / 4096 worlds runs 28.7 / 52.8 M body-steps/s as ONE context against
     # 26.8 / 49.7 M as two (both halves sit on the step's latency floor, so splitting doubles it); at 8192 worlds two contexts win (77 vs 67 M).
-    K = max(1, min(args.e2e_contexts if args.e2e_contexts > 0 else (2 if W > 4096 else 1), W))
+    K = e2e_contexts_for(W, args.e2e_contexts)
 
     def pipelined(fields, up=None, down=None):
         subs = []

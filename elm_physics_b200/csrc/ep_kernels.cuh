@@ -803,8 +803,11 @@ __device__ __forceinline__ void gather_contact(const Dev& d, int out, ContactRec
   }
 }
 // k_equations: one thread per contact (contactEquations), rows to the per-contact records (RowRec / QRow)
+#ifndef EP_EQ_OCC
+#define EP_EQ_OCC 3
+#endif
 template <bool Q>
-__global__ void __launch_bounds__(128, 3) k_equations(Dev d) {
+__global__ void __launch_bounds__(128, EP_EQ_OCC) k_equations(Dev d) {
   if (d.flags[FLAG_POOL_OVERFLOW]) return;       // contact_src has holes then; ep_sync reports the overflow
   const int ncont = min(d.cur.counters[CNT_CONTACTS], d.contact_cap);
   for (int out = blockIdx.x * blockDim.x + threadIdx.x; out < ncont; out += gridDim.x * blockDim.x) {

@@ -67,3 +67,18 @@ def test_two_rank_gloo_shards_equal_the_unsharded_batch(oracle):
     oracle.step(shapes, bodies, params, None, out, STEPS)
     for name in abi.BODY_INOUT:
         assert got[name] == getattr(bodies, name).tobytes(), name
+
+
+def test_bench_end_to_end_driving_policy():
+    """How bench.py drives a shard end to end (measured: profiles/r02_e2e_contexts_sweep.txt, r02_e2e_host_wait_probe.txt):
+    one context per GPU up to 4096 worlds, two above; spinning host waits only with four cores per driving thread."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert [bench.e2e_contexts_for(w) for w in (1, 1024, 4096, 4097, 8192)] == [1, 1, 1, 2, 2]
+    assert bench.e2e_contexts_for(8192, 3) == 3 and bench.e2e_contexts_for(2, 4) == 2 and bench.e2e_contexts_for(1, 2) == 1
+    assert bench.host_waits_spin(8192, 1, 1, 16)            # one GPU, two threads, 16 cores
+    assert bench.host_waits_spin(8192, 8, 8, 32)            # eight ranks x one context on 32 cores
+    assert not bench.host_waits_spin(8192, 8, 8, 16)
+    assert not bench.host_waits_spin(65536, 8, 8, 32)       # eight ranks x two contexts
