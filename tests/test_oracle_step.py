@@ -265,3 +265,59 @@ def test_dropped_stack_of_five_lands_without_toppling(oracle):
         assert float(np.hypot(b.pos[:5, 0], b.pos[:5, 1]).max()) <= 0.25, f
     assert float(np.sqrt((b.vel[:5] ** 2).sum(axis=1)).max()) < 0.05
     assert np.allclose(np.sort(b.pos[:5, 2]), [0.5, 1.5, 2.5, 3.5, 4.5], atol=0.02)
+
+
+# ---- SURVEY §9.8 edge cases on the oracle (the GPU suite compares the same kinds of scenes bit for bit) ----------------------
+def test_two_dynamic_bodies_on_the_same_static_body_are_separate_islands(oracle):
+    """Islands.elm:3-7, Solver.elm:201-206: only dynamic-dynamic pairs are united; the floor does not connect what rests on it."""
+    bodies = [("floor", P.plane(P.wood)),
+              ("a", P.move_to((-3, 0, 0.5), P.block((1, 1, 1), P.wood))),
+              ("b", P.move_to((3, 0, 0.5), P.block((1, 1, 1), P.wood)))]
+    _, contacts = run(oracle, [(P.on_earth(), P.assign_ids(bodies)[0])], 3)
+    assert contacts.n_groups == 2 and contacts.world_n_islands[0] == 2
+    assert contacts.group_island[0] != contacts.group_island[1]
+
+
+def test_touching_dynamic_bodies_share_an_island_and_a_kinematic_body_does_not_unite(oracle):
+    """Islands.elm:23-66: box on box on the floor = one island of two groups; the same two boxes side by side on a kinematic
+    platform stay two islands (kinematic-dynamic pairs make rows but never unions, Solver.elm:201-206)."""
+    stack = [("floor", P.plane(P.wood)),
+             ("lo", P.move_to((0, 0, 0.5), P.block((1, 1, 1), P.wood))),
+             ("hi", P.move_to((0, 0, 1.5), P.block((1, 1, 1), P.wood)))]
+    _, c1 = run(oracle, [(P.on_earth(), P.assign_ids(stack)[0])], 3)
+    assert c1.n_groups == 2 and c1.world_n_islands[0] == 1
+    platform = P.move_to((0, 0, 0.25), P.kinematic([(P.shape_block((8, 8, 0.5)), P.wood)]))
+    side = [("platform", platform),
+            ("a", P.move_to((-2, 0, 1.0), P.block((1, 1, 1), P.wood))),
+            ("b", P.move_to((2, 0, 1.0), P.block((1, 1, 1), P.wood)))]
+    _, c2 = run(oracle, [(P.on_earth(), P.assign_ids(side)[0])], 3)
+    assert c2.n_groups == 2 and c2.world_n_islands[0] == 2
+
+
+def test_point_masses_collide_with_shapes_but_not_with_each_other(oracle):
+    """NarrowPhase.elm:235-237 (particle-particle: nothing), PlaneParticle.elm:10-33 (a particle rests on the plane)."""
+    bodies = [("floor", P.plane(P.wood)),
+              ("p", P.point_mass((0, 0, 0.0005), 1.0, P.wood)),
+              ("q", P.point_mass((0, 0, 0.0005), 1.0, P.wood))]
+    _, contacts = run(oracle, [(P.on_earth(), P.assign_ids(bodies)[0])], 2)
+    ids = sorted((int(a), int(b)) for a, b in zip(contacts.group_id1[:contacts.n_groups], contacts.group_id2[:contacts.n_groups]))
+    assert contacts.n_groups == 2 and contacts.n_contacts == 2          # each particle against the floor, nothing between them
+    assert all(0 in pair for pair in ids)
+
+
+def test_only_the_warm_start_of_the_previous_frame_is_read(oracle):
+    """Physics.elm:528-529, 579: `simulate` reads cache.warmStart only -- a step warm-started by the previous frame's contacts
+    gives the same bodies whatever that frame reported as iterations / islands."""
+    shapes, bodies, params = pack.pack_worlds(scenes.readme_scene())
+    warm = None
+    for _ in range(40):
+        o = H.contacts_for(bodies)
+        oracle.step(shapes, bodies, params, warm, o, 1)
+        warm = o
+    b1, b2 = bodies.copy(), bodies.copy()
+    o1, o2 = H.contacts_for(b1), H.contacts_for(b2)
+    oracle.step(shapes, b1, params, warm, o1, 1)
+    warm.iterations[:] = 17
+    warm.world_n_islands[:] = 5
+    oracle.step(shapes, b2, params, warm, o2, 1)
+    H.assert_bodies_equal(b1, b2, "previous frame's iterations / islands must not matter")
