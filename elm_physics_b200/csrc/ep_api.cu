@@ -529,6 +529,7 @@ extern "C" int ep_upload_worlds(ep_ctx* ctx, const ep_bodies* B, const ep_params
     const char* sv = getenv("EP_SOLVER");
     d.quads = sv && !strcmp(sv, "quads") ? 1 : (sv && !strcmp(sv, "lanes") ? 0 : ((nb <= ctx->quads_max_bodies && d.nb_max <= ctx->quads_max_world) ? 1 : 0));
   }
+  d.sched_serial = getenv("EP_SCHED_SERIAL") && atoi(getenv("EP_SCHED_SERIAL")) != 0 ? 1 : 0;
   d.rows = nullptr; d.jrows = nullptr; d.qrows = nullptr; d.jqrows = nullptr; d.row_dl = nullptr; d.team_body = nullptr;
   if (d.quads) {
     TRY(dev_alloc(ctx, pool, &d.qrows, 3 * (size_t)d.contact_cap)); TRY(dev_alloc(ctx, pool, &d.jqrows, d.jrow_cap));

@@ -131,6 +131,7 @@ struct Dev {
   // rows of this frame (scratch of the step: the next frame reads only ContactRec.lam / t1).  Two solver families, chosen per
   // batch at ep_upload_worlds (Dev::quads): lane tiles read RowRec / JointRow, the quad solver QRow.
   int32_t quads;
+  int32_t sched_serial;       // EP_SCHED_SERIAL=1 (test / A-B aid): k_solve_cluster builds its level schedule with the one-thread walk
   RowRec* rows;               // [contact_cap]                         (lane solver)
   JointRow* jrows;            // [jrow_cap]
   QRow* qrows;                // [3 * contact_cap] rows 3c, 3c+1, 3c+2  (quad solver)
