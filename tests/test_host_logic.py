@@ -322,3 +322,54 @@ def test_contact_points_follows_contactPointsHelp():
     # (1,0,1) is (1,0,0) from the old origin; derotated by 0.3 rad about z, then put at the new origin
     import math
     assert abs(x - (0.5 + math.cos(0.3))) < 1e-12 and abs(y - (-1.0 - math.sin(0.3))) < 1e-12 and abs(z - 2.0) < 1e-12
+
+
+def test_level_schedule_parallel_formulation_equals_the_walk():
+    """The level schedule of a giant island (csrc/ep_solve_cluster.cuh): level(g) = max over the two dynamic bodies of g of
+    (1 + level of the previous group touching that body).  The kernel builds it in parallel -- unordered per-body group lists,
+    predecessor = the largest earlier group of the list, relaxation rounds in any order until nothing changes -- and that must be
+    the one-thread walk's result, in at most (levels + 1) rounds.  A model of both, on random islands."""
+    import random
+
+    def walk(groups, nb):
+        last, lv = [0] * (nb + 1), []
+        for a, b in groups:
+            l = max(last[a] if a else 0, last[b] if b else 0)
+            lv.append(l)
+            if a:
+                last[a] = l + 1
+            if b:
+                last[b] = l + 1
+        return lv
+
+    def parallel(groups, nb, rng):
+        gn = len(groups)
+        lists = [[] for _ in range(nb + 1)]
+        for g in rng.sample(range(gn), gn):                 # the fill order of the atomics is arbitrary
+            for x in groups[g]:
+                if x:
+                    lists[x].append(g)
+        pred = [[max([o for o in lists[x] if o < g], default=-1) if x else -1 for x in groups[g]] for g in range(gn)]
+        lv, rounds = [0] * gn, 0
+        while True:
+            rounds += 1
+            changed = False
+            for g in rng.sample(range(gn), gn):             # threads race: any order, stale reads allowed
+                l = max((lv[p] + 1 if p >= 0 else 0) for p in pred[g])
+                if l != lv[g]:
+                    lv[g], changed = l, True
+            if not changed:
+                return lv, rounds
+
+    rng = random.Random(7)
+    for _ in range(200):
+        nb, gn = rng.randint(1, 30), rng.randint(1, 150)
+        groups = []
+        while len(groups) < gn:
+            a, b = rng.randint(0, nb), rng.randint(0, nb)       # 0 = a non-dynamic body (the stand-in)
+            if a != b:
+                groups.append((a, b))
+        expect = walk(groups, nb)
+        got, rounds = parallel(groups, nb, rng)
+        assert got == expect
+        assert rounds <= max(expect) + 2
