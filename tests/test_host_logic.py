@@ -373,3 +373,36 @@ def test_level_schedule_parallel_formulation_equals_the_walk():
         got, rounds = parallel(groups, nb, rng)
         assert got == expect
         assert rounds <= max(expect) + 2
+
+
+def test_from_origin_and_basis_round_trips_a_rotated_frame():
+    """tests/Transform3dFromFrame3dTest.elm:43-71: a right-handed frame at (0.5, 0.6, 0.7) rotated by pi/5 around the world x axis and
+    then the world y axis -> Transform3d.fromOriginAndBasis -> the same basis back out of the quaternion, and the same placed point
+    as origin + p.x X + p.y Y + p.z Z.  All four branches of the matrix-to-quaternion conversion (Transform3d.elm:34-121) as well."""
+    import math
+
+    def rot(axis, ang, v):
+        c, s = math.cos(ang), math.sin(ang)
+        x, y, z = v
+        return (x, c * y - s * z, s * y + c * z) if axis == "x" else (c * x + s * z, y, -s * x + c * z)
+
+    def close(a, b, tol=1e-12):
+        return all(abs(p - q) < tol for p, q in zip(a, b))
+
+    def check(origin, X, Y, Z):
+        t = m3.from_origin_and_basis(origin, X, Y, Z)
+        o = m3.orientation(t)
+        assert close((o["m11"], o["m21"], o["m31"]), X) and close((o["m12"], o["m22"], o["m32"]), Y) and close((o["m13"], o["m23"], o["m33"]), Z)
+        p = (0.234, 0.234, 0.234)
+        expect = tuple(origin[k] + p[0] * X[k] + p[1] * Y[k] + p[2] * Z[k] for k in range(3))
+        assert close(m3.point_place_in(t, p), expect)
+
+    frame = [(0.5, 0.6, 0.7), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)]
+    frame = [rot("y", math.pi / 5, rot("x", math.pi / 5, v)) for v in frame]
+    check(*frame)
+    # the other three branches: half turns about x, y, z (trace = -1, largest diagonal element m00 / m11 / m22) slightly perturbed
+    for axis, ang in (("x", math.pi - 0.01), ("y", math.pi - 0.01)):
+        basis = [rot(axis, ang, v) for v in ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))]
+        check((0.1, -0.2, 0.3), *basis)
+    c, s = math.cos(math.pi - 0.01), math.sin(math.pi - 0.01)
+    check((0.0, 0.0, 0.0), (c, s, 0.0), (-s, c, 0.0), (0.0, 0.0, 1.0))
